@@ -1,0 +1,355 @@
+#!/usr/bin/env python
+"""Benchmark: log-marginal-likelihood evaluations per second.
+
+Metric (BASELINE.json): log-ML evals/sec at N=1e6, d=21, K=2048 random
+Fourier features (StandardLinearModel + RandomMatern32(2048), config 2) on
+1/2/4/8 B200, next to the reference algorithm on the host CPU.
+
+One "step" = one ``StandardLinearModel._elbo``-equivalent evaluation: value
+AND gradients wrt (var, regulariser, lengthscale) -- fused value pass, one
+allreduce (N>1), float64 solve, residual + gradient passes, second allreduce,
+host assembly.  Rows of X are sharded contiguously over the ranks (total N
+fixed => strong scaling).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+"""
+
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "log-ML evals/sec N=1e6 D=21 K=2048 RFF"
+EVAL_POINTS = [(1.0, 0.02), (4.0, 0.02), (10.0, 0.02),
+               (1.0, 1.0), (4.0, 1.0), (10.0, 1.0)]   # (lengthscale, var)
+REG = 1.0
+
+
+def synthetic(N, d, seed=0):
+    """SARCOS-shaped synthetic regression data."""
+    rs = np.random.RandomState(seed)
+    X = rs.randn(N, d).astype(np.float32)
+    w = rs.randn(d)
+    y = (np.sin(X.astype(np.float64).dot(w) / 3.0)
+         + 0.1 * rs.randn(N)).astype(np.float32)
+    return X, y
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        j = json.load(open(p))
+        return dict(tflops=float(j.get("bf16_tflops_sustained", j["bf16_tflops"])),
+                    hbm=float(j["hbm_gbs"]), src="measured")
+    return dict(tflops=1400.0, hbm=6650.0, src="fallback")
+
+
+class ClockSampler(threading.Thread):
+    """Samples nvidia-smi clocks / throttle reasons during the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.rows, self.stop_flag = index, [], False
+
+    def run(self):
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(
+                    ["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                     "--format=csv,noheader,nounits"], capture_output=True,
+                    text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([c.strip() for c in out.split(",")])
+            except Exception:
+                pass
+            time.sleep(0.2)
+
+    def summary(self):
+        if not self.rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        sm = sorted(float(r[0]) for r in self.rows if r[0].replace('.', '').isdigit())
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown",
+                 "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names)
+                   if any(len(r) > 2 + i and r[2 + i].startswith("Active")
+                          for r in self.rows)]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None,
+                "sm_max_mhz": float(self.rows[0][1]) if self.rows else None,
+                "reasons": reasons}
+
+
+# ---------------------------------------------------------------------------
+# CPU baseline (the oracle port of the reference algorithm)
+# ---------------------------------------------------------------------------
+
+def cpu_eval_seconds(N, d, K, sample_rows, reps=1):
+    """Time the row-chunked float64 restatement of ``_elbo`` (value + grads)
+    on ``sample_rows`` rows of the workload with all host BLAS threads, and
+    extrapolate to N rows: everything but the O(D^3) solve is linear in N."""
+    from oracle import oracle as orc
+    from scipy.linalg import cho_solve, cholesky
+    X, y = synthetic(sample_rows, d)
+    X, y = X.astype(np.float64), y.astype(np.float64)
+    W = np.random.RandomState(1).randn(d, K)  # values irrelevant for timing
+    ls, var = EVAL_POINTS[1]
+    blocks = [dict(kind="trig", W=W, lenscale=ls, cols=None)]
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        orc.slm_elbo_chunked(X, y, var, [REG], blocks, chunk=20000)
+    t_total = (time.perf_counter() - t0) / reps
+    D = 2 * K
+    A = np.eye(D) * 2.0 + 0.01
+    t0 = time.perf_counter()
+    L = cholesky(A, lower=False)
+    cho_solve((L, False), np.eye(D))
+    t_solve = time.perf_counter() - t0
+    t_rows = max(t_total - t_solve, 1e-9)
+    t_full = t_solve + t_rows * (N / float(sample_rows))
+    return t_total, t_solve, t_full
+
+
+def cpu_threads():
+    try:
+        from threadpoolctl import threadpool_info
+        n = [p.get("num_threads", 1) for p in threadpool_info()
+             if p.get("user_api") == "blas"]
+        return max(n) if n else os.cpu_count()
+    except Exception:
+        return os.cpu_count()
+
+
+def run_reference(args):
+    """--impl reference: the reference algorithm (oracle port; the reference
+    itself is pure Python/NumPy and is not present on the GPU box) timed on
+    the host cores for the same metric and config."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    sample = args.cpu_sample
+    times = []
+    for i in range(args.warmup + args.steps):
+        t_total, t_solve, t_full = cpu_eval_seconds(args.N, args.d, args.K, sample)
+        if i >= args.warmup:
+            times.append(t_full)
+    t = float(np.mean(times))
+    val = 1.0 / t
+    desc = ("oracle port of slm._elbo (value+grad, isotropic lengthscale), "
+            "%d of %d rows in 20000-row chunks, time linear-extrapolated in N "
+            "(solve measured once at D=%d)" % (sample, args.N, 2 * args.K))
+    line = {
+        "impl": "reference", "metric": METRIC, "value": val, "unit": "evals/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": 1e3 * t, "higher_is_better": True, "scaling": "strong",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "config2: SLM + RandomMatern32(nbases=%d), N=%d, d=%d"
+                   % (args.K, args.N, args.d)},
+        "cpu_baseline": {"value": val, "unit": "evals/s", "cores": cpu_threads(),
+                         "kind": "port", "sample": desc},
+        "e2e": {"value": val, "unit": "evals/s", "h2d_bytes_per_step": 0,
+                "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ---------------------------------------------------------------------------
+# GPU arm
+# ---------------------------------------------------------------------------
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from revrand_b200 import StandardLinearModel, _cabi, _engine
+    from revrand_b200.basis_functions import RandomMatern32
+    from revrand_b200.slm import _SLMProblem
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", rank=rank, world_size=world,
+                                device_id=torch.device("cuda", local))
+    lib = _cabi.load()
+    N, d, K = args.N, args.d, args.K
+    X, y = synthetic(N, d)
+    basis = RandomMatern32(nbases=K, Xdim=d, random_state=1)
+    prob = _SLMProblem(basis, X, y)          # shards rows over ranks
+    lo, hi = _engine.shard_rows(N, rank, world)
+    n_local = hi - lo
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+
+    def one_eval(i):
+        ls, var = EVAL_POINTS[i % len(EVAL_POINTS)]
+        return prob.evaluate(var, [REG], [ls], want_grad=True)
+
+    # ---- device-resident throughput ("value") -------------------------------
+    for i in range(args.warmup):
+        one_eval(i)
+    barrier()
+    sampler = ClockSampler(local)
+    sampler.start()
+    l0 = lib.rr_launch_count()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+          for _ in range(args.steps)]
+    barrier()
+    for i in range(args.steps):
+        flush.zero_()                       # evict L2 between timed steps
+        ev[i][0].record()
+        one_eval(i)
+        ev[i][1].record()
+    barrier()
+    launches = lib.rr_launch_count() - l0
+    ms = sum(a.elapsed_time(b) for a, b in ev)
+    sampler.stop_flag = True
+    tms = torch.tensor([ms], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(tms, op=dist.ReduceOp.MAX)
+    ms = float(tms.item())
+    ms_per_step = ms / args.steps
+    value = 1e3 / ms_per_step
+
+    # ---- roofline of the dominant kernel (fused value pass) -----------------
+    st = prob.stats
+    ls, var = EVAL_POINTS[1]
+    prob.plan.set_lenscales([ls])
+    for _ in range(2):
+        st.zero_()
+        _engine.slm_suffstats(prob.plan, prob.Xd, prob.yd, st, engine=prob.engine,
+                              want_yy=False)
+    kev = []
+    for _ in range(max(3, min(args.steps, 5))):
+        st.zero_()
+        flush.zero_()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        _engine.slm_suffstats(prob.plan, prob.Xd, prob.yd, st, engine=prob.engine,
+                              want_yy=False)
+        b.record()
+        kev.append((a, b))
+    torch.cuda.synchronize()
+    k_ms = float(np.mean([a.elapsed_time(b) for a, b in kev]))
+    D = 2 * K
+    flops = 2.0 * n_local * D * D + 2.0 * n_local * d * K   # algorithmic, per launch
+    pk = peaks()
+    achieved = flops / (k_ms * 1e-3) / 1e12
+    roofline = {"bound": "tensor", "kernel": "tc_suffstats_kernel (fused Phi^T Phi)",
+                "achieved": achieved, "peak": pk["tflops"], "unit": "TFLOP/s",
+                "frac": achieved / pk["tflops"], "traffic": None,
+                "peak_source": pk["src"] + " bf16 sustained",
+                "ms_per_launch": k_ms,
+                "algorithmic_flops_per_launch": flops}
+    tpath = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tpath):
+        try:
+            roofline["traffic"] = json.load(open(tpath)).get("tc_suffstats_bytes_per_launch")
+        except Exception:
+            pass
+
+    # ---- end to end through the public API with HOST buffers ----------------
+    Xh = torch.from_numpy(X[lo:hi]).pin_memory()
+    yh = torch.from_numpy(y[lo:hi]).pin_memory()
+    slm = StandardLinearModel(basis=basis)
+    slm.obj_ = -np.inf
+    slm._problem = prob       # reuse buffers; inputs are re-uploaded every step
+
+    def e2e_step(i):
+        ls, var = EVAL_POINTS[i % len(EVAL_POINTS)]
+        prob.Xd.copy_(Xh, non_blocking=True)
+        prob.yd.copy_(yh, non_blocking=True)
+        nelbo, grads = slm._elbo(None, None, var, REG, ls)   # D2H of results inside
+        return nelbo
+    for i in range(min(2, args.warmup)):
+        e2e_step(i)
+    barrier()
+    n_e2e = max(2, min(args.steps, 5))
+    ev2 = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+           for _ in range(n_e2e)]
+    for i in range(n_e2e):
+        ev2[i][0].record()
+        e2e_step(i)
+        ev2[i][1].record()
+    barrier()
+    ms2 = sum(a.elapsed_time(b) for a, b in ev2)
+    t2 = torch.tensor([ms2], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t2, op=dist.ReduceOp.MAX)
+    e2e_val = 1e3 / (float(t2.item()) / n_e2e)
+    h2d = int(Xh.numel() * 4 + yh.numel() * 4 + prob.plan.d * K * 4)
+    d2h = int(8 * (4 + 1 + d))
+
+    line = {
+        "metric": METRIC, "value": value, "unit": "evals/s", "n_gpus": world,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "dtype": "fp16x3-split tensor-core products, fp32 accumulate, f64 solve",
+        "data": "synthetic",
+        "config": {"workload": "config2: SLM + RandomMatern32(nbases=%d), N=%d, d=%d, "
+                               "value+grad eval, isotropic lengthscale" % (K, N, d),
+                   "rows_per_gpu": n_local, "l2": "flushed between timed steps "
+                   "(256 MiB write)", "engine": os.environ.get("REVRAND_B200_ENGINE", "auto"),
+                   "parallelism": "rows sharded x%d, 2 allreduces/eval" % world},
+        "clocks": sampler.summary(),
+        "e2e": {"value": e2e_val, "unit": "evals/s", "h2d_bytes_per_step": h2d,
+                "d2h_bytes_per_step": d2h},
+        "gpu_launches": int(launches),
+        "roofline": roofline,
+    }
+    if rank == 0 and world == 1 and not args.no_cpu:
+        t_total, t_solve, t_full = cpu_eval_seconds(N, d, K, args.cpu_sample)
+        line["cpu_baseline"] = {
+            "value": 1.0 / t_full, "unit": "evals/s", "cores": cpu_threads(),
+            "kind": "port",
+            "sample": "oracle port of slm._elbo (value+grad) on %d of %d rows: "
+                      "%.1f s measured (solve %.1f s), linear extrapolation in N"
+                      % (args.cpu_sample, N, t_total, t_solve)}
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=6)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--N", type=int, default=1000000)
+    ap.add_argument("--d", type=int, default=21)
+    ap.add_argument("--K", type=int, default=2048)
+    ap.add_argument("--cpu-sample", type=int, default=20000)
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == "ours":
+        args.warmup = 3
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        import __graft_entry__ as g
+        g.build()
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

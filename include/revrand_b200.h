@@ -1,0 +1,218 @@
+/*
+ * revrand_b200 C-ABI: the drop-in boundary for the random-feature
+ * log-marginal-likelihood hot path.
+ *
+ * The reference (NICTA/revrand @ 4c1881b) has no FFI; its boundary for this
+ * path is the Python protocol between slm.py / glm.py and
+ * basis_functions.py.  Every entry point below replaces one NumPy call site
+ * of that protocol (cited per function, paths relative to the reference
+ * checkout) and is what a binding on the reference side would load with
+ * ctypes.
+ *
+ * Conventions
+ *  - All data pointers are DEVICE pointers owned by the caller; the library
+ *    allocates nothing persistent.  Matrices are row-major.
+ *  - `stream` is a cudaStream_t passed as void* (NULL = default stream).
+ *    Calls are asynchronous with respect to the host.
+ *  - Return value: 0 on success, negative rr_status otherwise;
+ *    rr_last_error() returns a thread-local message.  No C++ exceptions
+ *    cross this boundary.
+ *  - Accumulating outputs (G, p, R, ...) are float64 and are ADDED to, so
+ *    row-sharded callers (one rank per GPU) can allreduce them directly.
+ */
+#ifndef REVRAND_B200_H
+#define REVRAND_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum rr_status {
+  RR_OK = 0,
+  RR_ERR_INVALID = -1,   /* bad argument / shape */
+  RR_ERR_WORKSPACE = -2, /* workspace too small */
+  RR_ERR_CUDA = -3,      /* CUDA runtime error (see rr_last_error) */
+  RR_ERR_UNSUPPORTED = -4
+} rr_status;
+
+/*
+ * Feature plan: a concatenation of random trigonometric blocks and "extra"
+ * affine columns, i.e. what BasisCat.transform (basis_functions.py:1599-1627)
+ * evaluates for RandomRBF/Laplace/Cauchy/Matern32/Matern52/OrthogonalRBF/
+ * FastFoodRBF blocks (basis_functions.py:838-864, 1263-1289) concatenated
+ * with LinearBasis / BiasBasis columns (:468-485, :415-432).
+ *
+ * Frequency k of the plan produces two feature columns
+ *   Phi[n, col_cos[k]] = amp[k] * cos(2*pi*u),  Phi[n, col_sin[k]] = amp[k] * sin(2*pi*u),
+ *   u = sum_i X[n,i] * Wt[i*ktot + k]            (Wt = W / lenscale / (2*pi): "turns")
+ * and extra column j is  X[n, ext_src[j]]  (ext_src[j] >= 0)  or the constant
+ * ext_val[j] (ext_src[j] < 0), written to column ext_col[j].
+ */
+typedef struct rr_plan {
+  int32_t d;            /* input dimension of X                              */
+  int32_t ktot;         /* number of random frequencies over all trig blocks */
+  int32_t next;         /* number of extra (non-trigonometric) columns       */
+  int32_t D;            /* total number of feature columns                   */
+  const float* Wt;      /* (d, ktot) projection in turns                     */
+  const float* amp;     /* (ktot) amplitude, 1/sqrt(K_block)                 */
+  const int32_t* col_cos; /* (ktot)                                          */
+  const int32_t* col_sin; /* (ktot)                                          */
+  const int32_t* ext_src; /* (next)                                          */
+  const float* ext_val;   /* (next)                                          */
+  const int32_t* ext_col; /* (next)                                          */
+} rr_plan;
+
+/* Likelihood ids for rr_glm_step; revrand/likelihoods.py:18-545. */
+typedef enum rr_likelihood {
+  RR_LIK_GAUSSIAN = 0,
+  RR_LIK_BERNOULLI = 1,
+  RR_LIK_BINOMIAL = 2,
+  RR_LIK_POISSON_EXP = 3,
+  RR_LIK_POISSON_SOFTPLUS = 4
+} rr_likelihood;
+
+/* Engine selection flags for the SLM passes. */
+#define RR_ENGINE_AUTO 0   /* fused tcgen05 path when the plan allows it */
+#define RR_ENGINE_SIMT 1   /* chunked CUDA-core path (any plan)          */
+#define RR_ENGINE_TCGEN05 2 /* fused tcgen05 path, error if unsupported  */
+
+int rr_version(void);
+const char* rr_last_error(void);
+/* Number of kernels this library has launched in the process so far. */
+uint64_t rr_launch_count(void);
+/* SM count and compute capability of the current device. */
+int rr_device_info(int32_t* sm_count, int32_t* cc_major, int32_t* cc_minor);
+
+/*
+ * Phi = transform(X): replaces np.dot/np.cos/np.sin/np.hstack at
+ * basis_functions.py:862-864 (and BasisCat.transform :1622-1627).
+ * Phi is (N, ldphi) with ldphi >= plan->D.
+ */
+int rr_features(const rr_plan* plan, const float* X, int64_t N, float* Phi,
+                int64_t ldphi, void* stream);
+
+/*
+ * dPhi = grad(X) of ONE trig block wrt its lengthscale(s): replaces
+ * basis_functions.py:888-901.  W is the raw (d,K) frequency matrix,
+ * lenscale has n_ls entries (1 or d).  Output layout is the reference's:
+ * (N, 2K) for n_ls == 1, else (N, 2K, d) with the lengthscale index fastest.
+ * compat != 0 reproduces the reference's scalar-lengthscale behaviour (only
+ * input dimension 0 contributes, :896-899); compat == 0 gives the full
+ * derivative for a shared scalar lengthscale.
+ */
+int rr_trig_grad(const float* X, int64_t N, int32_t d, const float* W,
+                 int32_t K, const float* lenscale, int32_t n_ls,
+                 int32_t compat, float* dPhi, void* stream);
+
+/*
+ * FastFood projection  VX = hstack_b( H(PI_b(H(X~ * B_b)) * G_b) * S_b * sqrt(d2) )
+ * followed by the trig map: replaces FastFoodRBF._makeVX + transform,
+ * basis_functions.py:1356-1371, 1285-1289, with mathfun/linalg.py:182-220
+ * (hadamard, ordering=False) done as an in-register butterfly.
+ * Xs is X / lenscale, (N, d) with d <= d2; B,G,S are (k, d2) float, PI (k, d2)
+ * int32.  Phi is (N, 2*k*d2): [cos | sin] / sqrt(k*d2).  If VX_out != NULL
+ * the raw projection (N, k*d2) is also written.
+ */
+int rr_fastfood_features(const float* Xs, int64_t N, int32_t d, int32_t d2,
+                         int32_t k, const float* B, const float* G,
+                         const int32_t* PI, const float* S, float* Phi,
+                         float* VX_out, void* stream);
+
+/*
+ * Value pass of StandardLinearModel._elbo: G += Phi^T Phi, p += Phi^T y,
+ * yy += y^T y over this rank's rows; replaces slm.py:145-146 and the
+ * Phi.T.dot(y) of :157.  G is (D,D) float64, p (D) float64, yy (1) float64.
+ * Phi is never written to HBM by the tcgen05 engine.
+ */
+int rr_slm_suffstats(const rr_plan* plan, const float* X, const float* y,
+                     int64_t N, double* G, double* p, double* yy,
+                     void* workspace, size_t workspace_bytes, int32_t engine,
+                     void* stream);
+
+/*
+ * Residual pass: sqerr += sum_n (y_n - phi_n^T m)^2 (slm.py:161-162);
+ * if err != NULL also writes the N residuals.
+ */
+int rr_slm_residual(const rr_plan* plan, const float* X, const float* y,
+                    int64_t N, const float* m, float* err, double* sqerr,
+                    void* stream);
+
+/*
+ * Gradient pass of StandardLinearModel._elbo wrt the basis hyper-parameters
+ * (slm.py:193-197 with basis_functions.py:888-901 and apply_grad :109-152),
+ * restated so that dPhi is never formed:
+ *   T = Err (x) m - Phi C,  Q[n,k] = -Phi_sin[n,k] T[n,col_cos k] + Phi_cos[n,k] T[n,col_sin k],
+ *   R += X^T Q     (d, ktot) float64.
+ * The caller turns R into d(-ELBO)/d lenscale_i = sum_k W[i,k] R[i,k] / (var * l_i^2).
+ * err are the residuals from rr_slm_residual; m (D) and C (D,D) float32.
+ */
+int rr_slm_gradpass(const rr_plan* plan, const float* X, const float* err,
+                    int64_t N, const float* m, const float* C, double* R,
+                    void* workspace, size_t workspace_bytes, int32_t engine,
+                    void* stream);
+
+/*
+ * Predictive moments (slm.py:239-242): Ey = Phi m, Vf = rowsum((Phi C) * Phi).
+ */
+int rr_slm_predict(const rr_plan* plan, const float* X, int64_t N,
+                   const float* m, const float* C, float* Ey, float* Vf,
+                   void* workspace, size_t workspace_bytes, void* stream);
+
+/*
+ * Data-dependent part of one GLM SVI step, all K_mix mixture components and
+ * L reparameterised draws at once: replaces GeneralizedLinearModel._reparam_k
+ * (glm.py:296-322) for k = 0..Kmix-1 and the EdPhi contraction of
+ * glm.py:274-275.
+ *   inputs : minibatch X (M,d), y (M), optional per-row likelihood argument
+ *            larg (M) (Binomial n) or NULL; variational mean/var mq, Cq
+ *            (D,Kmix) row-major; eps (Kmix,L,D) noise; lik / lik_param.
+ *   outputs: Edm (D,Kmix), EdC (D,Kmix) as glm.py:306-309 (NOT yet scaled by
+ *            B); R (d,ktot) float64 += X^T Q with T := EdPhi (mean over k);
+ *            Ell (Kmix) float64 expected log-likelihood sums (glm.py:320);
+ *            dlpar (1) float64 += sum over k of mean_l sum_n dp (glm.py:313-316).
+ */
+int rr_glm_step(const rr_plan* plan, const float* X, const float* y,
+                const float* larg, int64_t M, const float* mq, const float* Cq,
+                int32_t Kmix, const float* eps, int32_t L, int32_t lik,
+                float lik_param, float* Edm, float* EdC, double* R,
+                double* Ell, double* dlpar, void* workspace,
+                size_t workspace_bytes, void* stream);
+
+/*
+ * GLM predictive sampling (glm.py:404-418, 572-620): f = Phi(Xs) ws^T for S
+ * posterior weight draws ws (S,D); accumulates Ey (N) = mean_s Ey(f) and
+ * optionally its second moment for the variance.
+ */
+int rr_glm_predict(const rr_plan* plan, const float* X, int64_t N,
+                   const float* ws, int32_t S, int32_t lik, float lik_param,
+                   const float* larg, float* Ey, float* Ey2, void* workspace,
+                   size_t workspace_bytes, void* stream);
+
+/* Workspace query: op is one of the RR_OP_* codes. */
+#define RR_OP_SUFFSTATS 1
+#define RR_OP_GRADPASS 2
+#define RR_OP_PREDICT 3
+#define RR_OP_GLM_STEP 4
+#define RR_OP_GLM_PREDICT 5
+size_t rr_workspace_bytes(int32_t op, int64_t N, int32_t d, int32_t ktot,
+                          int32_t D, int32_t aux0, int32_t aux1,
+                          int32_t engine);
+
+/* 1 if the fused tcgen05 engine can run this plan shape, else 0. */
+int rr_tcgen05_supported(int32_t d, int32_t ktot, int32_t next, int32_t D);
+
+/*
+ * Self-test of the tcgen05 / TMEM building blocks (descriptor encodings,
+ * swizzled shared-memory layout, TMEM load mapping) against a CUDA-core
+ * reference on random data; returns 0 when bit-level layout checks pass.
+ * max_abs_err (host pointer) receives the largest deviation.
+ */
+int rr_tcgen05_selftest(double* max_abs_err);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* REVRAND_B200_H */

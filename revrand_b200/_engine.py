@@ -1,0 +1,432 @@
+"""Device engine: feature plans, buffers and launches of the C-ABI kernels.
+
+PyTorch is used for device memory, streams, the (single GPU) dense solve and
+``torch.distributed``; every data-parallel pass goes through
+``librevrand_b200.so``.  Nothing here falls back to the CPU.
+"""
+
+from __future__ import annotations
+
+import ctypes as C
+import math
+
+import numpy as np
+
+from . import _cabi
+from ._cabi import RRPlan, RevrandB200Error, check
+
+CHOLTHRESH = 1e-5   # revrand/mathfun/linalg.py:31
+SVD_FLOOR = 1e-15   # revrand/mathfun/linalg.py:128 (s_tol)
+TWO_PI = 2.0 * math.pi
+
+_torch = None
+
+
+def torch():
+    global _torch
+    if _torch is None:
+        import torch as _t
+        _torch = _t
+    return _torch
+
+
+def require_cuda():
+    t = torch()
+    if not t.cuda.is_available():
+        raise RevrandB200Error(
+            "revrand_b200 needs a CUDA device (B200, sm_100a); there is no CPU "
+            "fallback for the feature / likelihood passes")
+    return t
+
+
+def device():
+    t = require_cuda()
+    return t.device("cuda", t.cuda.current_device())
+
+
+def _stream_ptr():
+    return C.c_void_p(torch().cuda.current_stream().cuda_stream)
+
+
+def _ptr(tensor):
+    return C.c_void_p(0 if tensor is None else tensor.data_ptr())
+
+
+def to_device(a, dtype=None):
+    """numpy / tensor -> contiguous CUDA tensor (float32 unless told)."""
+    t = require_cuda()
+    dtype = dtype or t.float32
+    if isinstance(a, t.Tensor):
+        return a.to(device=device(), dtype=dtype).contiguous()
+    a = np.ascontiguousarray(a)
+    return t.from_numpy(a).to(device=device(), dtype=dtype).contiguous()
+
+
+# ---------------------------------------------------------------------------
+# Feature plan
+# ---------------------------------------------------------------------------
+
+class TrigBlock(object):
+    """One random trigonometric basis inside a concatenation.
+
+    ``W`` is the raw (d_eff, K) frequency matrix, ``cols`` the input columns it
+    applies to (``apply_ind``) or None, ``lenscale`` a float array of length
+    1 or d_eff.
+    """
+    kind = "trig"
+
+    def __init__(self, W, lenscale, cols=None):
+        self.W = np.asarray(W, dtype=np.float64)
+        self.cols = None if cols is None else np.asarray(cols, dtype=np.int64)
+        self.lenscale = np.atleast_1d(np.asarray(lenscale, dtype=np.float64))
+        self.K = self.W.shape[1]
+        self.width = 2 * self.K
+
+
+class ExtraBlock(object):
+    """Affine columns: ``src[j] >= 0`` copies X[:, src[j]], else constant."""
+    kind = "extra"
+
+    def __init__(self, src, val):
+        self.src = np.asarray(src, dtype=np.int32)
+        self.val = np.asarray(val, dtype=np.float32)
+        self.width = len(self.src)
+
+
+class FeaturePlan(object):
+    """Host description + device image of a concatenated feature map."""
+
+    def __init__(self, blocks, d):
+        t = require_cuda()
+        self.blocks = list(blocks)
+        self.d = int(d)
+        self.trig = [b for b in self.blocks if b.kind == "trig"]
+        self.ktot = int(sum(b.K for b in self.trig))
+        self.D = int(sum(b.width for b in self.blocks))
+        col_cos, col_sin, amp = [], [], []
+        ext_src, ext_val, ext_col = [], [], []
+        self.block_offsets = []
+        self.freq_offsets = []
+        off = 0
+        koff = 0
+        for b in self.blocks:
+            self.block_offsets.append(off)
+            if b.kind == "trig":
+                self.freq_offsets.append(koff)
+                col_cos.append(off + np.arange(b.K))
+                col_sin.append(off + b.K + np.arange(b.K))
+                amp.append(np.full(b.K, 1.0 / math.sqrt(b.K)))
+                koff += b.K
+            else:
+                ext_src.append(b.src)
+                ext_val.append(b.val)
+                ext_col.append(off + np.arange(b.width))
+            off += b.width
+        self.next = int(sum(len(s) for s in ext_src))
+
+        def cat(lst, dtype):
+            return (np.concatenate(lst).astype(dtype) if lst
+                    else np.zeros(0, dtype=dtype))
+        i32, f32 = t.int32, t.float32
+        self._col_cos = to_device(cat(col_cos, np.int32), i32)
+        self._col_sin = to_device(cat(col_sin, np.int32), i32)
+        self._amp = to_device(cat(amp, np.float32), f32)
+        self._ext_src = to_device(cat(ext_src, np.int32), i32)
+        self._ext_val = to_device(cat(ext_val, np.float32), f32)
+        self._ext_col = to_device(cat(ext_col, np.int32), i32)
+        # full-d raw frequency matrix (zeros outside each block's columns)
+        Wfull = np.zeros((self.d, max(self.ktot, 1)))
+        for b, ko in zip(self.trig, self.freq_offsets):
+            rows = np.arange(self.d) if b.cols is None else b.cols
+            Wfull[rows, ko:ko + b.K] = b.W
+        self.Wfull = Wfull[:, :self.ktot] if self.ktot else Wfull[:, :0]
+        self._Wfull_dev = to_device(self.Wfull, t.float64)
+        self._Wt = t.zeros((self.d, max(self.ktot, 1)), dtype=f32,
+                           device=device())
+        self.struct = RRPlan()
+        self.refresh()
+
+    def set_lenscales(self, lenscales):
+        """New lengthscale per trig block (scalar or (d_eff,) each)."""
+        assert len(lenscales) == len(self.trig)
+        for b, ls in zip(self.trig, lenscales):
+            b.lenscale = np.atleast_1d(np.asarray(ls, dtype=np.float64))
+        self.refresh()
+
+    def inv_lenscale_full(self):
+        """(d, ktot) array of 1/lenscale seen by each (input dim, frequency)."""
+        inv = np.zeros((self.d, max(self.ktot, 1)))
+        for b, ko in zip(self.trig, self.freq_offsets):
+            rows = np.arange(self.d) if b.cols is None else b.cols
+            ls = b.lenscale if len(b.lenscale) > 1 else np.full(len(rows),
+                                                                b.lenscale[0])
+            inv[rows, ko:ko + b.K] = (1.0 / ls)[:, None]
+        return inv[:, :self.ktot]
+
+    def refresh(self):
+        """Recompute Wt = W / lenscale / 2pi (float64 on host) and upload."""
+        t = torch()
+        if self.ktot:
+            Wt = self.Wfull * self.inv_lenscale_full() / TWO_PI
+            self._Wt.copy_(t.from_numpy(np.ascontiguousarray(
+                Wt.astype(np.float32))), non_blocking=False)
+        s = self.struct
+        s.d, s.ktot, s.next, s.D = self.d, self.ktot, self.next, self.D
+        s.Wt = self._Wt.data_ptr()
+        s.amp = self._amp.data_ptr()
+        s.col_cos = self._col_cos.data_ptr()
+        s.col_sin = self._col_sin.data_ptr()
+        s.ext_src = self._ext_src.data_ptr()
+        s.ext_val = self._ext_val.data_ptr()
+        s.ext_col = self._ext_col.data_ptr()
+
+    def tcgen05_ok(self):
+        return bool(_cabi.load().rr_tcgen05_supported(self.d, self.ktot,
+                                                     self.next, self.D))
+
+
+# ---------------------------------------------------------------------------
+# Workspace cache
+# ---------------------------------------------------------------------------
+
+_workspace = {}
+
+
+def workspace(nbytes):
+    t = require_cuda()
+    dev = t.cuda.current_device()
+    buf = _workspace.get(dev)
+    if buf is None or buf.numel() < nbytes:
+        buf = None
+        _workspace.pop(dev, None)
+        buf = t.empty(int(nbytes) + 1024, dtype=t.uint8, device=device())
+        _workspace[dev] = buf
+    return buf
+
+
+def _ws_bytes(op, N, plan, aux0=0, aux1=0, engine=_cabi.RR_ENGINE_AUTO):
+    return int(_cabi.load().rr_workspace_bytes(op, int(N), plan.d, plan.ktot,
+                                               plan.D, aux0, aux1, engine))
+
+
+# ---------------------------------------------------------------------------
+# Kernel wrappers
+# ---------------------------------------------------------------------------
+
+def features(plan, Xd):
+    t = require_cuda()
+    lib = _cabi.load()
+    N = Xd.shape[0]
+    Phi = t.empty((N, plan.D), dtype=t.float32, device=Xd.device)
+    check(lib.rr_features(C.byref(plan.struct), _ptr(Xd), N, _ptr(Phi), plan.D,
+                          _stream_ptr()), "rr_features")
+    return Phi
+
+
+def trig_grad(Xd, W, lenscale, compat=True):
+    """(N, 2K[, d]) gradient tensor of one trig block (reference layout)."""
+    t = require_cuda()
+    lib = _cabi.load()
+    N, d = Xd.shape
+    K = W.shape[1]
+    ls = np.atleast_1d(np.asarray(lenscale, dtype=np.float64))
+    P = len(ls)
+    Wd = to_device(W)
+    lsd = to_device(ls)
+    shape = (N, 2 * K) if P == 1 else (N, 2 * K, P)
+    out = t.empty(shape, dtype=t.float32, device=Xd.device)
+    check(lib.rr_trig_grad(_ptr(Xd), N, d, _ptr(Wd), K, _ptr(lsd), P,
+                           1 if compat else 0, _ptr(out), _stream_ptr()),
+          "rr_trig_grad")
+    return out
+
+
+def fastfood_features(Xs_d, B, G, PI, S, want_vx=False):
+    t = require_cuda()
+    lib = _cabi.load()
+    N, d = Xs_d.shape
+    k, d2 = B.shape
+    Bd, Gd, Sd = to_device(B), to_device(G), to_device(S)
+    Pd = to_device(PI, t.int32)
+    Phi = t.empty((N, 2 * k * d2), dtype=t.float32, device=Xs_d.device)
+    VX = (t.empty((N, k * d2), dtype=t.float32, device=Xs_d.device)
+          if want_vx else None)
+    check(lib.rr_fastfood_features(_ptr(Xs_d), N, d, d2, k, _ptr(Bd), _ptr(Gd),
+                                   _ptr(Pd), _ptr(Sd), _ptr(Phi), _ptr(VX),
+                                   _stream_ptr()), "rr_fastfood_features")
+    return (Phi, VX) if want_vx else Phi
+
+
+class SuffStats(object):
+    """Flat float64 buffer [G (D*D) | p (D) | yy (1)] so that a row-sharded
+    job needs exactly one allreduce."""
+
+    def __init__(self, D):
+        t = require_cuda()
+        self.D = D
+        self.flat = t.zeros(D * D + D + 1, dtype=t.float64, device=device())
+        self.G = self.flat[:D * D].view(D, D)
+        self.p = self.flat[D * D:D * D + D]
+        self.yy = self.flat[D * D + D:]
+
+    def zero_(self):
+        self.flat.zero_()
+
+
+def slm_suffstats(plan, Xd, yd, stats, engine=_cabi.RR_ENGINE_AUTO,
+                  want_yy=True):
+    lib = _cabi.load()
+    N = Xd.shape[0]
+    nb = _ws_bytes(_cabi.RR_OP_SUFFSTATS, N, plan, engine=engine)
+    ws = workspace(nb)
+    check(lib.rr_slm_suffstats(C.byref(plan.struct), _ptr(Xd), _ptr(yd), N,
+                               _ptr(stats.G), _ptr(stats.p),
+                               _ptr(stats.yy) if want_yy else C.c_void_p(0),
+                               _ptr(ws), ws.numel(), engine, _stream_ptr()),
+          "rr_slm_suffstats")
+
+
+def slm_residual(plan, Xd, yd, m32, err=None, sqerr=None):
+    t = require_cuda()
+    lib = _cabi.load()
+    N = Xd.shape[0]
+    if sqerr is None:
+        sqerr = t.zeros(1, dtype=t.float64, device=Xd.device)
+    check(lib.rr_slm_residual(C.byref(plan.struct), _ptr(Xd), _ptr(yd), N,
+                              _ptr(m32), _ptr(err), _ptr(sqerr),
+                              _stream_ptr()), "rr_slm_residual")
+    return sqerr
+
+
+def slm_gradpass(plan, Xd, err, m32, C32, R, engine=_cabi.RR_ENGINE_AUTO):
+    lib = _cabi.load()
+    N = Xd.shape[0]
+    nb = _ws_bytes(_cabi.RR_OP_GRADPASS, N, plan, engine=engine)
+    ws = workspace(nb)
+    check(lib.rr_slm_gradpass(C.byref(plan.struct), _ptr(Xd), _ptr(err), N,
+                              _ptr(m32), _ptr(C32), _ptr(R), _ptr(ws),
+                              ws.numel(), engine, _stream_ptr()),
+          "rr_slm_gradpass")
+
+
+def slm_predict(plan, Xd, m32, C32=None):
+    t = require_cuda()
+    lib = _cabi.load()
+    N = Xd.shape[0]
+    Ey = t.empty(N, dtype=t.float32, device=Xd.device)
+    Vf = t.empty(N, dtype=t.float32, device=Xd.device) if C32 is not None else None
+    nb = _ws_bytes(_cabi.RR_OP_PREDICT, N, plan)
+    ws = workspace(nb)
+    check(lib.rr_slm_predict(C.byref(plan.struct), _ptr(Xd), N, _ptr(m32),
+                             _ptr(C32), _ptr(Ey), _ptr(Vf), _ptr(ws),
+                             ws.numel(), _stream_ptr()), "rr_slm_predict")
+    return Ey, Vf
+
+
+def glm_step(plan, Xd, yd, largd, mq, Cq, eps, lik, lik_param, want_ll=True,
+             want_R=True):
+    """Data part of one SVI step; returns device tensors."""
+    t = require_cuda()
+    lib = _cabi.load()
+    M = Xd.shape[0]
+    D, Kmix = mq.shape
+    L = eps.shape[1]
+    dev = Xd.device
+    Edm = t.empty((D, Kmix), dtype=t.float32, device=dev)
+    EdC = t.empty((D, Kmix), dtype=t.float32, device=dev)
+    R = (t.zeros((plan.d, max(plan.ktot, 1)), dtype=t.float64, device=dev)
+         if want_R and plan.ktot else None)
+    Ell = t.zeros(Kmix, dtype=t.float64, device=dev) if want_ll else None
+    dlp = t.zeros(1, dtype=t.float64, device=dev)
+    nb = _ws_bytes(_cabi.RR_OP_GLM_STEP, M, plan, Kmix, L)
+    ws = workspace(nb)
+    check(lib.rr_glm_step(C.byref(plan.struct), _ptr(Xd), _ptr(yd), _ptr(largd),
+                          M, _ptr(mq), _ptr(Cq), Kmix, _ptr(eps), L, int(lik),
+                          float(lik_param), _ptr(Edm), _ptr(EdC), _ptr(R),
+                          _ptr(Ell), _ptr(dlp), _ptr(ws), ws.numel(),
+                          _stream_ptr()), "rr_glm_step")
+    return Edm, EdC, R, Ell, dlp
+
+
+def glm_predict(plan, Xd, ws_draws, lik, lik_param, largd=None, want_sq=False):
+    t = require_cuda()
+    lib = _cabi.load()
+    N = Xd.shape[0]
+    S = ws_draws.shape[0]
+    Ey = t.empty(N, dtype=t.float32, device=Xd.device)
+    Ey2 = t.empty(N, dtype=t.float32, device=Xd.device) if want_sq else None
+    nb = _ws_bytes(_cabi.RR_OP_GLM_PREDICT, N, plan, S)
+    wsb = workspace(nb)
+    check(lib.rr_glm_predict(C.byref(plan.struct), _ptr(Xd), N, _ptr(ws_draws),
+                             S, int(lik), float(lik_param), _ptr(largd),
+                             _ptr(Ey), _ptr(Ey2), _ptr(wsb), wsb.numel(),
+                             _stream_ptr()), "rr_glm_predict")
+    return Ey, Ey2
+
+
+def tcgen05_selftest():
+    require_cuda()
+    err = C.c_double(0.0)
+    rc = _cabi.load().rr_tcgen05_selftest(C.byref(err))
+    check(rc, "rr_tcgen05_selftest")
+    return err.value
+
+
+# ---------------------------------------------------------------------------
+# Posterior solve on one GPU (library dense linear algebra, float64)
+# ---------------------------------------------------------------------------
+
+def solve_posterior(G, p, var, lam):
+    """C = (diag(1/lam) + G/var)^-1, logdet(iC), m = C p / var.
+
+    Semantics of ``solve_posdef`` (revrand/mathfun/linalg.py:84-125): upper
+    Cholesky; if it fails or any diagonal of the factor is < CHOLTHRESH fall
+    back to the clamped-spectrum solve (:128-179) with logdet = sum log s.
+    ``G``, ``p`` float64 device tensors; ``lam`` float64 device vector.
+    """
+    t = torch()
+    iC = G / var
+    iC.diagonal().add_(1.0 / lam)
+    L, info = t.linalg.cholesky_ex(iC)
+    ok = int(info.item()) == 0
+    if ok:
+        dg = L.diagonal()
+        ok = bool((dg >= CHOLTHRESH).all().item())
+    if ok:
+        Cm = t.cholesky_inverse(L)
+        logdet = 2.0 * t.log(dg).sum()
+    else:
+        U, s, Vh = t.linalg.svd(iC)
+        sc = t.clamp(s, min=SVD_FLOOR)
+        Cm = (U / sc) @ Vh
+        logdet = t.log(s).sum()
+    m = (Cm @ p) / var
+    return Cm, logdet, m
+
+
+# ---------------------------------------------------------------------------
+# Row-sharded reduction (one process per GPU)
+# ---------------------------------------------------------------------------
+
+def world():
+    """(rank, world_size) of the default process group, (0, 1) if none."""
+    t = torch()
+    if t.distributed.is_available() and t.distributed.is_initialized():
+        return t.distributed.get_rank(), t.distributed.get_world_size()
+    return 0, 1
+
+
+def allreduce_sum_(flat):
+    """In-place sum over ranks of a flat tensor (NCCL on GPU, gloo on CPU)."""
+    t = torch()
+    if world()[1] > 1:
+        t.distributed.all_reduce(flat, op=t.distributed.ReduceOp.SUM)
+    return flat
+
+
+def shard_rows(N, rank, world_size):
+    """Contiguous row range [lo, hi) owned by ``rank``."""
+    base, rem = divmod(int(N), int(world_size))
+    lo = rank * base + min(rank, rem)
+    hi = lo + base + (1 if rank < rem else 0)
+    return lo, hi

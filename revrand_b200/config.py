@@ -1,0 +1,25 @@
+"""Run-time switches of revrand_b200 (module-level, read at call time)."""
+
+import os
+
+# Reproduce the reference's behaviour for a *scalar* (isotropic) lengthscale on
+# d > 1 inputs, where only input dimension 0 contributes to d Phi / d lenscale
+# (revrand/basis_functions.py:896-899).  Set to False for the mathematically
+# complete derivative.  Posterior mean / covariance / log marginal likelihood
+# are unaffected either way.
+REFERENCE_COMPAT = os.environ.get("REVRAND_B200_REFERENCE_COMPAT", "1") != "0"
+
+# Engine for the SLM passes: "auto" (fused tcgen05 when the basis allows it),
+# "simt" (chunked CUDA-core path) or "tcgen05" (error if unsupported).
+ENGINE = os.environ.get("REVRAND_B200_ENGINE", "auto")
+
+
+def engine_code():
+    from . import _cabi
+    return {"auto": _cabi.RR_ENGINE_AUTO, "simt": _cabi.RR_ENGINE_SIMT,
+            "tcgen05": _cabi.RR_ENGINE_TCGEN05}[ENGINE]
+
+# Draw the GLM reparameterisation noise on the host from the model's
+# RandomState in the reference's order (slow: K_mix*L*D normals per step)
+# instead of on the device.
+GLM_HOST_RNG = os.environ.get("REVRAND_B200_HOST_RNG", "0") == "1"

@@ -1,0 +1,106 @@
+// Shared helpers for the revrand_b200 CUDA sources (sm_100a only).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/revrand_b200.h"
+
+namespace rr {
+
+void set_error(const char* fmt, ...);
+void count_launch();
+
+#define RR_CUDA_CHECK(expr)                                                  \
+  do {                                                                       \
+    cudaError_t _e = (expr);                                                 \
+    if (_e != cudaSuccess) {                                                 \
+      rr::set_error("%s failed at %s:%d: %s", #expr, __FILE__, __LINE__,     \
+                    cudaGetErrorString(_e));                                 \
+      return RR_ERR_CUDA;                                                    \
+    }                                                                        \
+  } while (0)
+
+#define RR_LAUNCH_CHECK(name)                                                \
+  do {                                                                       \
+    rr::count_launch();                                                      \
+    cudaError_t _e = cudaGetLastError();                                     \
+    if (_e != cudaSuccess) {                                                 \
+      rr::set_error("launch of %s failed: %s", name, cudaGetErrorString(_e));\
+      return RR_ERR_CUDA;                                                    \
+    }                                                                        \
+  } while (0)
+
+#define RR_REQUIRE(cond, msg)                                                \
+  do {                                                                       \
+    if (!(cond)) {                                                           \
+      rr::set_error("invalid argument: %s (%s)", msg, #cond);                \
+      return RR_ERR_INVALID;                                                 \
+    }                                                                        \
+  } while (0)
+
+static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+// Bump allocator over the caller-provided workspace.
+struct Workspace {
+  char* base;
+  size_t size;
+  size_t off;
+  Workspace(void* p, size_t n) : base((char*)p), size(n), off(0) {}
+  template <typename T>
+  T* take(size_t count) {
+    size_t o = align_up(off, 256);
+    size_t need = o + count * sizeof(T);
+    if (need > size || base == nullptr) return nullptr;
+    off = need;
+    return (T*)(base + o);
+  }
+};
+
+int sm_count();
+
+// ---- device helpers --------------------------------------------------------
+
+// sin/cos of 2*pi*u for u in turns, with exact range reduction in fp32:
+// u - rint(u) is exact for |u| < 2^23, leaving r in [-0.5, 0.5].
+__device__ __forceinline__ void sincos_turns(float u, float* s, float* c) {
+  float r = u - rintf(u);
+  sincospif(2.0f * r, s, c);
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// ---- launchers implemented across the .cu files ----------------------------
+
+// Generic strided SGEMM on CUDA cores: C (+)= alpha * A' B', A'(m,k) =
+// A[m*sAm + k*sAk], B'(k,n) = B[k*sBk + n*sBn]; C row-major with ldc.  Output
+// either float (Cf) or float64 (Cd); accumulate != 0 adds to C.
+int sgemm(int M, int N, int K, float alpha, const float* A, int64_t sAm,
+          int64_t sAk, const float* B, int64_t sBk, int64_t sBn, float* Cf,
+          double* Cd, int64_t ldc, int accumulate, cudaStream_t st);
+
+int launch_features(const rr_plan* plan, const float* X, int64_t N, float* Phi,
+                    int64_t ldphi, cudaStream_t st);
+
+// tcgen05 engines (rr_tc_*.cu)
+int tc_suffstats_supported(const rr_plan* plan);
+size_t tc_suffstats_workspace(const rr_plan* plan, int64_t N);
+int tc_suffstats(const rr_plan* plan, const float* X, const float* y, int64_t N,
+                 double* G, double* p, void* ws, size_t ws_bytes,
+                 cudaStream_t st);
+size_t tc_gradpass_workspace(const rr_plan* plan, int64_t N);
+int tc_gradpass(const rr_plan* plan, const float* X, const float* err, int64_t N,
+                const float* m, const float* C, double* R, void* ws,
+                size_t ws_bytes, cudaStream_t st);
+
+}  // namespace rr

@@ -1,0 +1,110 @@
+// Generic strided fp32 GEMM on CUDA cores (FFMA), used by the chunked SIMT
+// engine (any feature plan) and by the GLM step.  128x128x16 block tile, 256
+// threads, 8x8 register tile per thread, fp32 accumulation, optional float64
+// read-modify-write epilogue so long row sums are carried in double.
+#include "rr_common.cuh"
+
+namespace rr {
+
+constexpr int GB_M = 128, GB_N = 128, GB_K = 16, G_THREADS = 256;
+
+template <bool OUT_DOUBLE>
+__global__ void __launch_bounds__(G_THREADS)
+sgemm_kernel(int M, int N, int K, float alpha, const float* __restrict__ A,
+             int64_t sAm, int64_t sAk, const float* __restrict__ B, int64_t sBk,
+             int64_t sBn, float* __restrict__ Cf, double* __restrict__ Cd,
+             int64_t ldc, int accumulate) {
+  __shared__ float As[GB_K][GB_M + 4];
+  __shared__ float Bs[GB_K][GB_N + 4];
+  const int tid = threadIdx.x;
+  const int m0 = blockIdx.y * GB_M, n0 = blockIdx.x * GB_N;
+  const int tx = tid & 15, ty = tid >> 4;  // 16 x 16 thread grid
+
+  float acc[8][8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[i][j] = 0.0f;
+
+  // Load mapping: pick the orientation whose fastest index is contiguous.
+  const bool a_m_fast = (sAm == 1);
+  const bool b_n_fast = (sBn == 1);
+
+  for (int k0 = 0; k0 < K; k0 += GB_K) {
+#pragma unroll
+    for (int it = 0; it < (GB_M * GB_K) / G_THREADS; ++it) {
+      int e = tid + it * G_THREADS;
+      int mm, kk;
+      if (a_m_fast) { mm = e % GB_M; kk = e / GB_M; }
+      else          { kk = e % GB_K; mm = e / GB_K; }
+      int gm = m0 + mm, gk = k0 + kk;
+      As[kk][mm] = (gm < M && gk < K) ? A[gm * sAm + gk * sAk] : 0.0f;
+    }
+#pragma unroll
+    for (int it = 0; it < (GB_N * GB_K) / G_THREADS; ++it) {
+      int e = tid + it * G_THREADS;
+      int nn, kk;
+      if (b_n_fast) { nn = e % GB_N; kk = e / GB_N; }
+      else          { kk = e % GB_K; nn = e / GB_K; }
+      int gn = n0 + nn, gk = k0 + kk;
+      Bs[kk][nn] = (gn < N && gk < K) ? B[gk * sBk + gn * sBn] : 0.0f;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int kk = 0; kk < GB_K; ++kk) {
+      float a[8], b[8];
+      // rows ty*4..+3 and 64+ty*4..+3; cols tx*4..+3 and 64+tx*4..+3
+      float4 a0 = *(const float4*)&As[kk][ty * 4];
+      float4 a1 = *(const float4*)&As[kk][64 + ty * 4];
+      float4 b0 = *(const float4*)&Bs[kk][tx * 4];
+      float4 b1 = *(const float4*)&Bs[kk][64 + tx * 4];
+      a[0] = a0.x; a[1] = a0.y; a[2] = a0.z; a[3] = a0.w;
+      a[4] = a1.x; a[5] = a1.y; a[6] = a1.z; a[7] = a1.w;
+      b[0] = b0.x; b[1] = b0.y; b[2] = b0.z; b[3] = b0.w;
+      b[4] = b1.x; b[5] = b1.y; b[6] = b1.z; b[7] = b1.w;
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    int gm = m0 + (i < 4 ? ty * 4 + i : 64 + ty * 4 + (i - 4));
+    if (gm >= M) continue;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      int gn = n0 + (j < 4 ? tx * 4 + j : 64 + tx * 4 + (j - 4));
+      if (gn >= N) continue;
+      float v = alpha * acc[i][j];
+      if (OUT_DOUBLE) {
+        double* c = Cd + (int64_t)gm * ldc + gn;
+        *c = accumulate ? (*c + (double)v) : (double)v;
+      } else {
+        float* c = Cf + (int64_t)gm * ldc + gn;
+        *c = accumulate ? (*c + v) : v;
+      }
+    }
+  }
+}
+
+int sgemm(int M, int N, int K, float alpha, const float* A, int64_t sAm,
+          int64_t sAk, const float* B, int64_t sBk, int64_t sBn, float* Cf,
+          double* Cd, int64_t ldc, int accumulate, cudaStream_t st) {
+  if (M <= 0 || N <= 0) return RR_OK;
+  dim3 grid((N + GB_N - 1) / GB_N, (M + GB_M - 1) / GB_M);
+  if (Cd)
+    sgemm_kernel<true><<<grid, G_THREADS, 0, st>>>(M, N, K, alpha, A, sAm, sAk, B,
+                                                  sBk, sBn, nullptr, Cd, ldc,
+                                                  accumulate);
+  else
+    sgemm_kernel<false><<<grid, G_THREADS, 0, st>>>(M, N, K, alpha, A, sAm, sAk,
+                                                   B, sBk, sBn, Cf, nullptr, ldc,
+                                                   accumulate);
+  RR_LAUNCH_CHECK("sgemm_kernel");
+  return RR_OK;
+}
+
+}  // namespace rr

@@ -1,0 +1,288 @@
+// Standard linear model passes: C-ABI entry points, engine dispatch and the
+// chunked SIMT engine (works for any feature plan; Phi is materialised one
+// row chunk at a time in the caller's workspace).  The fused tcgen05 engine
+// lives in rr_tc_suffstats.cu / rr_tc_gradpass.cu.
+//
+// Reference: revrand/slm.py:142-199 (_elbo), :219-244 (predict_moments).
+#include "rr_common.cuh"
+
+namespace rr {
+
+constexpr int64_t SIMT_CHUNK = 8192;  // rows of Phi held in the workspace
+
+// p[j] += sum_r Phi[r,j] * y[r]; yy += sum y^2.  Thread per column, grid.y
+// splits rows; fp32 partials per thread, float64 atomics across blocks.
+__global__ void __launch_bounds__(256)
+colsum_weighted_kernel(const float* __restrict__ Phi, int64_t ld, int rows,
+                       int D, const float* __restrict__ y,
+                       double* __restrict__ p) {
+  int j = blockIdx.x * blockDim.x + threadIdx.x;
+  int per = (rows + gridDim.y - 1) / gridDim.y;
+  int r0 = blockIdx.y * per, r1 = min(rows, r0 + per);
+  if (j >= D) return;
+  float acc = 0.0f;
+  for (int r = r0; r < r1; ++r) acc = fmaf(Phi[(int64_t)r * ld + j], y[r], acc);
+  atomicAdd(p + j, (double)acc);
+}
+
+__global__ void __launch_bounds__(256)
+sumsq_kernel(const float* __restrict__ y, int64_t n, double* __restrict__ out) {
+  double acc = 0.0;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    double v = y[i];
+    acc += v * v;
+  }
+  acc = warp_sum(acc);
+  if ((threadIdx.x & 31) == 0) atomicAdd(out, acc);
+}
+
+// One warp per row: f = phi_n . m computed from X directly (no Phi in HBM).
+// Lanes stride over frequencies; extras handled by lane 0.
+__global__ void __launch_bounds__(256)
+residual_kernel(rr_plan plan, const float* __restrict__ X,
+                const float* __restrict__ y, int64_t N,
+                const float* __restrict__ m, float* __restrict__ err,
+                double* __restrict__ sqerr) {
+  extern __shared__ float xs[];  // warps x d
+  const int warps = blockDim.x >> 5;
+  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int d = plan.d;
+  float* xr = xs + w * d;
+  double local = 0.0;
+  for (int64_t n = (int64_t)blockIdx.x * warps + w; n < N;
+       n += (int64_t)gridDim.x * warps) {
+    for (int i = lane; i < d; i += 32) xr[i] = X[n * d + i];
+    __syncwarp();
+    float f = 0.0f;
+    for (int k = lane; k < plan.ktot; k += 32) {
+      float u = 0.0f;
+      for (int i = 0; i < d; ++i)
+        u = fmaf(xr[i], __ldg(plan.Wt + (int64_t)i * plan.ktot + k), u);
+      float s, c;
+      sincos_turns(u, &s, &c);
+      float a = plan.amp[k];
+      f = fmaf(a * c, m[plan.col_cos[k]], f);
+      f = fmaf(a * s, m[plan.col_sin[k]], f);
+    }
+    for (int j = lane; j < plan.next; j += 32) {
+      int src = plan.ext_src[j];
+      float v = src >= 0 ? xr[src] : plan.ext_val[j];
+      f = fmaf(v, m[plan.ext_col[j]], f);
+    }
+    f = warp_sum(f);
+    float e = y[n] - f;
+    if (lane == 0) {
+      if (err) err[n] = e;
+      local += (double)e * (double)e;
+    }
+    __syncwarp();
+  }
+  if (lane == 0 && local != 0.0) atomicAdd(sqerr, local);
+}
+
+// T <- Err (x) m - T   restricted to what Q needs, then
+// Q[r,k] = -Phi_sin[r,k] * T[r,col_cos k] + Phi_cos[r,k] * T[r,col_sin k].
+// (amp and 1/sqrt(K) are already inside Phi.)
+__global__ void __launch_bounds__(256)
+q_kernel(rr_plan plan, const float* __restrict__ Phi, const float* __restrict__ T,
+         int64_t ld, int rows, const float* __restrict__ err,
+         const float* __restrict__ m, float* __restrict__ Q) {
+  int k = blockIdx.x * blockDim.x + threadIdx.x;
+  int r = blockIdx.y;
+  if (k >= plan.ktot || r >= rows) return;
+  int cc = plan.col_cos[k], cs = plan.col_sin[k];
+  float e = err ? err[r] : 0.0f;
+  float tc = e * m[cc] - T[(int64_t)r * ld + cc];
+  float ts = e * m[cs] - T[(int64_t)r * ld + cs];
+  float pc = Phi[(int64_t)r * ld + cc], ps = Phi[(int64_t)r * ld + cs];
+  Q[(int64_t)r * plan.ktot + k] = -ps * tc + pc * ts;
+}
+
+// Ey[r] = Phi[r,:] . m ; Vf[r] = sum_j T[r,j] * Phi[r,j].  Warp per row.
+__global__ void __launch_bounds__(256)
+rowdot_kernel(const float* __restrict__ Phi, const float* __restrict__ T,
+              int64_t ld, int rows, int D, const float* __restrict__ m,
+              float* __restrict__ Ey, float* __restrict__ Vf) {
+  int r = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  int lane = threadIdx.x & 31;
+  if (r >= rows) return;
+  float a = 0.0f, b = 0.0f;
+  for (int j = lane; j < D; j += 32) {
+    float ph = Phi[(int64_t)r * ld + j];
+    a = fmaf(ph, m[j], a);
+    if (T) b = fmaf(ph, T[(int64_t)r * ld + j], b);
+  }
+  a = warp_sum(a);
+  b = warp_sum(b);
+  if (lane == 0) {
+    if (Ey) Ey[r] = a;
+    if (Vf) Vf[r] = b;
+  }
+}
+
+static size_t simt_ws(int op, int64_t N, const rr_plan* pl) {
+  int64_t R = N < SIMT_CHUNK ? N : SIMT_CHUNK;
+  if (R < 1) R = 1;
+  size_t phi = align_up((size_t)R * pl->D * 4, 256);
+  size_t q = align_up((size_t)R * (pl->ktot > 0 ? pl->ktot : 1) * 4, 256);
+  switch (op) {
+    case RR_OP_SUFFSTATS: return phi + 256;
+    case RR_OP_GRADPASS: return 2 * phi + q + 1024;
+    case RR_OP_PREDICT: return 2 * phi + 1024;
+    default: return 0;
+  }
+}
+
+static int simt_suffstats(const rr_plan* pl, const float* X, const float* y,
+                          int64_t N, double* G, double* p, void* ws,
+                          size_t wsb, cudaStream_t st) {
+  Workspace W(ws, wsb);
+  int64_t R = N < SIMT_CHUNK ? N : SIMT_CHUNK;
+  float* Phi = W.take<float>((size_t)R * pl->D);
+  if (!Phi) { set_error("suffstats workspace too small"); return RR_ERR_WORKSPACE; }
+  const int D = pl->D;
+  for (int64_t s = 0; s < N; s += R) {
+    int rows = (int)((N - s) < R ? (N - s) : R);
+    int rc = launch_features(pl, X + s * pl->d, rows, Phi, D, st);
+    if (rc) return rc;
+    // G += Phi^T Phi : A'(m,k) = Phi[k*D + m], B'(k,n) = Phi[k*D + n]
+    rc = sgemm(D, D, rows, 1.0f, Phi, 1, D, Phi, D, 1, nullptr, G, D, 1, st);
+    if (rc) return rc;
+    if (p) {
+      dim3 grid((D + 255) / 256, 32);
+      colsum_weighted_kernel<<<grid, 256, 0, st>>>(Phi, D, rows, D, y + s, p);
+      RR_LAUNCH_CHECK("colsum_weighted_kernel");
+    }
+  }
+  return RR_OK;
+}
+
+static int simt_gradpass(const rr_plan* pl, const float* X, const float* err,
+                         int64_t N, const float* m, const float* C, double* Rout,
+                         void* ws, size_t wsb, cudaStream_t st) {
+  Workspace W(ws, wsb);
+  int64_t R = N < SIMT_CHUNK ? N : SIMT_CHUNK;
+  const int D = pl->D, d = pl->d, kt = pl->ktot;
+  float* Phi = W.take<float>((size_t)R * D);
+  float* T = W.take<float>((size_t)R * D);
+  float* Q = W.take<float>((size_t)R * kt);
+  if (!Phi || !T || !Q) { set_error("gradpass workspace too small"); return RR_ERR_WORKSPACE; }
+  for (int64_t s = 0; s < N; s += R) {
+    int rows = (int)((N - s) < R ? (N - s) : R);
+    int rc = launch_features(pl, X + s * d, rows, Phi, D, st);
+    if (rc) return rc;
+    rc = sgemm(rows, D, D, 1.0f, Phi, D, 1, C, D, 1, T, nullptr, D, 0, st);
+    if (rc) return rc;
+    dim3 grid((kt + 255) / 256, rows);
+    q_kernel<<<grid, 256, 0, st>>>(*pl, Phi, T, D, rows, err + s, m, Q);
+    RR_LAUNCH_CHECK("q_kernel");
+    // R += X^T Q : A'(i,r) = X[r*d + i], B'(r,k) = Q[r*kt + k]
+    rc = sgemm(d, kt, rows, 1.0f, X + s * d, 1, d, Q, kt, 1, nullptr, Rout, kt, 1, st);
+    if (rc) return rc;
+  }
+  return RR_OK;
+}
+
+}  // namespace rr
+
+using namespace rr;
+
+extern "C" int rr_slm_suffstats(const rr_plan* plan, const float* X,
+                                const float* y, int64_t N, double* G, double* p,
+                                double* yy, void* workspace,
+                                size_t workspace_bytes, int32_t engine,
+                                void* stream) {
+  RR_REQUIRE(plan && X && G, "null pointer");
+  RR_REQUIRE(N >= 0, "negative N");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (N == 0) return RR_OK;
+  if (yy && y) {
+    sumsq_kernel<<<sm_count() * 4, 256, 0, st>>>(y, N, yy);
+    RR_LAUNCH_CHECK("sumsq_kernel");
+  }
+  bool tc_ok = tc_suffstats_supported(plan) != 0;
+  if (engine == RR_ENGINE_TCGEN05 && !tc_ok) {
+    set_error("tcgen05 engine does not support this plan");
+    return RR_ERR_UNSUPPORTED;
+  }
+  if (engine != RR_ENGINE_SIMT && tc_ok)
+    return tc_suffstats(plan, X, y, N, G, p, workspace, workspace_bytes, st);
+  return simt_suffstats(plan, X, y, N, G, y ? p : nullptr, workspace,
+                        workspace_bytes, st);
+}
+
+extern "C" int rr_slm_residual(const rr_plan* plan, const float* X,
+                               const float* y, int64_t N, const float* m,
+                               float* err, double* sqerr, void* stream) {
+  RR_REQUIRE(plan && X && y && m && sqerr, "null pointer");
+  if (N == 0) return RR_OK;
+  int warps = 8;
+  size_t smem = (size_t)warps * plan->d * sizeof(float);
+  int64_t want = (N + warps - 1) / warps;
+  int grid = (int)(want < (int64_t)sm_count() * 8 ? want : (int64_t)sm_count() * 8);
+  residual_kernel<<<grid, warps * 32, smem, (cudaStream_t)stream>>>(
+      *plan, X, y, N, m, err, sqerr);
+  RR_LAUNCH_CHECK("residual_kernel");
+  return RR_OK;
+}
+
+extern "C" int rr_slm_gradpass(const rr_plan* plan, const float* X,
+                               const float* err, int64_t N, const float* m,
+                               const float* C, double* R, void* workspace,
+                               size_t workspace_bytes, int32_t engine,
+                               void* stream) {
+  RR_REQUIRE(plan && X && err && m && C && R, "null pointer");
+  if (N == 0 || plan->ktot == 0) return RR_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  bool tc_ok = tc_suffstats_supported(plan) != 0;
+  if (engine == RR_ENGINE_TCGEN05 && !tc_ok) {
+    set_error("tcgen05 engine does not support this plan");
+    return RR_ERR_UNSUPPORTED;
+  }
+  if (engine != RR_ENGINE_SIMT && tc_ok)
+    return tc_gradpass(plan, X, err, N, m, C, R, workspace, workspace_bytes, st);
+  return simt_gradpass(plan, X, err, N, m, C, R, workspace, workspace_bytes, st);
+}
+
+extern "C" int rr_slm_predict(const rr_plan* plan, const float* X, int64_t N,
+                              const float* m, const float* C, float* Ey,
+                              float* Vf, void* workspace, size_t workspace_bytes,
+                              void* stream) {
+  RR_REQUIRE(plan && X && m, "null pointer");
+  RR_REQUIRE(!Vf || C, "Vf requested without C");
+  if (N == 0) return RR_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  Workspace W(workspace, workspace_bytes);
+  int64_t R = N < SIMT_CHUNK ? N : SIMT_CHUNK;
+  const int D = plan->D;
+  float* Phi = W.take<float>((size_t)R * D);
+  float* T = Vf ? W.take<float>((size_t)R * D) : nullptr;
+  if (!Phi || (Vf && !T)) { set_error("predict workspace too small"); return RR_ERR_WORKSPACE; }
+  for (int64_t s = 0; s < N; s += R) {
+    int rows = (int)((N - s) < R ? (N - s) : R);
+    int rc = launch_features(plan, X + s * plan->d, rows, Phi, D, st);
+    if (rc) return rc;
+    if (Vf) {
+      rc = sgemm(rows, D, D, 1.0f, Phi, D, 1, C, D, 1, T, nullptr, D, 0, st);
+      if (rc) return rc;
+    }
+    rowdot_kernel<<<(rows + 7) / 8, 256, 0, st>>>(Phi, T, D, rows, D, m,
+                                                   Ey ? Ey + s : nullptr,
+                                                   Vf ? Vf + s : nullptr);
+    RR_LAUNCH_CHECK("rowdot_kernel");
+  }
+  return RR_OK;
+}
+
+namespace rr {
+size_t slm_workspace_bytes(int op, int64_t N, const rr_plan* pl, int engine) {
+  size_t s = simt_ws(op, N, pl);
+  if (engine != RR_ENGINE_SIMT && tc_suffstats_supported(pl)) {
+    size_t t = op == RR_OP_SUFFSTATS ? tc_suffstats_workspace(pl, N)
+             : op == RR_OP_GRADPASS ? tc_gradpass_workspace(pl, N) : 0;
+    if (op != RR_OP_PREDICT) return t > 256 ? t : 256;
+  }
+  return s;
+}
+}  // namespace rr

@@ -1,0 +1,279 @@
+"""Bayesian standard linear model on the GPU.
+
+Drop-in for revrand/slm.py:38-257: same constructor, ``fit`` / ``predict`` /
+``predict_moments`` and learned attributes.  The log marginal likelihood
+(= ELBO, slm.py:142-199) is evaluated from row-wise sufficient statistics so
+that Phi (N x D) and dPhi (N x D x d) never exist:
+
+  pass 1 (rows, fused tcgen05 kernel)  G = Phi^T Phi, p = Phi^T y, y^T y
+  [one allreduce of (G, p, yy) when rows are sharded over ranks]
+  solve  (one GPU, float64)            C = (Lambda^-1 + G/var)^-1, m, logdet
+  pass 2 (rows)                        Err, sum Err^2, R = X^T Q
+  [one allreduce of (R, sum Err^2)]
+  assemble (host, float64)             -ELBO and its gradients.
+"""
+
+from __future__ import annotations
+
+import logging
+
+import numpy as np
+from scipy.optimize import minimize
+from scipy.stats import gamma
+from sklearn.base import BaseEstimator, RegressorMixin
+from sklearn.utils import check_random_state
+from sklearn.utils.validation import check_array, check_is_fitted, check_X_y
+
+from . import _engine as eng
+from . import config
+from .basis_functions import BasisCat, LinearBasis
+from .btypes import Parameter, Positive
+from .optimize import logtrick_minimizer, structured_minimizer
+
+log = logging.getLogger(__name__)
+
+
+def _aslist(a):
+    return a if isinstance(a, list) else [a]
+
+
+class _SLMProblem(object):
+    """Device-resident data + buffers for repeated log-ML evaluations."""
+
+    def __init__(self, basis, X, y, shard=True):
+        t = eng.require_cuda()
+        self.basis = basis
+        self.N_total, self.d = X.shape
+        self.rank, self.world = eng.world() if shard else (0, 1)
+        lo, hi = eng.shard_rows(self.N_total, self.rank, self.world)
+        self.Xd = eng.to_device(X[lo:hi])
+        self.yd = eng.to_device(y[lo:hi])
+        self.Xhost_probe = np.asarray(X[:1], dtype=float)
+        hyp0 = basis.params_values()
+        self.plan = basis._plan(self.d, hyp0)
+        self.D = self.plan.D
+        self.stats = eng.SuffStats(self.D)
+        self.first = True
+        self.err = t.empty(self.Xd.shape[0], dtype=t.float32, device=self.Xd.device)
+        nfl = self.plan.d * max(self.plan.ktot, 1) + 1
+        self.rflat = t.zeros(nfl, dtype=t.float64, device=self.Xd.device)
+        self.R = self.rflat[:nfl - 1].view(self.plan.d, max(self.plan.ktot, 1))
+        self.sqerr = self.rflat[nfl - 1:]
+        self.yy = None
+        self.engine = config.engine_code()
+
+    def evaluate(self, var, regs, hypers, want_grad=True):
+        """Return dict of host scalars + device posterior for one eval."""
+        t = eng.torch()
+        plan, st = self.plan, self.stats
+        if plan.trig:
+            plan.set_lenscales([h for h in hypers])
+        st.zero_()
+        eng.slm_suffstats(plan, self.Xd, self.yd, st, engine=self.engine,
+                          want_yy=self.yy is None)
+        eng.allreduce_sum_(st.flat)
+        if self.yy is None:
+            self.yy = float(st.yy.item())
+        lam_np, slices = self.basis.regularizer_diagonal(self.Xhost_probe, *regs)
+        slices = slices if isinstance(slices, list) else [slice(0, self.D)]
+        lam = eng.to_device(lam_np, t.float64)
+        Cm, logdet, m = eng.solve_posterior(st.G, st.p, float(var), lam)
+        trgc = (st.G * Cm).sum()
+        mc = m * m + Cm.diagonal()
+        q = t.stack([mc[s].sum() for s in slices])
+        out = {"m": m, "C": Cm, "slices": slices, "lam": lam_np}
+        m32 = m.float().contiguous()
+        self.rflat.zero_()
+        eng.slm_residual(plan, self.Xd, self.yd, m32, err=self.err,
+                         sqerr=self.sqerr)
+        g = None
+        if want_grad and plan.ktot:
+            C32 = Cm.float().contiguous()
+            eng.slm_gradpass(plan, self.Xd, self.err, m32, C32, self.R,
+                             engine=self.engine)
+        eng.allreduce_sum_(self.rflat)
+        parts = [logdet.reshape(1), trgc.reshape(1), self.sqerr, q]
+        if want_grad and plan.ktot:
+            WR = plan._Wfull_dev * self.R[:, :plan.ktot]
+            g = t.stack([WR[:, ko:ko + b.K].sum(dim=1)
+                         for b, ko in zip(plan.trig, plan.freq_offsets)])
+            parts.append(g.reshape(-1))
+        host = t.cat(parts).cpu().numpy()
+        out["logdet"], out["trgc"], out["sqerr"] = host[0], host[1], host[2]
+        out["q"] = host[3:3 + len(slices)]
+        if g is not None:
+            out["g"] = host[3 + len(slices):].reshape(len(plan.trig), plan.d)
+        return out
+
+
+class StandardLinearModel(BaseEstimator, RegressorMixin):
+    """Bayesian linear regression with a learnable basis.
+
+    Parameters
+    ----------
+    basis : Basis
+        a basis object from :mod:`revrand_b200.basis_functions`.
+    var : Parameter, optional
+        observation variance initial value.
+    tol : float, optional
+        optimiser convergence tolerance.
+    maxiter : int, optional
+        maximum number of L-BFGS-B iterations.
+    nstarts : int, optional
+        number of random candidate starts evaluated before optimisation when
+        any parameter has a distribution as its initial value.
+    random_state : None, int or RandomState, optional
+        seed for the random starts.
+    """
+
+    def __init__(self, basis=LinearBasis(), var=Parameter(gamma(1.), Positive()),
+                 tol=1e-8, maxiter=1000, nstarts=100, random_state=None):
+        self.basis = basis
+        self.var = var
+        self.tol = tol
+        self.maxiter = maxiter
+        self.nstarts = nstarts
+        self.random_state = random_state
+        self.random_ = check_random_state(random_state)
+
+    # -- training ------------------------------------------------------------------
+    def fit(self, X, y):
+        """Learn the hyper-parameters by maximising the log marginal
+        likelihood with L-BFGS-B (slm.py:74-140)."""
+        X, y = check_X_y(X, y)
+        self.obj_ = -np.inf
+        self._problem = _SLMProblem(self.basis, X, y)
+        self._problem_key = None
+        params = [self.var, self.basis.regularizer, self.basis.params]
+        nmin = structured_minimizer(logtrick_minimizer(minimize))
+
+        def elbo(var, reg, hypers):
+            return self._elbo(X, y, var, reg, hypers)
+
+        res = nmin(elbo, params, method='L-BFGS-B', jac=True, tol=self.tol,
+                   options={'maxiter': self.maxiter, 'maxcor': 100},
+                   random_state=self.random_, nstarts=self.nstarts)
+        self.var_, self.regularizer_, self.hypers_ = res.x
+        self._sync_posterior()
+        log.info("Done! ELBO = {}, var = {}, reg = {}, hypers = {}, "
+                 "message = {}.".format(-res['fun'], self.var_,
+                                        self.regularizer_, self.hypers_,
+                                        res.message))
+        self._problem = None
+        return self
+
+    def _get_problem(self, X, y):
+        prob = getattr(self, "_problem", None)
+        if prob is not None:
+            return prob
+        key = (id(X), id(y), np.shape(X))
+        if getattr(self, "_problem_key", None) != key or \
+                getattr(self, "_cached_problem", None) is None:
+            self._cached_problem = _SLMProblem(self.basis, np.asarray(X, float),
+                                               np.asarray(y, float))
+            self._problem_key = key
+        return self._cached_problem
+
+    def _elbo(self, X, y, var, reg, hypers):
+        """(-ELBO, [-dvar, dreg, dhypers]) at the given hyper-parameters; same
+        contract as slm.py:142-199."""
+        prob = self._get_problem(X, y)
+        t = eng.torch()
+        if prob.world > 1:  # keep ranks in lockstep on identical parameters
+            flat = np.concatenate([np.ravel(np.asarray(v, dtype=float)) for v in
+                                   [var] + _aslist(reg) + _aslist(hypers)
+                                   if np.size(v)])
+            buf = eng.to_device(flat, t.float64)
+            t.distributed.broadcast(buf, src=0)
+            flat = buf.cpu().numpy()
+            pos = 0
+
+            def take(v):
+                nonlocal pos
+                n = int(np.size(v))
+                out = flat[pos:pos + n].reshape(np.shape(v))
+                pos += n
+                return float(out) if np.shape(v) == () else out
+            var = take(var)
+            reg = [take(r) for r in reg] if isinstance(reg, list) else take(reg)
+            hypers = ([take(h) for h in hypers] if isinstance(hypers, list)
+                      else (take(hypers) if np.size(hypers) else hypers))
+        regs = _aslist(reg)
+        hyps = [h for h in _aslist(hypers)]
+        if len(hyps) == 1 and np.size(hyps[0]) == 0:
+            hyps = []
+        r = prob.evaluate(var, regs, hyps, want_grad=True)
+        N, D = prob.N_total, prob.D
+        lam, slices = r["lam"], r["slices"]
+        lam_s = np.array([lam[s][0] for s in slices])
+        n_s = np.array([len(lam[s]) for s in slices])
+        ELBO = -0.5 * (N * np.log(2 * np.pi * var) + r["sqerr"] / var
+                       + r["trgc"] / var + (r["q"] / lam_s).sum() + r["logdet"]
+                       + np.log(lam).sum() - D)
+        if ELBO > self.obj_:
+            self._m_dev, self._C_dev = r["m"], r["C"]
+            self.obj_ = ELBO
+            if getattr(self, "_problem", None) is None:
+                self._sync_posterior()
+        if log.isEnabledFor(logging.INFO):
+            log.info("ELBO = {}, var = {}, reg = {}, hypers = {}."
+                     .format(ELBO, var, reg, hypers))
+        dvar = 0.5 * (-N + (r["sqerr"] + r["trgc"]) / var) / var
+        dregs = [-0.5 * (qs / ls ** 2 - ns / ls)
+                 for qs, ls, ns in zip(r["q"], lam_s, n_s)]
+        dL = dregs if isinstance(reg, list) else dregs[0]
+        dh = []
+        plan = prob.plan
+        for bi, b in enumerate(plan.trig):
+            rows = np.arange(plan.d) if b.cols is None else b.cols
+            gi = r["g"][bi, rows]
+            ls = b.lenscale
+            if len(ls) > 1:
+                dh.append(gi / (var * ls ** 2))
+            elif config.REFERENCE_COMPAT:
+                dh.append(float(gi[0] / (var * ls[0] ** 2)))
+            else:
+                dh.append(float(gi.sum() / (var * ls[0] ** 2)))
+        dhypers = dh if len(dh) != 1 else dh[0]
+        return -ELBO, [-dvar, dL, dhypers]
+
+    def _sync_posterior(self):
+        """Materialise the cached best posterior as numpy attributes."""
+        if getattr(self, "_m_dev", None) is not None:
+            self.weights_ = self._m_dev.cpu().numpy()
+            self.covariance_ = self._C_dev.cpu().numpy()
+
+    # -- prediction ------------------------------------------------------------------
+    def predict(self, X):
+        """Predictive mean (slm.py:201-217)."""
+        Ey, _ = self.predict_moments(X)
+        return Ey
+
+    def predict_moments(self, X):
+        """Predictive mean and variance (slm.py:219-244)."""
+        check_is_fitted(self, ['var_', 'regularizer_', 'weights_',
+                               'covariance_', 'hypers_'])
+        X = check_array(X)
+        t = eng.require_cuda()
+        hyps = [h for h in _aslist(self.hypers_)]
+        if len(hyps) == 1 and np.size(hyps[0]) == 0:
+            hyps = []
+        plan = self.basis._plan(X.shape[1], hyps)
+        m32 = eng.to_device(self.weights_)
+        C32 = eng.to_device(self.covariance_)
+        Ey, Vf = eng.slm_predict(plan, eng.to_device(X), m32, C32)
+        return (Ey.double().cpu().numpy(),
+                Vf.double().cpu().numpy() + self.var_)
+
+    def __getstate__(self):
+        state = dict(self.__dict__)
+        for k in ("_problem", "_cached_problem", "_problem_key", "_m_dev",
+                  "_C_dev"):
+            state.pop(k, None)
+        return state
+
+    def __repr__(self):
+        return "{}(basis={}, var={}, tol={}, maxiter={}, nstarts={}, " \
+            "random_state={})".format(type(self).__name__, self.basis, self.var,
+                                      self.tol, self.maxiter, self.nstarts,
+                                      self.random_state)

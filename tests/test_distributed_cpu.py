@@ -1,0 +1,54 @@
+"""CPU, world_size 2 over gloo: the row-sharded reduction used when one
+process drives each GPU.  Each rank forms the sufficient statistics of its
+own contiguous row shard (here with the oracle, standing in for the CUDA
+pass), the flat [G | p | yy] buffer is summed with ONE allreduce, and both
+ranks must end with the statistics of the full data set."""
+
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _worker(rank, world, port, ret):
+    sys.path.insert(0, ROOT)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from oracle import oracle as orc
+        from revrand_b200 import _engine
+        rs = np.random.RandomState(0)
+        N, d, K = 501, 3, 8
+        X, y = rs.randn(N, d), rs.randn(N)
+        W = np.random.RandomState(1).randn(d, K)
+        assert _engine.world() == (rank, world)
+        lo, hi = _engine.shard_rows(N, rank, world)
+        Phi = orc.trig_features(X[lo:hi], W, 1.3)
+        D = 2 * K
+        flat = torch.zeros(D * D + D + 1, dtype=torch.float64)
+        flat[:D * D] = torch.from_numpy(Phi.T.dot(Phi).ravel())
+        flat[D * D:D * D + D] = torch.from_numpy(Phi.T.dot(y[lo:hi]))
+        flat[-1] = float(y[lo:hi].dot(y[lo:hi]))
+        _engine.allreduce_sum_(flat)
+        Pf = orc.trig_features(X, W, 1.3)
+        ok = (np.allclose(flat[:D * D].numpy().reshape(D, D), Pf.T.dot(Pf))
+              and np.allclose(flat[D * D:D * D + D].numpy(), Pf.T.dot(y))
+              and np.isclose(flat[-1].item(), y.dot(y)))
+        ret[rank] = bool(ok)
+    finally:
+        dist.destroy_process_group()
+
+
+def test_row_sharded_allreduce_gloo():
+    world = 2
+    port = 29500 + (os.getpid() % 2000)
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_worker, args=(world, port, ret), nprocs=world, join=True)
+    assert dict(ret) == {0: True, 1: True}

@@ -1,0 +1,302 @@
+"""GPU: parity of the CUDA path (through the C-ABI) with the oracle and the
+committed reference outputs.
+
+Tolerances (north_star: rtol 1e-4 in fp32 on identical seeded bases):
+  * features / feature gradients: absolute 2e-6 * (1 + |theta|) on O(1) values
+  * posterior mean: normwise relative error <= 1e-4
+  * diag(C), log marginal likelihood, dvar, dreg: rtol 1e-4
+  * lengthscale gradients: normwise 1e-3 (SIMT engine, fp32) / 5e-3 (tcgen05
+    engine, single fp16 pass for the Phi C product)
+"""
+
+import numpy as np
+import pytest
+
+import revrand_b200 as rr
+from revrand_b200 import Parameter, Positive, _cabi, _engine, config
+from revrand_b200 import basis_functions as bf
+from revrand_b200 import likelihoods as lk
+from oracle import oracle as orc
+from tests.golden import cases
+from tests import helpers
+from tests.helpers import relerr
+
+pytestmark = pytest.mark.gpu
+
+
+def test_tcgen05_selftest():
+    assert _engine.tcgen05_selftest() < 1e-3
+
+
+@pytest.mark.parametrize("cls", cases.RANDOM_BASES)
+def test_transform_and_grad_vs_reference(golden, cls):
+    g = golden["bases"]
+    for (d, K, N) in cases.BASIS_SHAPES:
+        for seed in cases.BASIS_SEEDS:
+            X, ls_iso, ls_ard = cases.basis_case_inputs(d, K, N, seed)
+            for ard in (False, True):
+                ls = ls_ard if ard else ls_iso
+                b = helpers.make_basis(cls, K, d, seed, ard, ls)
+                key = cases.basis_case_key(cls, d, K, N, seed, ard)
+                Phi = b.transform(X, ls)
+                ref = g[key + "/Phi"]
+                assert Phi.shape == ref.shape
+                # heavy-tailed bases reach |theta| ~ 1e3: fp32 phase error
+                tol = 5e-5 if cls == "RandomLaplace" else 5e-6
+                assert np.max(np.abs(Phi - ref)) < tol, key
+                dPhi = b.grad(X, ls)
+                if key + "/dPhi" in g:
+                    refg = g[key + "/dPhi"]
+                    assert dPhi.shape == refg.shape
+                    scale = 1 + np.max(np.abs(refg))
+                    assert np.max(np.abs(dPhi - refg)) < 2e-5 * scale, key
+                else:
+                    probe = cases.probe_matrix(N, Phi.shape[1], seed)
+                    got = np.einsum("nj,njp->p", probe, dPhi)
+                    assert relerr(got, g[key + "/dPhi_probe"]) < 1e-4, key
+
+
+def test_transform_defaults_empty_and_apply_ind():
+    X = np.random.RandomState(0).randn(33, 5)
+    b = bf.RandomRBF(nbases=7, Xdim=2, random_state=0, apply_ind=[1, 3])
+    Phi = b.transform(X)  # lenscale=None -> initial value
+    ref = orc.trig_features(X[:, [1, 3]], b.W, b.params.value)
+    assert np.max(np.abs(Phi - ref)) < 5e-6
+    assert b.transform(X[:0]).shape == (0, 14)
+    lin = bf.LinearBasis(onescol=True, apply_ind=slice(0, 3))
+    np.testing.assert_allclose(lin.transform(X),
+                               np.hstack((np.ones((33, 1)), X[:, :3])),
+                               rtol=1e-6, atol=1e-6)
+    np.testing.assert_allclose(bf.BiasBasis(offset=2.5).transform(X),
+                               2.5 * np.ones((33, 1)))
+    cat = b + lin + bf.BiasBasis()
+    assert cat.transform(X).shape == (33, 14 + 4 + 1)
+    gs = list(cat.grad(X, 0.9))
+    assert len(gs) == 1 and gs[0].shape == (33, 19)
+    assert np.all(gs[0][:, 14:] == 0)
+
+
+def _run_slm_case(name, golden, engine):
+    g = golden["slm"]
+    case = cases.SLM_CASES[name]
+    X, y = cases.slm_case_inputs(case)
+    basis, bases, hypers, regs = helpers.build_case_basis(case)
+    old = config.ENGINE
+    config.ENGINE = engine
+    try:
+        slm = rr.StandardLinearModel(basis=basis)
+        slm.obj_ = -np.inf
+        single = len(bases) == 1
+        reg_arg = regs[0] if single else list(regs)
+        hyp_arg = hypers[0] if len(hypers) == 1 else list(hypers)
+        nelbo, (dvar, dreg, dhyp) = slm._elbo(X, y, case["var"], reg_arg, hyp_arg)
+    finally:
+        config.ENGINE = old
+    assert abs(nelbo - g[name + "/neg_elbo"]) <= 1e-4 * abs(g[name + "/neg_elbo"])
+    assert relerr(slm.weights_, g[name + "/m"]) < 1e-4
+    np.testing.assert_allclose(slm.covariance_.diagonal(), g[name + "/diagC"],
+                               rtol=1e-4)
+    np.testing.assert_allclose(dvar, g[name + "/dvar"], rtol=1e-4, atol=1e-6)
+    np.testing.assert_allclose(np.atleast_1d(dreg), g[name + "/dreg"],
+                               rtol=1e-4, atol=1e-6)
+    dl = [dhyp] if len(hypers) == 1 else list(dhyp)
+    gtol = 1e-3 if engine == "simt" else 5e-3
+    for i, gg in enumerate(dl):
+        ref = g[name + "/dhyp%d" % i]
+        assert np.shape(gg) == np.shape(ref)
+        assert relerr(gg, ref) < gtol, (name, i, gg, ref)
+    # predictive moments
+    slm.var_, slm.regularizer_, slm.hypers_ = case["var"], reg_arg, hyp_arg
+    Xs = np.random.RandomState(5000 + case["seed"]).randn(50, case["d"])
+    Ey, Vy = slm.predict_moments(Xs)
+    assert relerr(Ey, g[name + "/Ey"]) < 1e-4
+    np.testing.assert_allclose(Vy, g[name + "/Vy"], rtol=2e-4)
+
+
+@pytest.mark.parametrize("name", sorted(cases.SLM_CASES))
+def test_slm_elbo_simt_engine(golden, name):
+    _run_slm_case(name, golden, "simt")
+
+
+@pytest.mark.parametrize("name", sorted(cases.SLM_CASES))
+def test_slm_elbo_auto_engine(golden, name):
+    # fused tcgen05 path for pure trigonometric bases, SIMT otherwise
+    _run_slm_case(name, golden, "auto")
+
+
+def test_tcgen05_engine_is_selected_for_rff():
+    b = bf.RandomMatern32(nbases=2048, Xdim=21, random_state=1)
+    plan = b._plan(21, [1.0])
+    assert plan.tcgen05_ok()
+    plan2 = (b + bf.LinearBasis())._plan(21, [1.0])
+    assert not plan2.tcgen05_ok()
+
+
+LIK = dict(gaussian=lk.Gaussian, bernoulli=lk.Bernoulli, binomial=lk.Binomial,
+           poisson_exp=lambda: lk.Poisson('exp'),
+           poisson_softplus=lambda: lk.Poisson('softplus'))
+
+
+class _Injected(object):
+    def __init__(self, eps):
+        self.eps = list(eps)
+
+    def randn(self, L, D):
+        return self.eps.pop(0)
+
+
+@pytest.mark.parametrize("name", sorted(cases.GLM_CASES))
+def test_glm_step_vs_reference(golden, name):
+    g = golden["glm"]
+    spec = cases.GLM_CASES[name]
+    sh = cases.GLM_SHAPE
+    inp = cases.glm_case_inputs(name)
+    basis = helpers.make_basis("RandomRBF", sh["K"], sh["d"], 31, True,
+                               inp["ls"], reg=inp["reg"])
+    glm = rr.GeneralizedLinearModel(likelihood=LIK[name](), basis=basis,
+                                    K=sh["Kmix"], nsamples=sh["L"])
+    glm.B_, glm.D_, glm._it = inp["B"], 2 * sh["K"], -1
+    glm.random_ = _Injected(inp["eps"])
+    old = config.GLM_HOST_RNG
+    config.GLM_HOST_RNG = True
+    try:
+        lpars = spec["lpar"] if spec["lpar"] is not None else []
+        largs = (inp["n"],) if spec["largs"] == "n" else ()
+        nelbo, (dm, dC, dreg, dlp, dbp) = glm._elbo(
+            inp["m"], inp["C"], inp["reg"], lpars, inp["ls"], inp["X"],
+            inp["y"], *largs)
+    finally:
+        config.GLM_HOST_RNG = old
+    assert abs(nelbo - g[name + "/neg_elbo"]) <= 1e-4 * abs(g[name + "/neg_elbo"])
+    assert relerr(dm, g[name + "/dm"]) < 1e-4
+    assert relerr(dC, g[name + "/dC"]) < 1e-4
+    np.testing.assert_allclose(dreg, g[name + "/dreg"], rtol=1e-6)
+    assert relerr(dbp, g[name + "/dbpars"]) < 1e-3
+    if spec["lpar"] is not None:
+        np.testing.assert_allclose(dlp[0], g[name + "/dlpar"], rtol=1e-4)
+
+
+def _synthetic(N, d, seed=0):
+    rs = np.random.RandomState(seed)
+    X = rs.randn(N, d).astype(np.float32).astype(np.float64)
+    w = rs.randn(d)
+    y = np.sin(X.dot(w) / 3.0) + 0.1 * rs.randn(N)
+    return X, y
+
+
+@pytest.mark.parametrize("K,d,N", [(64, 21, 5000), (200, 21, 20000),
+                                   (512, 8, 4097), (70, 3, 129)])
+def test_fused_suffstats_vs_oracle(K, d, N):
+    """G, Phi^T y of the tcgen05 value pass against float64 on ragged sizes
+    (K not a multiple of 64, N not a multiple of 64)."""
+    X, y = _synthetic(N, d)
+    b = bf.RandomMatern32(nbases=K, Xdim=d, random_state=1)
+    ls = 2.0
+    plan = b._plan(d, [ls])
+    assert plan.tcgen05_ok()
+    Xd, yd = _engine.to_device(X), _engine.to_device(y)
+    Phi = orc.trig_features(X, b.W, ls)
+    Gref, pref = Phi.T.dot(Phi), Phi.T.dot(y)
+    for engine in (_cabi.RR_ENGINE_TCGEN05, _cabi.RR_ENGINE_SIMT):
+        st = _engine.SuffStats(plan.D)
+        _engine.slm_suffstats(plan, Xd, yd, st, engine=engine)
+        G = st.G.cpu().numpy()
+        assert np.max(np.abs(G - G.T)) <= 1e-12 * np.max(np.abs(G)) + 1e-12
+        assert relerr(G, Gref) < 2e-6, engine
+        assert relerr(st.p.cpu().numpy(), pref) < 5e-6, engine
+        assert abs(st.yy.item() - y.astype(np.float32).astype(float).dot(
+            y.astype(np.float32).astype(float))) < 1e-6 * y.dot(y)
+
+
+def test_full_size_properties_config2():
+    """BASELINE config 2 shape (N=1e6, d=21, K=2048): size-independent
+    properties of the fused value pass.
+      * trace identity: sum_k (G[cos k, cos k] + G[sin k, sin k]) = N
+        (cos^2 + sin^2 = 1, amplitude 1/sqrt(K))
+      * row additivity: stats(rows A) + stats(rows B) = stats(all rows)
+      * symmetry.
+    """
+    import torch
+    N, d, K = 1000000, 21, 2048
+    rs = np.random.RandomState(0)
+    X = rs.randn(N, d).astype(np.float32)
+    y = np.sin(X[:, 0]).astype(np.float32)
+    b = bf.RandomMatern32(nbases=K, Xdim=d, random_state=1)
+    plan = b._plan(d, [4.0])
+    Xd, yd = _engine.to_device(X), _engine.to_device(y)
+    full = _engine.SuffStats(plan.D)
+    _engine.slm_suffstats(plan, Xd, yd, full)
+    tr = full.G.diagonal().sum().item()
+    assert abs(tr - N) < 1e-5 * N
+    assert torch.equal(full.G, full.G.T)
+    part = _engine.SuffStats(plan.D)
+    cut = 333337
+    _engine.slm_suffstats(plan, Xd[:cut], yd[:cut], part)
+    _engine.slm_suffstats(plan, Xd[cut:], yd[cut:], part, want_yy=True)
+    num = (part.G - full.G).norm().item()
+    assert num < 2e-6 * full.G.norm().item()
+    assert (part.p - full.p).norm().item() < 1e-5 * full.p.norm().item()
+    # spot-check one 64x64 block of G against float64 on a row subsample sum
+    idx = np.arange(0, N, 997)
+    Phi = orc.trig_features(X[idx].astype(float), b.W, 4.0)[:, :64]
+    sub = _engine.SuffStats(plan.D)
+    _engine.slm_suffstats(plan, _engine.to_device(X[idx]), None, sub)
+    assert relerr(sub.G[:64, :64].cpu().numpy(), Phi.T.dot(Phi)) < 2e-6
+
+
+def test_gradient_matches_finite_differences_of_value():
+    """ARD lengthscale gradient of the fused engine vs central differences of
+    its own value (float64 oracle supplies the step-size-safe reference)."""
+    X, y = _synthetic(6000, 4, seed=3)
+    ls = np.array([1.0, 1.5, 2.0, 0.8])
+    b = bf.RandomRBF(nbases=128, Xdim=4, random_state=2,
+                     lenscale=Parameter(ls, Positive()))
+    slm = rr.StandardLinearModel(basis=b)
+    slm.obj_ = -np.inf
+    f0, (dv, dr, dl) = slm._elbo(X, y, 0.05, 1.0, ls)
+    blocks = [dict(kind="trig", W=b.W, lenscale=ls, cols=None)]
+    ref = orc.slm_elbo(X, y, 0.05, [1.0], blocks)
+    assert relerr(dl, ref["dhyp"][0]) < 5e-3
+    assert abs(dv - ref["dvar"]) < 1e-4 * abs(ref["dvar"])
+
+
+def test_slm_fit_config1_end_to_end():
+    """BASELINE config 1: SLM + RandomRBF(256) on a 1-D sine, N=1000."""
+    rs = np.random.RandomState(0)
+    X = np.sort(rs.uniform(-5, 5, size=(1000, 1)), axis=0)
+    y = np.sin(X[:, 0]) + 0.1 * rs.randn(1000)
+    Xs = np.linspace(-4.5, 4.5, 200)[:, None]
+    slm = rr.StandardLinearModel(
+        basis=bf.RandomRBF(nbases=256, Xdim=1, random_state=1), nstarts=20,
+        maxiter=200, random_state=2)
+    slm.fit(X, y)
+    Ey, Vy = slm.predict_moments(Xs)
+    assert rr.metrics.smse(np.sin(Xs[:, 0]), Ey) < 0.01
+    assert np.all(Vy > 0) and 0.003 < slm.var_ < 0.03
+    # the learned posterior agrees with the float64 oracle at the learned point
+    blocks = [dict(kind="trig", W=slm.basis.W, lenscale=slm.hypers_, cols=None)]
+    o = orc.slm_elbo(X, y, slm.var_, [slm.regularizer_], blocks)
+    oEy, oVy = orc.slm_predict_moments(Xs, blocks, o["m"], o["C"], slm.var_)
+    assert relerr(Ey, oEy) < 2e-3
+    assert abs(-o["neg_elbo"] - slm.obj_) < 1e-3 * abs(slm.obj_) + 1e-2
+
+
+def test_glm_fit_poisson_small():
+    rs = np.random.RandomState(1)
+    N = 4000
+    X = rs.uniform(-3, 3, size=(N, 1))
+    rate = np.exp(np.sin(X[:, 0]))
+    y = rs.poisson(rate).astype(float)
+    glm = rr.GeneralizedLinearModel(
+        likelihood=lk.Poisson('exp'),
+        basis=bf.RandomRBF(nbases=50, Xdim=1, random_state=0,
+                           lenscale=Parameter(1.0, Positive())),
+        K=3, maxiter=600, batch_size=500, nsamples=20, nstarts=20,
+        random_state=3)
+    glm.fit(X, y)
+    Xs = np.linspace(-2.5, 2.5, 50)[:, None]
+    Ey, Vy = glm.predict_moments(Xs)
+    assert rr.metrics.smse(np.exp(np.sin(Xs[:, 0])), Ey) < 0.15
+    assert np.all(Vy >= 0)
+    p, _, _ = glm.predict_cdf(Xs, 2.0)
+    assert np.all((p >= 0) & (p <= 1))
