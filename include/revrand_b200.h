@@ -212,6 +212,18 @@ int rr_tcgen05_supported(int32_t d, int32_t ktot, int32_t next, int32_t D);
  */
 int rr_tcgen05_selftest(double* max_abs_err);
 
+/*
+ * Diagnostic: repeat D += A B^T over one 128 x 256 x 64 fp16 tile `reps`
+ * times in TMEM and return the fp32 accumulator (HOST pointers; A* are
+ * (128,64), B* (256,64) fp16 bit patterns, D and Aux (128,256) float).
+ * mode 0: hi*hi only; 1: hi*hi + lo*hi + hi*lo into one accumulator;
+ * 2: the two cross terms into a second accumulator (Aux).  Used to calibrate
+ * how many rows may be accumulated before a flush to float64.
+ */
+int rr_tcgen05_accum_probe(const uint16_t* Ahi, const uint16_t* Alo,
+                           const uint16_t* Bhi, const uint16_t* Blo,
+                           int32_t reps, int32_t mode, float* D, float* Aux);
+
 #ifdef __cplusplus
 }
 #endif

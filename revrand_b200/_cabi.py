@@ -60,6 +60,7 @@ SIGNATURES = {
     "rr_workspace_bytes": (_SZ, [_I32, _I64, _I32, _I32, _I32, _I32, _I32, _I32]),
     "rr_tcgen05_supported": (C.c_int, [_I32, _I32, _I32, _I32]),
     "rr_tcgen05_selftest": (C.c_int, [C.POINTER(C.c_double)]),
+    "rr_tcgen05_accum_probe": (C.c_int, [_P, _P, _P, _P, _I32, _I32, _P, _P]),
 }
 
 _lib = None
