@@ -2,6 +2,8 @@
 // engine (any feature plan) and by the GLM step.  128x128x16 block tile, 256
 // threads, 8x8 register tile per thread, fp32 accumulation, optional float64
 // read-modify-write epilogue so long row sums are carried in double.
+#include <type_traits>
+
 #include "rr_common.cuh"
 
 namespace rr {
@@ -20,11 +22,15 @@ sgemm_kernel(int M, int N, int K, float alpha, const float* __restrict__ A,
   const int m0 = blockIdx.y * GB_M, n0 = blockIdx.x * GB_N;
   const int tx = tid & 15, ty = tid >> 4;  // 16 x 16 thread grid
 
-  float acc[8][8];
+  // float64 outputs carry float64 accumulators (exact products of the fp32
+  // inputs): posterior solves amplify Gram errors by the conditioning of the
+  // problem, so fp32 accumulation is not enough for parity with the reference.
+  using acc_t = typename std::conditional<OUT_DOUBLE, double, float>::type;
+  acc_t acc[8][8];
 #pragma unroll
   for (int i = 0; i < 8; ++i)
 #pragma unroll
-    for (int j = 0; j < 8; ++j) acc[i][j] = 0.0f;
+    for (int j = 0; j < 8; ++j) acc[i][j] = (acc_t)0;
 
   // Load mapping: pick the orientation whose fastest index is contiguous.
   const bool a_m_fast = (sAm == 1);
@@ -65,7 +71,10 @@ sgemm_kernel(int M, int N, int K, float alpha, const float* __restrict__ A,
 #pragma unroll
       for (int i = 0; i < 8; ++i)
 #pragma unroll
-        for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+        for (int j = 0; j < 8; ++j) {
+          if (OUT_DOUBLE) acc[i][j] = fma((double)a[i], (double)b[j], (double)acc[i][j]);
+          else acc[i][j] = fmaf(a[i], b[j], (float)acc[i][j]);
+        }
     }
     __syncthreads();
   }
@@ -78,11 +87,12 @@ sgemm_kernel(int M, int N, int K, float alpha, const float* __restrict__ A,
     for (int j = 0; j < 8; ++j) {
       int gn = n0 + (j < 4 ? tx * 4 + j : 64 + tx * 4 + (j - 4));
       if (gn >= N) continue;
-      float v = alpha * acc[i][j];
       if (OUT_DOUBLE) {
+        const double v = (double)alpha * (double)acc[i][j];
         double* c = Cd + (int64_t)gm * ldc + gn;
-        *c = accumulate ? (*c + (double)v) : (double)v;
+        *c = accumulate ? (*c + v) : v;
       } else {
+        const float v = alpha * (float)acc[i][j];
         float* c = Cf + (int64_t)gm * ldc + gn;
         *c = accumulate ? (*c + v) : v;
       }

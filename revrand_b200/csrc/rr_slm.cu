@@ -9,6 +9,18 @@
 namespace rr {
 
 constexpr int64_t SIMT_CHUNK = 8192;  // rows of Phi held in the workspace
+// RR_ENGINE_AUTO runs the fused tcgen05 engine from this many rows on; below it
+// the job is launch-latency sized and the chunked SIMT engine (fp32 features,
+// float64 Gram accumulation) is both fast enough and the most accurate.
+constexpr int64_t TC_AUTO_MIN_ROWS = 8192;
+
+// 1 = tcgen05, 0 = SIMT, -1 = tcgen05 demanded but unsupported.
+static int pick_engine(int engine, const rr_plan* plan, int64_t N) {
+  const bool tc_ok = tc_suffstats_supported(plan) != 0;
+  if (engine == RR_ENGINE_TCGEN05) return tc_ok ? 1 : -1;
+  if (engine == RR_ENGINE_SIMT) return 0;
+  return (tc_ok && N >= TC_AUTO_MIN_ROWS) ? 1 : 0;
+}
 
 // p[j] += sum_r Phi[r,j] * y[r]; yy += sum y^2.  Thread per column, grid.y
 // splits rows; fp32 partials per thread, float64 atomics across blocks.
@@ -201,12 +213,12 @@ extern "C" int rr_slm_suffstats(const rr_plan* plan, const float* X,
     sumsq_kernel<<<sm_count() * 4, 256, 0, st>>>(y, N, yy);
     RR_LAUNCH_CHECK("sumsq_kernel");
   }
-  bool tc_ok = tc_suffstats_supported(plan) != 0;
-  if (engine == RR_ENGINE_TCGEN05 && !tc_ok) {
+  const int use_tc = pick_engine(engine, plan, N);
+  if (use_tc < 0) {
     set_error("tcgen05 engine does not support this plan");
     return RR_ERR_UNSUPPORTED;
   }
-  if (engine != RR_ENGINE_SIMT && tc_ok)
+  if (use_tc)
     return tc_suffstats(plan, X, y, N, G, p, workspace, workspace_bytes, st);
   return simt_suffstats(plan, X, y, N, G, y ? p : nullptr, workspace,
                         workspace_bytes, st);
@@ -235,12 +247,12 @@ extern "C" int rr_slm_gradpass(const rr_plan* plan, const float* X,
   RR_REQUIRE(plan && X && err && m && C && R, "null pointer");
   if (N == 0 || plan->ktot == 0) return RR_OK;
   cudaStream_t st = (cudaStream_t)stream;
-  bool tc_ok = tc_suffstats_supported(plan) != 0;
-  if (engine == RR_ENGINE_TCGEN05 && !tc_ok) {
+  const int use_tc = pick_engine(engine, plan, N);
+  if (use_tc < 0) {
     set_error("tcgen05 engine does not support this plan");
     return RR_ERR_UNSUPPORTED;
   }
-  if (engine != RR_ENGINE_SIMT && tc_ok)
+  if (use_tc)
     return tc_gradpass(plan, X, err, N, m, C, R, workspace, workspace_bytes, st);
   return simt_gradpass(plan, X, err, N, m, C, R, workspace, workspace_bytes, st);
 }
@@ -278,10 +290,10 @@ extern "C" int rr_slm_predict(const rr_plan* plan, const float* X, int64_t N,
 namespace rr {
 size_t slm_workspace_bytes(int op, int64_t N, const rr_plan* pl, int engine) {
   size_t s = simt_ws(op, N, pl);
-  if (engine != RR_ENGINE_SIMT && tc_suffstats_supported(pl)) {
+  if (op != RR_OP_PREDICT && pick_engine(engine, pl, N) == 1) {
     size_t t = op == RR_OP_SUFFSTATS ? tc_suffstats_workspace(pl, N)
-             : op == RR_OP_GRADPASS ? tc_gradpass_workspace(pl, N) : 0;
-    if (op != RR_OP_PREDICT) return t > 256 ? t : 256;
+                                     : tc_gradpass_workspace(pl, N);
+    return t > 256 ? t : 256;
   }
   return s;
 }

@@ -1,0 +1,563 @@
+// Fused value pass of the SLM log marginal likelihood on tcgen05, CTA-pair
+// edition:  G += Phi^T Phi,  p += Phi^T y,  Phi = amp * [cos | sin](2 pi X Wt).
+// Phi never exists in HBM.
+//
+// One cluster of two CTAs (cta_group::2) owns a 256 x 224 tile of G in the
+// "internal" feature order and streams row slabs of X through two chained
+// tensor-core products:
+//
+//   MMA#1 (kind::tf32, 3-way split => fp32-grade):  U = Wt_tile^T X_slab^T
+//         256 frequencies (128 per CTA) x 64 rows, accumulators in TMEM.
+//   generator warps: tcgen05.ld U, exact range reduction in turns, sin/cos,
+//         and split every trigonometric value c into
+//             h1 = c rounded to the 2^-6 grid   (7-bit fixed point)
+//             r  = fp16(c - h1)                  (|r| <= 2^-7)
+//             cf = fp16(c)
+//         written straight into 128B-swizzled K-major fp16 operand tiles.
+//   MMA#2 (kind::f16):   MAIN += H1_a H1_b^T                      (exact)
+//                        AUX  += R_a CF_b^T + H1_a R_b^T          (tiny)
+//
+// Why this split: the tensor core adds fp16 products into its fp32 accumulator
+// with truncation (measured with rr_tcgen05_accum_probe: aligned to the
+// accumulator exponent with two guard bits, then rounded toward zero), which
+// biases long all-positive sums such as the diagonal of G by ~1e-5 after a few
+// thousand rows.  Products of 2^-6-grid values are multiples of 2^-12 and their
+// running sum stays below 2^12 for 4096 rows, so every partial sum of MAIN is
+// exactly representable and nothing is ever truncated; AUX only holds terms
+// <= 2^-7 whose truncation is far below fp32 resolution of the result.  Every
+// 4096 rows the two accumulators are drained, combined in float64 and added to
+// a float64 scratch image of G.
+//
+// The tile set covers every unordered feature pair exactly once (rows = 128
+// frequencies of block ib, columns = 112 frequencies of block jb, kept when
+// theta_row < theta_col or equal with type_row <= type_col); a finalize kernel
+// mirrors the scratch image into the caller's G.
+//
+// Replaces: revrand/slm.py:145-146, :157 and basis_functions.py:859-864.
+#include "rr_common.cuh"
+#include "rr_tc.cuh"
+
+namespace rr {
+
+using namespace tc;
+
+constexpr int T2_SLAB = 64;          // rows of X per pipeline step
+constexpr int T2_NA = 64;            // row-block frequencies per CTA
+constexpr int T2_NB = 56;            // column-block frequencies per CTA
+constexpr int T2_IB = 2 * T2_NA;     // frequencies per row block (pair)
+constexpr int T2_JB = 2 * T2_NB;     // frequencies per column block (pair)
+constexpr int T2_NCOL = 4 * T2_NB;   // 224 accumulator columns
+constexpr int T2_XSTAGES = 3;
+constexpr int T2_PSTAGES = 2;
+constexpr int T2_CHAIN = 4096;       // rows per exact accumulation chain
+constexpr int T2_SUPER = 32768;      // rows per work item (8 chains)
+constexpr float T2_GRID_MAGIC = 196608.0f;  // 1.5 * 2^17: (c + M) - M rounds to 2^-6
+constexpr float T2_RINT_MAGIC = 12582912.0f;  // 1.5 * 2^23
+constexpr float T2_TWO_PI = 6.283185307179586f;
+
+constexpr int T2_A_BYTES = 128 * 128;            // one fp16 image of the A tile
+constexpr int T2_B_BYTES = 2 * T2_NB * 128;      // one fp16 image of the B half tile
+constexpr int T2_OFF_AH = 0;
+constexpr int T2_OFF_AR = T2_A_BYTES;
+constexpr int T2_OFF_BH = 2 * T2_A_BYTES;
+constexpr int T2_OFF_BR = T2_OFF_BH + T2_B_BYTES;
+constexpr int T2_OFF_BC = T2_OFF_BR + T2_B_BYTES;
+constexpr int T2_PHI_BYTES = T2_OFF_BC + T2_B_BYTES;   // 75776
+constexpr int T2_W_BYTES = 128 * 128;            // one tf32 image of the W tile
+constexpr int T2_X_BYTES = 32 * 128;             // one tf32 image of the X half slab
+constexpr int T2_SMEM_PHI = 0;
+constexpr int T2_SMEM_W = T2_PSTAGES * T2_PHI_BYTES;
+constexpr int T2_SMEM_X = T2_SMEM_W + 2 * T2_W_BYTES;
+constexpr int T2_SMEM_BYTES = T2_SMEM_X + T2_XSTAGES * 2 * T2_X_BYTES;
+
+constexpr int T2_TMEM_MAIN = 0;
+constexpr int T2_TMEM_AUX = T2_NCOL;
+constexpr int T2_TMEM_U = 2 * T2_NCOL;           // 448 .. 511
+
+constexpr int T2_EPI_WARPS = 4;                  // warps 0..3
+constexpr int T2_GEN_WARPS = 8;                  // warps 4..11
+constexpr int T2_WARP_MMA = 12;
+constexpr int T2_WARP_LOAD = 13;
+constexpr int T2_THREADS = 14 * 32;
+
+static_assert(T2_PHI_BYTES % 1024 == 0, "operand tiles must stay 1024-byte aligned");
+static_assert(T2_TMEM_U + 64 == 512, "TMEM budget");
+
+struct T2Bars {
+  uint64_t x_full[T2_XSTAGES];    // leader waits; count 2 (one loader per CTA)
+  uint64_t x_empty[T2_XSTAGES];   // multicast commit
+  uint64_t w_full;                // leader waits; count 8 (4 writer warps per CTA)
+  uint64_t u_full;                // multicast commit
+  uint64_t u_empty;               // leader waits; count 16 (generator warps)
+  uint64_t phi_full[T2_PSTAGES];  // leader waits; count 16
+  uint64_t phi_empty[T2_PSTAGES]; // multicast commit
+  uint64_t acc_full;              // multicast commit
+  uint64_t acc_empty;             // leader waits; count 8 (epilogue warps)
+  uint32_t tmem_base;
+  // epilogue column tables for the current item
+  int ecol[T2_NCOL];
+  int etheta[T2_NCOL];
+  float eamp[T2_NCOL];
+};
+
+__host__ __device__ __forceinline__ int t2_jmin(int ib) {
+  int v = T2_IB * ib - (T2_JB - 1);
+  return v <= 0 ? 0 : (v + T2_JB - 1) / T2_JB;
+}
+
+struct T2Item {
+  int ib, jb;
+  int64_t r0, r1;
+  bool designated;
+};
+
+__device__ __forceinline__ T2Item t2_decode(int item, int ntiles, int NIB, int NJB,
+                                            int64_t N, int64_t rpi) {
+  T2Item it;
+  int t = item % ntiles;
+  const int sc = item / ntiles;
+  int ib = 0;
+  for (; ib < NIB; ++ib) {
+    const int cnt = NJB - t2_jmin(ib);
+    if (t < cnt) break;
+    t -= cnt;
+  }
+  it.ib = ib;
+  it.jb = t2_jmin(ib) + t;
+  it.designated = (t == 0);
+  it.r0 = (int64_t)sc * rpi;
+  it.r1 = it.r0 + rpi < N ? it.r0 + rpi : N;
+  return it;
+}
+
+// arrive on the leader CTA's copy of a barrier (local or remote)
+__device__ __forceinline__ void t2_arrive_leader(uint64_t* bar, uint32_t my_rank) {
+  const uint32_t a = smem_u32(bar);
+  mbar_arrive_cluster(mapa_u32(a, 0));
+  (void)my_rank;
+}
+
+__global__ void __launch_bounds__(T2_THREADS, 1)
+tc2_suffstats_kernel(rr_plan plan, const float* __restrict__ X,
+                     const float* __restrict__ y, int64_t N, double* __restrict__ T,
+                     double* __restrict__ p, int NIB, int NJB, int ntiles,
+                     int nitems, int64_t rpi) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>(
+      (reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  __shared__ T2Bars sb;
+
+  const int tid = threadIdx.x;
+  const int warp = tid >> 5, lane = tid & 31;
+  const uint32_t crank = cluster_ctarank();
+  const int pair = blockIdx.x >> 1, npairs = gridDim.x >> 1;
+  const int d = plan.d, ktot = plan.ktot, D = plan.D;
+  const int nk1 = (d + 7) >> 3;   // tf32 k-steps of the projection
+
+  // ---- one-time setup ----------------------------------------------------------
+  for (int i = tid; i < T2_SMEM_BYTES / 16; i += T2_THREADS)
+    reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
+  if (tid == 0) {
+    for (int s = 0; s < T2_XSTAGES; ++s) {
+      mbar_init(&sb.x_full[s], 2);
+      mbar_init(&sb.x_empty[s], 1);
+    }
+    mbar_init(&sb.w_full, 8);
+    mbar_init(&sb.u_full, 1);
+    mbar_init(&sb.u_empty, 2 * T2_GEN_WARPS);
+    for (int s = 0; s < T2_PSTAGES; ++s) {
+      mbar_init(&sb.phi_full[s], 2 * T2_GEN_WARPS);
+      mbar_init(&sb.phi_empty[s], 1);
+    }
+    mbar_init(&sb.acc_full, 1);
+    mbar_init(&sb.acc_empty, 2 * T2_EPI_WARPS);
+    mbar_fence_init();
+  }
+  if (warp == T2_WARP_MMA) tmem_alloc_2cta(&sb.tmem_base, 512);
+  fence_proxy_async_smem();
+  tc_fence_before_sync();
+  __syncthreads();
+  cluster_sync_all();
+  tc_fence_after_sync();
+  const uint32_t tmem = sb.tmem_base;
+
+  if (warp == T2_WARP_MMA) {
+    // ============================ MMA issuer (leader CTA) =========================
+    if (crank == 0) {
+      const uint32_t idesc1 = make_idesc(2, 256, T2_SLAB);     // tf32, N = 64 rows
+      const uint32_t idesc2 = make_idesc(0, 256, T2_NCOL);     // f16, N = 224
+      const uint32_t w_hi = smem_u32(smem + T2_SMEM_W), w_lo = w_hi + T2_W_BYTES;
+      uint32_t gs = 0, gc = 0, itc = 0;
+
+      auto issue_mma1 = [&](uint32_t g) {
+        const uint32_t xs = g % T2_XSTAGES;
+        mbar_wait_cl(&sb.x_full[xs], (g / T2_XSTAGES) & 1);
+        mbar_wait_cl(&sb.u_empty, (g & 1) ^ 1);
+        tc_fence_after_sync();
+        if (lane == 0) {
+          const uint32_t x_hi = smem_u32(smem + T2_SMEM_X + xs * 2 * T2_X_BYTES);
+          const uint32_t x_lo = x_hi + T2_X_BYTES;
+          const uint64_t dwh = make_desc_sw128(w_hi), dwl = make_desc_sw128(w_lo);
+          const uint64_t dxh = make_desc_sw128(x_hi), dxl = make_desc_sw128(x_lo);
+          for (int k = 0; k < nk1; ++k) {
+            const uint64_t adv = (uint64_t)(2 * k);
+            umma2_tf32_ss(tmem + T2_TMEM_U, dwh + adv, dxh + adv, idesc1, k != 0);
+            umma2_tf32_ss(tmem + T2_TMEM_U, dwl + adv, dxh + adv, idesc1, 1);
+            umma2_tf32_ss(tmem + T2_TMEM_U, dwh + adv, dxl + adv, idesc1, 1);
+          }
+          umma2_commit_mc(&sb.u_full);
+          umma2_commit_mc(&sb.x_empty[xs]);
+        }
+        __syncwarp();
+      };
+
+      for (int item = pair; item < nitems; item += npairs, ++itc) {
+        const T2Item it = t2_decode(item, ntiles, NIB, NJB, N, rpi);
+        const int nsl = (int)((it.r1 - it.r0 + T2_SLAB - 1) / T2_SLAB);
+        constexpr int SPC = T2_CHAIN / T2_SLAB;
+        mbar_wait_cl(&sb.w_full, itc & 1);
+        issue_mma1(gs);
+        for (int t = 0; t < nsl; ++t, ++gs) {
+          if (t + 1 < nsl) issue_mma1(gs + 1);
+          const bool first = (t % SPC) == 0;
+          const bool last = (t % SPC) == SPC - 1 || t == nsl - 1;
+          if (first) mbar_wait_cl(&sb.acc_empty, (gc & 1) ^ 1);
+          const uint32_t ps = gs % T2_PSTAGES;
+          mbar_wait_cl(&sb.phi_full[ps], (gs / T2_PSTAGES) & 1);
+          tc_fence_after_sync();
+          if (lane == 0) {
+            const uint32_t base = smem_u32(smem + T2_SMEM_PHI + ps * T2_PHI_BYTES);
+            const uint64_t dah = make_desc_sw128(base + T2_OFF_AH);
+            const uint64_t dar = make_desc_sw128(base + T2_OFF_AR);
+            const uint64_t dbh = make_desc_sw128(base + T2_OFF_BH);
+            const uint64_t dbr = make_desc_sw128(base + T2_OFF_BR);
+            const uint64_t dbc = make_desc_sw128(base + T2_OFF_BC);
+#pragma unroll
+            for (int k = 0; k < T2_SLAB / 16; ++k) {
+              const uint64_t adv = (uint64_t)(2 * k);
+              const uint32_t acc = (first && k == 0) ? 0u : 1u;
+              umma2_f16_ss(tmem + T2_TMEM_MAIN, dah + adv, dbh + adv, idesc2, acc);
+              umma2_f16_ss(tmem + T2_TMEM_AUX, dar + adv, dbc + adv, idesc2, acc);
+              umma2_f16_ss(tmem + T2_TMEM_AUX, dah + adv, dbr + adv, idesc2, 1);
+            }
+            umma2_commit_mc(&sb.phi_empty[ps]);
+            if (last) umma2_commit_mc(&sb.acc_full);
+          }
+          __syncwarp();
+          if (last) ++gc;
+        }
+      }
+    }
+  } else if (warp == T2_WARP_LOAD) {
+    // ============================ X slab loader ===================================
+    const uint32_t magic = 65536u / (uint32_t)d + 1u;   // e / d for e < 1024
+    uint32_t gs = 0;
+    for (int item = pair; item < nitems; item += npairs) {
+      const T2Item it = t2_decode(item, ntiles, NIB, NJB, N, rpi);
+      const int nsl = (int)((it.r1 - it.r0 + T2_SLAB - 1) / T2_SLAB);
+      for (int t = 0; t < nsl; ++t, ++gs) {
+        const uint32_t xs = gs % T2_XSTAGES;
+        const int64_t row0 = it.r0 + (int64_t)t * T2_SLAB + 32 * (int64_t)crank;
+        int vr = (int)(it.r1 - row0);
+        vr = vr < 0 ? 0 : (vr > 32 ? 32 : vr);
+        const int cnt = vr * d;
+        const float* src = X + row0 * d;
+        mbar_wait_cl(&sb.x_empty[xs], ((gs / T2_XSTAGES) & 1) ^ 1);
+        const uint32_t x_hi = smem_u32(smem + T2_SMEM_X + xs * 2 * T2_X_BYTES);
+        const uint32_t x_lo = x_hi + T2_X_BYTES;
+        for (int j0 = 0; j0 < d; j0 += 8) {
+          float v[8];
+#pragma unroll
+          for (int jj = 0; jj < 8; ++jj) {
+            const int e = lane + 32 * (j0 + jj);
+            v[jj] = (j0 + jj < d && e < cnt) ? __ldg(src + e) : 0.0f;
+          }
+#pragma unroll
+          for (int jj = 0; jj < 8; ++jj) {
+            if (j0 + jj < d) {
+              const uint32_t e = (uint32_t)(lane + 32 * (j0 + jj));
+              const uint32_t r = (e * magic) >> 16;
+              const uint32_t i = e - r * (uint32_t)d;
+              const float hi = __uint_as_float(__float_as_uint(v[jj]) & 0xFFFFE000u);
+              const float lo = v[jj] - hi;
+              const uint32_t off = sw128_off(r, i >> 2) + (i & 3u) * 4u;
+              asm volatile("st.shared.f32 [%0], %1;" ::"r"(x_hi + off), "f"(hi) : "memory");
+              asm volatile("st.shared.f32 [%0], %1;" ::"r"(x_lo + off), "f"(lo) : "memory");
+            }
+          }
+        }
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) t2_arrive_leader(&sb.x_full[xs], crank);
+      }
+    }
+  } else if (warp >= T2_EPI_WARPS) {
+    // ============================ generators ======================================
+    const int gw = warp - T2_EPI_WARPS;       // 0..7
+    const int q = warp & 3;                   // TMEM lane quadrant of this warp
+    const int h = gw >> 2;                    // which half of the slab's rows
+    const int fl = 32 * q + lane;             // local frequency row 0..127
+    const bool is_a = fl < T2_NA;
+    const bool is_b = fl >= T2_NA && fl < T2_NA + T2_NB;
+    const uint32_t w_hi = smem_u32(smem + T2_SMEM_W), w_lo = w_hi + T2_W_BYTES;
+    uint32_t gs = 0;
+    for (int item = pair; item < nitems; item += npairs) {
+      const T2Item it = t2_decode(item, ntiles, NIB, NJB, N, rpi);
+      const int nsl = (int)((it.r1 - it.r0 + T2_SLAB - 1) / T2_SLAB);
+      const int theta = is_a ? T2_IB * it.ib + T2_NA * (int)crank + fl
+                             : T2_JB * it.jb + T2_NB * (int)crank + (fl - T2_NA);
+      const bool valid = (is_a || is_b) && theta < ktot;
+      // ---- W tile of this item (previous item's projections have all completed:
+      //      this thread has consumed their U) -------------------------------------
+      if (h == 0) {
+        for (int i = 0; i < 32; ++i) {
+          const float w = (valid && i < d) ? __ldg(plan.Wt + (int64_t)i * ktot + theta) : 0.0f;
+          const float hi = __uint_as_float(__float_as_uint(w) & 0xFFFFE000u);
+          const float lo = w - hi;
+          const uint32_t off = sw128_off((uint32_t)fl, (uint32_t)i >> 2) + ((uint32_t)i & 3u) * 4u;
+          asm volatile("st.shared.f32 [%0], %1;" ::"r"(w_hi + off), "f"(hi) : "memory");
+          asm volatile("st.shared.f32 [%0], %1;" ::"r"(w_lo + off), "f"(lo) : "memory");
+        }
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) t2_arrive_leader(&sb.w_full, crank);
+      }
+      const bool do_p = (p != nullptr) && (y != nullptr) && is_a && valid && it.designated;
+      double pc_d = 0.0, ps_d = 0.0;
+      const uint32_t row_cos = is_a ? (uint32_t)fl : (uint32_t)(fl - T2_NA);
+      const uint32_t row_sin = row_cos + (is_a ? (uint32_t)T2_NA : (uint32_t)T2_NB);
+
+      for (int t = 0; t < nsl; ++t, ++gs) {
+        const int64_t row0 = it.r0 + (int64_t)t * T2_SLAB;
+        const int vrows = (int)((it.r1 - row0) < T2_SLAB ? (it.r1 - row0) : T2_SLAB);
+        float u[32];
+        mbar_wait_cl(&sb.u_full, gs & 1);
+        tc_fence_after_sync();
+        tmem_ld32(tmem + ((uint32_t)(32 * q) << 16) + (uint32_t)(T2_TMEM_U + 32 * h), u);
+        tc_fence_before_sync();
+        __syncwarp();
+        if (lane == 0) t2_arrive_leader(&sb.u_empty, crank);
+
+        const uint32_t ps = gs % T2_PSTAGES;
+        const uint32_t base = smem_u32(smem + T2_SMEM_PHI + ps * T2_PHI_BYTES);
+        float pc = 0.0f, psn = 0.0f;
+        bool waited = false;
+#pragma unroll
+        for (int cg = 0; cg < 4; ++cg) {       // 8 rows per 16-byte chunk
+          float c8[8], s8[8];
+#pragma unroll
+          for (int r = 0; r < 8; ++r) {
+            const float uu = u[8 * cg + r];
+            const float kk = __fsub_rn(__fadd_rn(uu, T2_RINT_MAGIC), T2_RINT_MAGIC);
+            const float ang = __fsub_rn(uu, kk) * T2_TWO_PI;
+            c8[r] = __cosf(ang);
+            s8[r] = __sinf(ang);
+          }
+          if (vrows < T2_SLAB || !valid) {
+#pragma unroll
+            for (int r = 0; r < 8; ++r) {
+              const bool live = valid && (32 * h + 8 * cg + r) < vrows;
+              c8[r] = live ? c8[r] : 0.0f;
+              s8[r] = live ? s8[r] : 0.0f;
+            }
+          }
+          if (do_p) {
+#pragma unroll
+            for (int r = 0; r < 8; ++r) {
+              const int64_t rr = row0 + 32 * h + 8 * cg + r;
+              const float yv = rr < it.r1 ? __ldg(y + rr) : 0.0f;
+              pc = fmaf(c8[r], yv, pc);
+              psn = fmaf(s8[r], yv, psn);
+            }
+          }
+          // split into the fixed-point head and the fp16 remainder
+          float hc[8], rc[8], hs[8], rs[8];
+#pragma unroll
+          for (int r = 0; r < 8; ++r) {
+            hc[r] = __fsub_rn(__fadd_rn(c8[r], T2_GRID_MAGIC), T2_GRID_MAGIC);
+            rc[r] = __fsub_rn(c8[r], hc[r]);
+            hs[r] = __fsub_rn(__fadd_rn(s8[r], T2_GRID_MAGIC), T2_GRID_MAGIC);
+            rs[r] = __fsub_rn(s8[r], hs[r]);
+          }
+          if (!waited) {
+            mbar_wait_cl(&sb.phi_empty[ps], ((gs / T2_PSTAGES) & 1) ^ 1);
+            waited = true;
+          }
+          const uint32_t chunk = (uint32_t)(4 * h + cg);
+          auto pack8 = [](const float* x) {
+            __half2 hv[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) hv[i] = __floats2half2_rn(x[2 * i], x[2 * i + 1]);
+            return *reinterpret_cast<uint4*>(hv);
+          };
+          if (is_a) {
+            st_shared_v4(base + T2_OFF_AH + sw128_off(row_cos, chunk), pack8(hc));
+            st_shared_v4(base + T2_OFF_AH + sw128_off(row_sin, chunk), pack8(hs));
+            st_shared_v4(base + T2_OFF_AR + sw128_off(row_cos, chunk), pack8(rc));
+            st_shared_v4(base + T2_OFF_AR + sw128_off(row_sin, chunk), pack8(rs));
+          } else if (is_b) {
+            st_shared_v4(base + T2_OFF_BH + sw128_off(row_cos, chunk), pack8(hc));
+            st_shared_v4(base + T2_OFF_BH + sw128_off(row_sin, chunk), pack8(hs));
+            st_shared_v4(base + T2_OFF_BR + sw128_off(row_cos, chunk), pack8(rc));
+            st_shared_v4(base + T2_OFF_BR + sw128_off(row_sin, chunk), pack8(rs));
+            st_shared_v4(base + T2_OFF_BC + sw128_off(row_cos, chunk), pack8(c8));
+            st_shared_v4(base + T2_OFF_BC + sw128_off(row_sin, chunk), pack8(s8));
+          }
+        }
+        if (do_p) {
+          pc_d += (double)pc;
+          ps_d += (double)psn;
+        }
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) t2_arrive_leader(&sb.phi_full[ps], crank);
+      }
+      if (do_p) {
+        const double a = (double)plan.amp[theta];
+        atomicAdd(p + plan.col_cos[theta], a * pc_d);
+        atomicAdd(p + plan.col_sin[theta], a * ps_d);
+      }
+    }
+  } else {
+    // ============================ epilogue (warps 0..3) ===========================
+    const int q = warp;
+    const int L = 32 * q + lane;              // accumulator lane = local feature row
+    const int type_a = L >> 6;
+    uint32_t gc = 0;
+    for (int item = pair; item < nitems; item += npairs) {
+      const T2Item it = t2_decode(item, ntiles, NIB, NJB, N, rpi);
+      const int64_t rows = it.r1 - it.r0;
+      const int nch = (int)((rows + T2_CHAIN - 1) / T2_CHAIN);
+      // column tables (safe to rewrite: every epilogue warp has finished the
+      // previous item before any of them passes the barrier below)
+      asm volatile("bar.sync 2, 128;" ::: "memory");
+      for (int j = tid; j < T2_NCOL; j += 32 * T2_EPI_WARPS) {
+        const int cc = j / T2_JB, within = j % T2_JB;
+        const int ty = within / T2_NB;
+        const int th = T2_JB * it.jb + T2_NB * cc + within % T2_NB;
+        const bool ok = th < ktot;
+        sb.ecol[j] = ok ? (ty ? plan.col_sin[th] : plan.col_cos[th]) : -1;
+        sb.etheta[j] = 2 * th + ty;           // ordering key
+        sb.eamp[j] = ok ? plan.amp[th] : 0.0f;
+      }
+      asm volatile("bar.sync 2, 128;" ::: "memory");
+      const int theta_a = T2_IB * it.ib + T2_NA * (int)crank + (L & 63);
+      const bool valid_a = theta_a < ktot;
+      const int ca = valid_a ? (type_a ? plan.col_sin[theta_a] : plan.col_cos[theta_a]) : -1;
+      const double amp_a = valid_a ? (double)plan.amp[theta_a] : 0.0;
+      const int key_a = 2 * theta_a + type_a;
+      for (int ch = 0; ch < nch; ++ch, ++gc) {
+        mbar_wait_cl(&sb.acc_full, gc & 1);
+        tc_fence_after_sync();
+#pragma unroll 1
+        for (int c0 = 0; c0 < T2_NCOL; c0 += 32) {
+          float vm[32], vx[32];
+          const uint32_t ta = tmem + ((uint32_t)(32 * q) << 16) + (uint32_t)c0;
+          tmem_ld32_nowait(ta + T2_TMEM_MAIN, vm);
+          tmem_ld32_nowait(ta + T2_TMEM_AUX, vx);
+          tmem_ld_wait();
+#pragma unroll
+          for (int r = 0; r < 32; ++r) {
+            const int j = c0 + r;
+            const int cb = sb.ecol[j];
+            if (ca >= 0 && cb >= 0 && key_a <= sb.etheta[j]) {
+              const double val = ((double)vm[r] + (double)vx[r]) * amp_a * (double)sb.eamp[j];
+              atomicAdd(T + (int64_t)cb * D + ca, val);
+            }
+          }
+        }
+        tc_fence_before_sync();
+        __syncwarp();
+        if (lane == 0) t2_arrive_leader(&sb.acc_empty, crank);
+      }
+    }
+  }
+
+  // ---- teardown ------------------------------------------------------------------
+  tc_fence_before_sync();
+  __syncthreads();
+  cluster_sync_all();
+  if (warp == T2_WARP_MMA) tmem_dealloc_2cta(tmem, 512);
+}
+
+// G[i][j] += T[i][j] + T[j][i] (i != j), G[i][i] += T[i][i]: every unordered
+// feature pair was accumulated exactly once, at either position.
+__global__ void __launch_bounds__(256)
+t2_finalize_kernel(const double* __restrict__ T, double* __restrict__ G, int D) {
+  __shared__ double tile[32][33];
+  const int bx = blockIdx.x, by = blockIdx.y;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
+  // transposed block T[bx-block rows][by-block cols] -> tile
+  for (int r = ty; r < 32; r += 8) {
+    const int i = bx * 32 + r, j = by * 32 + tx;
+    tile[r][tx] = (i < D && j < D) ? T[(int64_t)i * D + j] : 0.0;
+  }
+  __syncthreads();
+  for (int r = ty; r < 32; r += 8) {
+    const int i = by * 32 + r, j = bx * 32 + tx;
+    if (i < D && j < D) {
+      const double a = T[(int64_t)i * D + j];
+      const double b = tile[tx][r];            // T[j][i]
+      G[(int64_t)i * D + j] += (i == j) ? a : a + b;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------
+// Host side
+// ---------------------------------------------------------------------------
+int tc_suffstats_supported(const rr_plan* pl) {
+  return (pl->d >= 1 && pl->d <= 32 && pl->ktot >= 1 && pl->next == 0 &&
+          pl->D == 2 * pl->ktot) ? 1 : 0;
+}
+
+size_t tc_suffstats_workspace(const rr_plan* pl, int64_t) {
+  return align_up((size_t)pl->D * pl->D * sizeof(double), 256) + 256;
+}
+
+int tc_suffstats(const rr_plan* pl, const float* X, const float* y, int64_t N,
+                 double* G, double* p, void* ws, size_t ws_bytes, cudaStream_t st) {
+  const int D = pl->D;
+  Workspace W(ws, ws_bytes);
+  double* T = W.take<double>((size_t)D * D);
+  if (!T) {
+    set_error("tcgen05 suffstats workspace too small (need %zu bytes)",
+              tc_suffstats_workspace(pl, N));
+    return RR_ERR_WORKSPACE;
+  }
+  RR_CUDA_CHECK(cudaMemsetAsync(T, 0, (size_t)D * D * sizeof(double), st));
+  const int NIB = (pl->ktot + T2_IB - 1) / T2_IB;
+  const int NJB = (pl->ktot + T2_JB - 1) / T2_JB;
+  int ntiles = 0;
+  for (int ib = 0; ib < NIB; ++ib) ntiles += NJB - t2_jmin(ib);
+  int64_t rpi = T2_SUPER;
+  const int64_t nsuper = (N + rpi - 1) / rpi;
+  const int64_t nitems = nsuper * ntiles;
+  int npairs = sm_count() / 2;
+  if (nitems < npairs) npairs = (int)nitems;
+  const size_t smem = T2_SMEM_BYTES + 1024;
+  RR_CUDA_CHECK(cudaFuncSetAttribute(tc2_suffstats_kernel,
+                                     cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     (int)smem));
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(2 * npairs);
+  cfg.blockDim = dim3(T2_THREADS);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  RR_CUDA_CHECK(cudaLaunchKernelEx(&cfg, tc2_suffstats_kernel, *pl, X, y, N, T, p, NIB,
+                                   NJB, ntiles, (int)nitems, rpi));
+  RR_LAUNCH_CHECK("tc2_suffstats_kernel");
+  dim3 fg((D + 31) / 32, (D + 31) / 32);
+  t2_finalize_kernel<<<fg, 256, 0, st>>>(T, G, D);
+  RR_LAUNCH_CHECK("t2_finalize_kernel");
+  return RR_OK;
+}
+
+}  // namespace rr
