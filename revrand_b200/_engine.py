@@ -218,6 +218,8 @@ def features(plan, Xd):
     lib = _cabi.load()
     N = Xd.shape[0]
     Phi = t.empty((N, plan.D), dtype=t.float32, device=Xd.device)
+    if N == 0:
+        return Phi
     check(lib.rr_features(C.byref(plan.struct), _ptr(Xd), N, _ptr(Phi), plan.D,
                           _stream_ptr()), "rr_features")
     return Phi

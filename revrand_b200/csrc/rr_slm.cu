@@ -22,8 +22,9 @@ static int pick_engine(int engine, const rr_plan* plan, int64_t N) {
   return (tc_ok && N >= TC_AUTO_MIN_ROWS) ? 1 : 0;
 }
 
-// p[j] += sum_r Phi[r,j] * y[r]; yy += sum y^2.  Thread per column, grid.y
-// splits rows; fp32 partials per thread, float64 atomics across blocks.
+// p[j] += sum_r Phi[r,j] * y[r].  Thread per column, grid.y splits rows;
+// float64 accumulation (the posterior mean inherits every bit lost here,
+// amplified by the conditioning of the problem).
 __global__ void __launch_bounds__(256)
 colsum_weighted_kernel(const float* __restrict__ Phi, int64_t ld, int rows,
                        int D, const float* __restrict__ y,
@@ -32,9 +33,9 @@ colsum_weighted_kernel(const float* __restrict__ Phi, int64_t ld, int rows,
   int per = (rows + gridDim.y - 1) / gridDim.y;
   int r0 = blockIdx.y * per, r1 = min(rows, r0 + per);
   if (j >= D) return;
-  float acc = 0.0f;
-  for (int r = r0; r < r1; ++r) acc = fmaf(Phi[(int64_t)r * ld + j], y[r], acc);
-  atomicAdd(p + j, (double)acc);
+  double acc = 0.0;
+  for (int r = r0; r < r1; ++r) acc = fma((double)Phi[(int64_t)r * ld + j], (double)y[r], acc);
+  atomicAdd(p + j, acc);
 }
 
 __global__ void __launch_bounds__(256)
