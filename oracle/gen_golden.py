@@ -271,9 +271,26 @@ def gen_misc():
     print("misc.npz: %d arrays" % len(out))
 
 
+def config1_fit():
+    """BASELINE config 1 end to end through the unmodified reference: the
+    learned hyper-parameters quoted in tests/test_gpu_parity.py::
+    test_slm_fit_config1_end_to_end (printed, not stored)."""
+    from revrand import StandardLinearModel
+    from revrand.basis_functions import RandomRBF
+    rs = np.random.RandomState(0)
+    X = np.sort(rs.uniform(-5, 5, size=(1000, 1)), axis=0)
+    y = np.sin(X[:, 0]) + 0.1 * rs.randn(1000)
+    slm = StandardLinearModel(basis=RandomRBF(nbases=256, Xdim=1, random_state=1),
+                              nstarts=20, maxiter=200, random_state=2)
+    slm.fit(X, y)
+    print("config1 fit: var_ = %r, regularizer_ = %r, hypers_ = %r, obj_ = %r"
+          % (slm.var_, slm.regularizer_, slm.hypers_, slm.obj_))
+
+
 if __name__ == "__main__":
     gen_bases()
     gen_slm()
     gen_glm()
     gen_misc()
+    config1_fit()
     print("oracle pinned against reference; fixtures written to", OUT)

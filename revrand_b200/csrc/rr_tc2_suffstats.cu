@@ -137,6 +137,76 @@ __device__ __forceinline__ void t2_arrive_leader(uint64_t* bar, uint32_t my_rank
   (void)my_rank;
 }
 
+struct T2GenCtx {
+  uint32_t off_cos[4], off_sin[4];   // chunk offsets inside an operand image
+  uint32_t base;                     // shared address of the current Phi stage
+  uint64_t* empty_bar;               // stage-free barrier, waited before the first store
+  uint32_t empty_parity;
+};
+
+__device__ __forceinline__ uint4 t2_pack8(const float* x) {
+  __half2 hv[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) hv[i] = __floats2half2_rn(x[2 * i], x[2 * i + 1]);
+  return *reinterpret_cast<uint4*>(hv);
+}
+
+// One generator thread, one slab: 32 projections (in turns) of its frequency
+// -> cos/sin -> fixed-point head / fp16 remainder images in shared memory.
+// IS_A: rows of the A tile (images h1, r) else of the B tile (h1, r, cf).
+// MASKED: some of the 32 rows are dead (tail slab, padded frequency).
+// DO_P: also return (sum cos*y, sum sin*y) over the live rows.
+template <bool IS_A, bool MASKED, bool DO_P>
+__device__ __forceinline__ float2 t2_gen_slab(const T2GenCtx& cx, const float* u,
+                                              uint32_t live, const float* yrow,
+                                              bool store = true) {
+  float pc = 0.0f, psn = 0.0f;
+#pragma unroll
+  for (int cg = 0; cg < 4; ++cg) {   // 8 rows per 16-byte chunk
+    float c8[8], s8[8], hc[8], rc[8], hs[8], rs[8];
+#pragma unroll
+    for (int r = 0; r < 8; ++r) {
+      const float uu = u[8 * cg + r];
+      const float kk = __fsub_rn(__fadd_rn(uu, T2_RINT_MAGIC), T2_RINT_MAGIC);
+      const float ang = __fsub_rn(uu, kk) * T2_TWO_PI;
+      c8[r] = __cosf(ang);
+      s8[r] = __sinf(ang);
+      if (MASKED) {
+        const bool on = (live >> (8 * cg + r)) & 1u;
+        c8[r] = on ? c8[r] : 0.0f;
+        s8[r] = on ? s8[r] : 0.0f;
+      }
+      if (DO_P) {
+        const float yv = (!MASKED || ((live >> (8 * cg + r)) & 1u)) ? __ldg(yrow + 8 * cg + r) : 0.0f;
+        pc = fmaf(c8[r], yv, pc);
+        psn = fmaf(s8[r], yv, psn);
+      }
+      hc[r] = __fsub_rn(__fadd_rn(c8[r], T2_GRID_MAGIC), T2_GRID_MAGIC);
+      rc[r] = __fsub_rn(c8[r], hc[r]);
+      hs[r] = __fsub_rn(__fadd_rn(s8[r], T2_GRID_MAGIC), T2_GRID_MAGIC);
+      rs[r] = __fsub_rn(s8[r], hs[r]);
+    }
+    if (cg == 0) mbar_wait_cl(cx.empty_bar, cx.empty_parity);
+    if (store) {
+      const uint32_t oc = cx.base + cx.off_cos[cg], os = cx.base + cx.off_sin[cg];
+      if (IS_A) {
+        st_shared_v4(oc + T2_OFF_AH, t2_pack8(hc));
+        st_shared_v4(os + T2_OFF_AH, t2_pack8(hs));
+        st_shared_v4(oc + T2_OFF_AR, t2_pack8(rc));
+        st_shared_v4(os + T2_OFF_AR, t2_pack8(rs));
+      } else {
+        st_shared_v4(oc + T2_OFF_BH, t2_pack8(hc));
+        st_shared_v4(os + T2_OFF_BH, t2_pack8(hs));
+        st_shared_v4(oc + T2_OFF_BR, t2_pack8(rc));
+        st_shared_v4(os + T2_OFF_BR, t2_pack8(rs));
+        st_shared_v4(oc + T2_OFF_BC, t2_pack8(c8));
+        st_shared_v4(os + T2_OFF_BC, t2_pack8(s8));
+      }
+    }
+  }
+  return make_float2(pc, psn);
+}
+
 __global__ void __launch_bounds__(T2_THREADS, 1)
 tc2_suffstats_kernel(rr_plan plan, const float* __restrict__ X,
                      const float* __restrict__ y, int64_t N, double* __restrict__ T,
@@ -297,16 +367,29 @@ tc2_suffstats_kernel(rr_plan plan, const float* __restrict__ X,
     const int q = warp & 3;                   // TMEM lane quadrant of this warp
     const int h = gw >> 2;                    // which half of the slab's rows
     const int fl = 32 * q + lane;             // local frequency row 0..127
-    const bool is_a = fl < T2_NA;
-    const bool is_b = fl >= T2_NA && fl < T2_NA + T2_NB;
+    const bool is_a = q < 2;                  // warp-uniform: lanes 0..63 feed the A tile
+    const bool has_row = fl < T2_NA + T2_NB;  // lanes 120..127 own no feature rows
     const uint32_t w_hi = smem_u32(smem + T2_SMEM_W), w_lo = w_hi + T2_W_BYTES;
+    // byte offsets of this thread's 16-byte chunks inside one operand image
+    // (fixed for the whole kernel: row and chunk index never change)
+    T2GenCtx cx;
+    {
+      const uint32_t row_cos = is_a ? (uint32_t)fl : (uint32_t)(fl - T2_NA);
+      const uint32_t row_sin = row_cos + (is_a ? (uint32_t)T2_NA : (uint32_t)T2_NB);
+#pragma unroll
+      for (int cg = 0; cg < 4; ++cg) {
+        cx.off_cos[cg] = sw128_off(row_cos, (uint32_t)(4 * h + cg));
+        cx.off_sin[cg] = sw128_off(row_sin, (uint32_t)(4 * h + cg));
+      }
+    }
     uint32_t gs = 0;
     for (int item = pair; item < nitems; item += npairs) {
       const T2Item it = t2_decode(item, ntiles, NIB, NJB, N, rpi);
       const int nsl = (int)((it.r1 - it.r0 + T2_SLAB - 1) / T2_SLAB);
       const int theta = is_a ? T2_IB * it.ib + T2_NA * (int)crank + fl
                              : T2_JB * it.jb + T2_NB * (int)crank + (fl - T2_NA);
-      const bool valid = (is_a || is_b) && theta < ktot;
+      const bool valid = has_row && theta < ktot;
+      const bool all_valid = __all_sync(0xffffffffu, valid);
       // ---- W tile of this item (previous item's projections have all completed:
       //      this thread has consumed their U) -------------------------------------
       if (h == 0) {
@@ -322,10 +405,8 @@ tc2_suffstats_kernel(rr_plan plan, const float* __restrict__ X,
         __syncwarp();
         if (lane == 0) t2_arrive_leader(&sb.w_full, crank);
       }
-      const bool do_p = (p != nullptr) && (y != nullptr) && is_a && valid && it.designated;
+      const bool want_p = (p != nullptr) && (y != nullptr) && is_a && it.designated;  // warp-uniform
       double pc_d = 0.0, ps_d = 0.0;
-      const uint32_t row_cos = is_a ? (uint32_t)fl : (uint32_t)(fl - T2_NA);
-      const uint32_t row_sin = row_cos + (is_a ? (uint32_t)T2_NA : (uint32_t)T2_NB);
 
       for (int t = 0; t < nsl; ++t, ++gs) {
         const int64_t row0 = it.r0 + (int64_t)t * T2_SLAB;
@@ -339,80 +420,34 @@ tc2_suffstats_kernel(rr_plan plan, const float* __restrict__ X,
         if (lane == 0) t2_arrive_leader(&sb.u_empty, crank);
 
         const uint32_t ps = gs % T2_PSTAGES;
-        const uint32_t base = smem_u32(smem + T2_SMEM_PHI + ps * T2_PHI_BYTES);
-        float pc = 0.0f, psn = 0.0f;
-        bool waited = false;
-#pragma unroll
-        for (int cg = 0; cg < 4; ++cg) {       // 8 rows per 16-byte chunk
-          float c8[8], s8[8];
-#pragma unroll
-          for (int r = 0; r < 8; ++r) {
-            const float uu = u[8 * cg + r];
-            const float kk = __fsub_rn(__fadd_rn(uu, T2_RINT_MAGIC), T2_RINT_MAGIC);
-            const float ang = __fsub_rn(uu, kk) * T2_TWO_PI;
-            c8[r] = __cosf(ang);
-            s8[r] = __sinf(ang);
-          }
-          if (vrows < T2_SLAB || !valid) {
-#pragma unroll
-            for (int r = 0; r < 8; ++r) {
-              const bool live = valid && (32 * h + 8 * cg + r) < vrows;
-              c8[r] = live ? c8[r] : 0.0f;
-              s8[r] = live ? s8[r] : 0.0f;
-            }
-          }
-          if (do_p) {
-#pragma unroll
-            for (int r = 0; r < 8; ++r) {
-              const int64_t rr = row0 + 32 * h + 8 * cg + r;
-              const float yv = rr < it.r1 ? __ldg(y + rr) : 0.0f;
-              pc = fmaf(c8[r], yv, pc);
-              psn = fmaf(s8[r], yv, psn);
-            }
-          }
-          // split into the fixed-point head and the fp16 remainder
-          float hc[8], rc[8], hs[8], rs[8];
-#pragma unroll
-          for (int r = 0; r < 8; ++r) {
-            hc[r] = __fsub_rn(__fadd_rn(c8[r], T2_GRID_MAGIC), T2_GRID_MAGIC);
-            rc[r] = __fsub_rn(c8[r], hc[r]);
-            hs[r] = __fsub_rn(__fadd_rn(s8[r], T2_GRID_MAGIC), T2_GRID_MAGIC);
-            rs[r] = __fsub_rn(s8[r], hs[r]);
-          }
-          if (!waited) {
-            mbar_wait_cl(&sb.phi_empty[ps], ((gs / T2_PSTAGES) & 1) ^ 1);
-            waited = true;
-          }
-          const uint32_t chunk = (uint32_t)(4 * h + cg);
-          auto pack8 = [](const float* x) {
-            __half2 hv[4];
-#pragma unroll
-            for (int i = 0; i < 4; ++i) hv[i] = __floats2half2_rn(x[2 * i], x[2 * i + 1]);
-            return *reinterpret_cast<uint4*>(hv);
-          };
-          if (is_a) {
-            st_shared_v4(base + T2_OFF_AH + sw128_off(row_cos, chunk), pack8(hc));
-            st_shared_v4(base + T2_OFF_AH + sw128_off(row_sin, chunk), pack8(hs));
-            st_shared_v4(base + T2_OFF_AR + sw128_off(row_cos, chunk), pack8(rc));
-            st_shared_v4(base + T2_OFF_AR + sw128_off(row_sin, chunk), pack8(rs));
-          } else if (is_b) {
-            st_shared_v4(base + T2_OFF_BH + sw128_off(row_cos, chunk), pack8(hc));
-            st_shared_v4(base + T2_OFF_BH + sw128_off(row_sin, chunk), pack8(hs));
-            st_shared_v4(base + T2_OFF_BR + sw128_off(row_cos, chunk), pack8(rc));
-            st_shared_v4(base + T2_OFF_BR + sw128_off(row_sin, chunk), pack8(rs));
-            st_shared_v4(base + T2_OFF_BC + sw128_off(row_cos, chunk), pack8(c8));
-            st_shared_v4(base + T2_OFF_BC + sw128_off(row_sin, chunk), pack8(s8));
-          }
+        cx.base = smem_u32(smem + T2_SMEM_PHI + ps * T2_PHI_BYTES);
+        cx.empty_bar = &sb.phi_empty[ps];
+        cx.empty_parity = ((gs / T2_PSTAGES) & 1) ^ 1;
+        // rows of this thread's half that are live (tail slab / padded frequency)
+        const int lim = vrows - 32 * h;
+        const uint32_t live = !valid ? 0u : (lim >= 32 ? 0xffffffffu
+                                             : (lim <= 0 ? 0u : ((1u << lim) - 1u)));
+        const bool masked = !(all_valid && vrows == T2_SLAB);   // warp-uniform
+        float2 pacc = make_float2(0.0f, 0.0f);
+        const float* yrow = want_p ? y + row0 + 32 * h : nullptr;
+        if (is_a) {
+          if (want_p) pacc = masked ? t2_gen_slab<true, true, true>(cx, u, live, yrow)
+                                    : t2_gen_slab<true, false, true>(cx, u, live, yrow);
+          else if (masked) t2_gen_slab<true, true, false>(cx, u, live, nullptr);
+          else t2_gen_slab<true, false, false>(cx, u, live, nullptr);
+        } else {
+          if (masked) t2_gen_slab<false, true, false>(cx, u, has_row ? live : 0u, nullptr, has_row);
+          else t2_gen_slab<false, false, false>(cx, u, live, nullptr, has_row);
         }
-        if (do_p) {
-          pc_d += (double)pc;
-          ps_d += (double)psn;
+        if (want_p) {
+          pc_d += (double)pacc.x;
+          ps_d += (double)pacc.y;
         }
         fence_proxy_async_smem();
         __syncwarp();
         if (lane == 0) t2_arrive_leader(&sb.phi_full[ps], crank);
       }
-      if (do_p) {
+      if (want_p && valid) {
         const double a = (double)plan.amp[theta];
         atomicAdd(p + plan.col_cos[theta], a * pc_d);
         atomicAdd(p + plan.col_sin[theta], a * ps_d);

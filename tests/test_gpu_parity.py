@@ -272,7 +272,14 @@ def test_slm_fit_config1_end_to_end():
     slm.fit(X, y)
     Ey, Vy = slm.predict_moments(Xs)
     assert rr.metrics.smse(np.sin(Xs[:, 0]), Ey) < 0.01
-    assert np.all(Vy > 0) and 0.003 < slm.var_ < 0.03
+    assert np.all(Vy > 0)
+    # the unmodified reference, same seeds (oracle/gen_golden.py::config1_fit):
+    # var_ = 0.0856612948789672, regularizer_ = 0.4562465361664085,
+    # hypers_ = 1.9028061472057793, obj_ = 226.95394542226677
+    np.testing.assert_allclose(slm.var_, 0.0856612948789672, rtol=1e-2)
+    np.testing.assert_allclose(slm.regularizer_, 0.4562465361664085, rtol=1e-2)
+    np.testing.assert_allclose(slm.hypers_, 1.9028061472057793, rtol=1e-2)
+    np.testing.assert_allclose(slm.obj_, 226.95394542226677, rtol=1e-3)
     # the learned posterior agrees with the float64 oracle at the learned point
     blocks = [dict(kind="trig", W=slm.basis.W, lenscale=slm.hypers_, cols=None)]
     o = orc.slm_elbo(X, y, slm.var_, [slm.regularizer_], blocks)
