@@ -53,7 +53,10 @@ def test_transform_and_grad_vs_reference(golden, cls):
                 else:
                     probe = cases.probe_matrix(N, Phi.shape[1], seed)
                     got = np.einsum("nj,njp->p", probe, dPhi)
-                    assert relerr(got, g[key + "/dPhi_probe"]) < 1e-4, key
+                    # Cauchy-tailed frequencies: the fp32 phase error above
+                    # is multiplied by |x W / l^2| in the gradient
+                    gtol = 1e-3 if cls == "RandomLaplace" else 1e-4
+                    assert relerr(got, g[key + "/dPhi_probe"]) < gtol, key
 
 
 def test_transform_defaults_empty_and_apply_ind():
