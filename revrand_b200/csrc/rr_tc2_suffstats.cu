@@ -68,7 +68,11 @@ constexpr int T2_X_BYTES = 32 * 128;             // one tf32 image of the X half
 constexpr int T2_SMEM_PHI = 0;
 constexpr int T2_SMEM_W = T2_PSTAGES * T2_PHI_BYTES;
 constexpr int T2_SMEM_X = T2_SMEM_W + 2 * T2_W_BYTES;
-constexpr int T2_SMEM_BYTES = T2_SMEM_X + T2_XSTAGES * 2 * T2_X_BYTES;
+constexpr int T2_SMEM_RAW = T2_SMEM_X + T2_XSTAGES * 2 * T2_X_BYTES;
+constexpr int T2_RAW_AHEAD = 3;                  // slabs of X in flight (cp.async)
+constexpr int T2_RAW_STAGES = T2_RAW_AHEAD + 1;
+constexpr int T2_RAW_BYTES = 32 * 32 * 4;        // 32 rows x d <= 32 floats, as in HBM
+constexpr int T2_SMEM_BYTES = T2_SMEM_RAW + T2_RAW_STAGES * T2_RAW_BYTES;
 
 constexpr int T2_TMEM_MAIN = 0;
 constexpr int T2_TMEM_AUX = T2_NCOL;
@@ -139,72 +143,133 @@ __device__ __forceinline__ void t2_arrive_leader(uint64_t* bar, uint32_t my_rank
 
 struct T2GenCtx {
   uint32_t off_cos[4], off_sin[4];   // chunk offsets inside an operand image
+  uint32_t img_h, img_r;             // image offsets of this thread's tile (A or B)
   uint32_t base;                     // shared address of the current Phi stage
   uint64_t* empty_bar;               // stage-free barrier, waited before the first store
   uint32_t empty_parity;
 };
 
-__device__ __forceinline__ uint4 t2_pack8(const float* x) {
-  __half2 hv[4];
-#pragma unroll
-  for (int i = 0; i < 4; ++i) hv[i] = __floats2half2_rn(x[2 * i], x[2 * i + 1]);
-  return *reinterpret_cast<uint4*>(hv);
+// ---- packed fp32x2 arithmetic (FADD2 / FMUL2 / FFMA2): one issue slot per two
+//      values; the generators are issue-bound, not FMA-pipe-bound -------------
+__device__ __forceinline__ uint64_t f2_pack(float a, float b) {
+  uint64_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b));
+  return r;
+}
+__device__ __forceinline__ void f2_unpack(uint64_t v, float& a, float& b) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v));
+}
+__device__ __forceinline__ uint64_t f2_add(uint64_t a, uint64_t b) {
+  uint64_t r;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ uint64_t f2_sub(uint64_t a, uint64_t b) {
+  uint64_t r;
+  asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ uint64_t f2_mul(uint64_t a, uint64_t b) {
+  uint64_t r;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ uint64_t f2_fma(uint64_t a, uint64_t b, uint64_t c) {
+  uint64_t r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+  return r;
+}
+__device__ __forceinline__ uint32_t f2_to_h2(uint64_t v) {
+  float a, b;
+  f2_unpack(v, a, b);
+  __half2 h = __floats2half2_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&h);
 }
 
 // One generator thread, one slab: 32 projections (in turns) of its frequency
 // -> cos/sin -> fixed-point head / fp16 remainder images in shared memory.
-// IS_A: rows of the A tile (images h1, r) else of the B tile (h1, r, cf).
-// MASKED: some of the 32 rows are dead (tail slab, padded frequency).
-// DO_P: also return (sum cos*y, sum sin*y) over the live rows.
-template <bool IS_A, bool MASKED, bool DO_P>
-__device__ __forceinline__ float2 t2_gen_slab(const T2GenCtx& cx, const float* u,
-                                              uint32_t live, const float* yrow,
-                                              bool store = true) {
-  float pc = 0.0f, psn = 0.0f;
+// A-tile threads write the images (h1, r), B-tile threads (h1, r, cf); the
+// tile kind, the store predicate and the Phi^T y request are runtime flags so
+// that ONE copy of this code serves every generator warp (the previous
+// six-way template expansion was 100 KB of SASS and spent half of its issue
+// slots waiting on instruction fetch).  MASKED: some of the 32 rows are dead
+// (tail slab, padded frequency) -- rare, kept out of the hot instance.
+template <bool MASKED>
+__device__ __forceinline__ void t2_gen_slab(const T2GenCtx& cx, const float* u,
+                                            uint32_t live, bool is_b, bool store,
+                                            const float* yrow, uint64_t& pc2,
+                                            uint64_t& ps2) {
+  const uint64_t RM2 = f2_pack(T2_RINT_MAGIC, T2_RINT_MAGIC);
+  const uint64_t GM2 = f2_pack(T2_GRID_MAGIC, T2_GRID_MAGIC);
+  const uint64_t TP2 = f2_pack(T2_TWO_PI, T2_TWO_PI);
 #pragma unroll
   for (int cg = 0; cg < 4; ++cg) {   // 8 rows per 16-byte chunk
-    float c8[8], s8[8], hc[8], rc[8], hs[8], rs[8];
+    uint64_t c2[4], s2[4];
 #pragma unroll
-    for (int r = 0; r < 8; ++r) {
-      const float uu = u[8 * cg + r];
-      const float kk = __fsub_rn(__fadd_rn(uu, T2_RINT_MAGIC), T2_RINT_MAGIC);
-      const float ang = __fsub_rn(uu, kk) * T2_TWO_PI;
-      c8[r] = __cosf(ang);
-      s8[r] = __sinf(ang);
+    for (int j = 0; j < 4; ++j) {
+      const uint64_t uu = f2_pack(u[8 * cg + 2 * j], u[8 * cg + 2 * j + 1]);
+      const uint64_t kk = f2_sub(f2_add(uu, RM2), RM2);
+      const uint64_t ang = f2_mul(f2_sub(uu, kk), TP2);
+      float a0, a1;
+      f2_unpack(ang, a0, a1);
+      float c0 = __cosf(a0), c1 = __cosf(a1), s0 = __sinf(a0), s1 = __sinf(a1);
       if (MASKED) {
-        const bool on = (live >> (8 * cg + r)) & 1u;
-        c8[r] = on ? c8[r] : 0.0f;
-        s8[r] = on ? s8[r] : 0.0f;
+        const bool on0 = (live >> (8 * cg + 2 * j)) & 1u;
+        const bool on1 = (live >> (8 * cg + 2 * j + 1)) & 1u;
+        c0 = on0 ? c0 : 0.0f;
+        s0 = on0 ? s0 : 0.0f;
+        c1 = on1 ? c1 : 0.0f;
+        s1 = on1 ? s1 : 0.0f;
       }
-      if (DO_P) {
-        const float yv = (!MASKED || ((live >> (8 * cg + r)) & 1u)) ? __ldg(yrow + 8 * cg + r) : 0.0f;
-        pc = fmaf(c8[r], yv, pc);
-        psn = fmaf(s8[r], yv, psn);
+      c2[j] = f2_pack(c0, c1);
+      s2[j] = f2_pack(s0, s1);
+    }
+    if (yrow != nullptr) {   // warp-uniform; designated A tiles only
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        float y0 = 0.0f, y1 = 0.0f;
+        if (!MASKED || ((live >> (8 * cg + 2 * j)) & 1u)) y0 = __ldg(yrow + 8 * cg + 2 * j);
+        if (!MASKED || ((live >> (8 * cg + 2 * j + 1)) & 1u)) y1 = __ldg(yrow + 8 * cg + 2 * j + 1);
+        const uint64_t y2 = f2_pack(y0, y1);
+        pc2 = f2_fma(c2[j], y2, pc2);
+        ps2 = f2_fma(s2[j], y2, ps2);
       }
-      hc[r] = __fsub_rn(__fadd_rn(c8[r], T2_GRID_MAGIC), T2_GRID_MAGIC);
-      rc[r] = __fsub_rn(c8[r], hc[r]);
-      hs[r] = __fsub_rn(__fadd_rn(s8[r], T2_GRID_MAGIC), T2_GRID_MAGIC);
-      rs[r] = __fsub_rn(s8[r], hs[r]);
+    }
+    uint4 hc, rc, hs, rs;
+    uint32_t* hcp = reinterpret_cast<uint32_t*>(&hc);
+    uint32_t* rcp = reinterpret_cast<uint32_t*>(&rc);
+    uint32_t* hsp = reinterpret_cast<uint32_t*>(&hs);
+    uint32_t* rsp = reinterpret_cast<uint32_t*>(&rs);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const uint64_t h_c = f2_sub(f2_add(c2[j], GM2), GM2);
+      const uint64_t h_s = f2_sub(f2_add(s2[j], GM2), GM2);
+      hcp[j] = f2_to_h2(h_c);
+      hsp[j] = f2_to_h2(h_s);
+      rcp[j] = f2_to_h2(f2_sub(c2[j], h_c));
+      rsp[j] = f2_to_h2(f2_sub(s2[j], h_s));
     }
     if (cg == 0) mbar_wait_cl(cx.empty_bar, cx.empty_parity);
     if (store) {
       const uint32_t oc = cx.base + cx.off_cos[cg], os = cx.base + cx.off_sin[cg];
-      if (IS_A) {
-        st_shared_v4(oc + T2_OFF_AH, t2_pack8(hc));
-        st_shared_v4(os + T2_OFF_AH, t2_pack8(hs));
-        st_shared_v4(oc + T2_OFF_AR, t2_pack8(rc));
-        st_shared_v4(os + T2_OFF_AR, t2_pack8(rs));
-      } else {
-        st_shared_v4(oc + T2_OFF_BH, t2_pack8(hc));
-        st_shared_v4(os + T2_OFF_BH, t2_pack8(hs));
-        st_shared_v4(oc + T2_OFF_BR, t2_pack8(rc));
-        st_shared_v4(os + T2_OFF_BR, t2_pack8(rs));
-        st_shared_v4(oc + T2_OFF_BC, t2_pack8(c8));
-        st_shared_v4(os + T2_OFF_BC, t2_pack8(s8));
+      st_shared_v4(oc + cx.img_h, hc);
+      st_shared_v4(os + cx.img_h, hs);
+      st_shared_v4(oc + cx.img_r, rc);
+      st_shared_v4(os + cx.img_r, rs);
+      if (is_b) {
+        uint4 cf, sf;
+        uint32_t* cfp = reinterpret_cast<uint32_t*>(&cf);
+        uint32_t* sfp = reinterpret_cast<uint32_t*>(&sf);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          cfp[j] = f2_to_h2(c2[j]);
+          sfp[j] = f2_to_h2(s2[j]);
+        }
+        st_shared_v4(oc + T2_OFF_BC, cf);
+        st_shared_v4(os + T2_OFF_BC, sf);
       }
     }
   }
-  return make_float2(pc, psn);
 }
 
 __global__ void __launch_bounds__(T2_THREADS, 1)
@@ -320,47 +385,101 @@ tc2_suffstats_kernel(rr_plan plan, const float* __restrict__ X,
     }
   } else if (warp == T2_WARP_LOAD) {
     // ============================ X slab loader ===================================
-    const uint32_t magic = 65536u / (uint32_t)d + 1u;   // e / d for e < 1024
-    uint32_t gs = 0;
-    for (int item = pair; item < nitems; item += npairs) {
-      const T2Item it = t2_decode(item, ntiles, NIB, NJB, N, rpi);
-      const int nsl = (int)((it.r1 - it.r0 + T2_SLAB - 1) / T2_SLAB);
-      for (int t = 0; t < nsl; ++t, ++gs) {
-        const uint32_t xs = gs % T2_XSTAGES;
-        const int64_t row0 = it.r0 + (int64_t)t * T2_SLAB + 32 * (int64_t)crank;
-        int vr = (int)(it.r1 - row0);
+    // Two steps per slab, both by this one warp.  (1) cp.async: the CTA's 32 rows
+    // are one contiguous block of X; lanes copy it word by word (coalesced, any
+    // 4-byte alignment, zero fill past the last row) into a raw staging ring,
+    // T2_RAW_AHEAD slabs ahead, so HBM latency never sits on the slab period.
+    // (2) lane r reads row r back (stride d words), splits it into tf32 hi/lo
+    // and writes both K-major swizzled tiles with 16-byte stores.
+    struct SlabIter {
+      int item, t, nsl;
+      int64_t r0, r1;
+    };
+    auto load_item = [&](SlabIter& si) {
+      if (si.item < nitems) {
+        const T2Item it = t2_decode(si.item, ntiles, NIB, NJB, N, rpi);
+        si.r0 = it.r0;
+        si.r1 = it.r1;
+        si.nsl = (int)((it.r1 - it.r0 + T2_SLAB - 1) / T2_SLAB);
+        si.t = 0;
+      }
+    };
+    auto advance = [&](SlabIter& si) {
+      if (si.item < nitems && ++si.t >= si.nsl) {
+        si.item += npairs;
+        load_item(si);
+      }
+    };
+    const uint32_t raw0 = smem_u32(smem + T2_SMEM_RAW);
+    auto prefetch = [&](const SlabIter& si, uint32_t stage) {
+      if (si.item < nitems) {
+        const int64_t row0 = si.r0 + (int64_t)si.t * T2_SLAB + 32 * (int64_t)crank;
+        int vr = (int)(si.r1 - row0);
         vr = vr < 0 ? 0 : (vr > 32 ? 32 : vr);
         const int cnt = vr * d;
         const float* src = X + row0 * d;
-        mbar_wait_cl(&sb.x_empty[xs], ((gs / T2_XSTAGES) & 1) ^ 1);
-        const uint32_t x_hi = smem_u32(smem + T2_SMEM_X + xs * 2 * T2_X_BYTES);
-        const uint32_t x_lo = x_hi + T2_X_BYTES;
-        for (int j0 = 0; j0 < d; j0 += 8) {
-          float v[8];
-#pragma unroll
-          for (int jj = 0; jj < 8; ++jj) {
-            const int e = lane + 32 * (j0 + jj);
-            v[jj] = (j0 + jj < d && e < cnt) ? __ldg(src + e) : 0.0f;
-          }
-#pragma unroll
-          for (int jj = 0; jj < 8; ++jj) {
-            if (j0 + jj < d) {
-              const uint32_t e = (uint32_t)(lane + 32 * (j0 + jj));
-              const uint32_t r = (e * magic) >> 16;
-              const uint32_t i = e - r * (uint32_t)d;
-              const float hi = __uint_as_float(__float_as_uint(v[jj]) & 0xFFFFE000u);
-              const float lo = v[jj] - hi;
-              const uint32_t off = sw128_off(r, i >> 2) + (i & 3u) * 4u;
-              asm volatile("st.shared.f32 [%0], %1;" ::"r"(x_hi + off), "f"(hi) : "memory");
-              asm volatile("st.shared.f32 [%0], %1;" ::"r"(x_lo + off), "f"(lo) : "memory");
-            }
-          }
+        const uint32_t dst = raw0 + stage * T2_RAW_BYTES + 4u * (uint32_t)lane;
+        for (int j = 0; j < d; ++j) {
+          const int e = lane + 32 * j;
+          const bool ok = e < cnt;
+          const float* g = ok ? src + e : X;
+          asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(dst + 128u * (uint32_t)j),
+                       "l"(g), "r"(ok ? 4 : 0)
+                       : "memory");
         }
-        fence_proxy_async_smem();
-        __syncwarp();
-        if (lane == 0) t2_arrive_leader(&sb.x_full[xs], crank);
       }
+      asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    SlabIter pf, cs;
+    pf.item = cs.item = pair;
+    load_item(pf);
+    load_item(cs);
+    for (int i = 0; i < T2_RAW_AHEAD; ++i) {
+      prefetch(pf, (uint32_t)i);
+      advance(pf);
     }
+    const int nch = 2 * nk1;   // 16-byte chunks of a tile row that MMA#1 reads
+    uint32_t gs = 0;
+    while (cs.item < nitems) {
+      prefetch(pf, (gs + T2_RAW_AHEAD) % T2_RAW_STAGES);
+      advance(pf);
+      asm volatile("cp.async.wait_group %0;" ::"n"(T2_RAW_AHEAD) : "memory");
+      __syncwarp();
+      const uint32_t rrow = raw0 + (gs % T2_RAW_STAGES) * T2_RAW_BYTES + 4u * (uint32_t)(lane * d);
+      float v[32];
+#pragma unroll
+      for (int i = 0; i < 32; ++i) {
+        v[i] = 0.0f;
+        if (i < d) asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v[i]) : "r"(rrow + 4u * i));
+      }
+      const uint32_t xs = gs % T2_XSTAGES;
+      mbar_wait_cl(&sb.x_empty[xs], ((gs / T2_XSTAGES) & 1) ^ 1);
+      const uint32_t x_hi = smem_u32(smem + T2_SMEM_X + xs * 2 * T2_X_BYTES);
+      const uint32_t x_lo = x_hi + T2_X_BYTES;
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {
+        if (c < nch) {
+          uint4 hi, lo;
+          uint32_t* hp = reinterpret_cast<uint32_t*>(&hi);
+          uint32_t* lp = reinterpret_cast<uint32_t*>(&lo);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const uint32_t hb = __float_as_uint(v[4 * c + k]) & 0xFFFFE000u;
+            hp[k] = hb;
+            lp[k] = __float_as_uint(v[4 * c + k] - __uint_as_float(hb));
+          }
+          const uint32_t off = sw128_off((uint32_t)lane, (uint32_t)c);
+          st_shared_v4(x_hi + off, hi);
+          st_shared_v4(x_lo + off, lo);
+        }
+      }
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) t2_arrive_leader(&sb.x_full[xs], crank);
+      advance(cs);
+      ++gs;
+    }
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
   } else if (warp >= T2_EPI_WARPS) {
     // ============================ generators ======================================
     const int gw = warp - T2_EPI_WARPS;       // 0..7
@@ -381,6 +500,8 @@ tc2_suffstats_kernel(rr_plan plan, const float* __restrict__ X,
         cx.off_cos[cg] = sw128_off(row_cos, (uint32_t)(4 * h + cg));
         cx.off_sin[cg] = sw128_off(row_sin, (uint32_t)(4 * h + cg));
       }
+      cx.img_h = is_a ? (uint32_t)T2_OFF_AH : (uint32_t)T2_OFF_BH;
+      cx.img_r = is_a ? (uint32_t)T2_OFF_AR : (uint32_t)T2_OFF_BR;
     }
     uint32_t gs = 0;
     for (int item = pair; item < nitems; item += npairs) {
@@ -389,7 +510,8 @@ tc2_suffstats_kernel(rr_plan plan, const float* __restrict__ X,
       const int theta = is_a ? T2_IB * it.ib + T2_NA * (int)crank + fl
                              : T2_JB * it.jb + T2_NB * (int)crank + (fl - T2_NA);
       const bool valid = has_row && theta < ktot;
-      const bool all_valid = __all_sync(0xffffffffu, valid);
+      // lanes without a feature row store nothing: they may run the unmasked code
+      const bool all_valid = __all_sync(0xffffffffu, valid || !has_row);
       // ---- W tile of this item (previous item's projections have all completed:
       //      this thread has consumed their U) -------------------------------------
       if (h == 0) {
@@ -428,20 +550,16 @@ tc2_suffstats_kernel(rr_plan plan, const float* __restrict__ X,
         const uint32_t live = !valid ? 0u : (lim >= 32 ? 0xffffffffu
                                              : (lim <= 0 ? 0u : ((1u << lim) - 1u)));
         const bool masked = !(all_valid && vrows == T2_SLAB);   // warp-uniform
-        float2 pacc = make_float2(0.0f, 0.0f);
+        uint64_t pc2 = 0ull, ps2 = 0ull;   // (+0.0f, +0.0f)
         const float* yrow = want_p ? y + row0 + 32 * h : nullptr;
-        if (is_a) {
-          if (want_p) pacc = masked ? t2_gen_slab<true, true, true>(cx, u, live, yrow)
-                                    : t2_gen_slab<true, false, true>(cx, u, live, yrow);
-          else if (masked) t2_gen_slab<true, true, false>(cx, u, live, nullptr);
-          else t2_gen_slab<true, false, false>(cx, u, live, nullptr);
-        } else {
-          if (masked) t2_gen_slab<false, true, false>(cx, u, has_row ? live : 0u, nullptr, has_row);
-          else t2_gen_slab<false, false, false>(cx, u, live, nullptr, has_row);
-        }
+        if (masked) t2_gen_slab<true>(cx, u, has_row ? live : 0u, !is_a, has_row, yrow, pc2, ps2);
+        else t2_gen_slab<false>(cx, u, live, !is_a, has_row, yrow, pc2, ps2);
         if (want_p) {
-          pc_d += (double)pacc.x;
-          ps_d += (double)pacc.y;
+          float a0, a1, b0, b1;
+          f2_unpack(pc2, a0, a1);
+          f2_unpack(ps2, b0, b1);
+          pc_d += (double)a0 + (double)a1;
+          ps_d += (double)b0 + (double)b1;
         }
         fence_proxy_async_smem();
         __syncwarp();
