@@ -66,6 +66,21 @@ __device__ __forceinline__ void tc_fence_after_sync() {
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 }
 
+// One thread of a fully converged warp (elect.sync): unlike `lane == 0` the
+// compiler knows the guarded region runs in exactly one thread, so tcgen05.mma
+// operands stay in uniform registers instead of going through an
+// ELECT / R2UR.BROADCAST / BRA.U.ANY loop per instruction (measured: ~100
+// cycles of issue per MMA with `lane == 0`, which starved the tensor pipe).
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
+
 // ---- TMEM allocation (one full warp executes these) -------------------------
 __device__ __forceinline__ void tmem_alloc(uint32_t* smem_dst, uint32_t ncols) {
   asm volatile(
@@ -205,14 +220,19 @@ __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
   asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr)
                : "memory");
 }
+// try_wait with a suspend-time hint: the warp is parked by the hardware until
+// the phase completes (or the hint, in ns, expires) instead of re-polling every
+// few dozen cycles.  Polling matters here: mbarrier tests travel through the
+// same MIO queue as MUFU and shared-memory stores, and in the fused value pass
+// idle role warps were issuing more than half of all instructions as polls.
 __device__ __forceinline__ bool mbar_try_wait_cl(uint64_t* bar, uint32_t parity) {
   uint32_t ok;
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
       "selp.u32 %0, 1, 0, p;\n\t}"
       : "=r"(ok)
-      : "r"(smem_u32(bar)), "r"(parity)
+      : "r"(smem_u32(bar)), "r"(parity), "r"(1000000u)
       : "memory");
   return ok != 0;
 }
@@ -289,6 +309,30 @@ __device__ __forceinline__ void tmem_ld32_nowait(uint32_t taddr, float* v) {
         "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]),
         "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]),
         "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+}
+
+// TMEM -> registers: 32 lanes x 16 consecutive fp32 columns per warp, no wait.
+__device__ __forceinline__ void tmem_ld16_nowait(uint32_t taddr, float* v) {
+  uint32_t* r = reinterpret_cast<uint32_t*>(v);
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]),
+        "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]),
+        "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+}
+
+// TMEM -> registers: 32 lanes x 8 consecutive fp32 columns per warp, no wait.
+__device__ __forceinline__ void tmem_ld8_nowait(uint32_t taddr, float* v) {
+  uint32_t* r = reinterpret_cast<uint32_t*>(v);
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]),
+        "=r"(r[6]), "=r"(r[7])
       : "r"(taddr)
       : "memory");
 }

@@ -57,12 +57,17 @@ constexpr float T2_TWO_PI = 6.283185307179586f;
 
 constexpr int T2_A_BYTES = 128 * 128;            // one fp16 image of the A tile
 constexpr int T2_B_BYTES = 2 * T2_NB * 128;      // one fp16 image of the B half tile
+// image order [A.h1 | B.h1 | A.r | B.r | B.cf]: the h1 -> r distance is the same
+// for both tiles, so one generator code path addresses either with immediates
 constexpr int T2_OFF_AH = 0;
-constexpr int T2_OFF_AR = T2_A_BYTES;
-constexpr int T2_OFF_BH = 2 * T2_A_BYTES;
-constexpr int T2_OFF_BR = T2_OFF_BH + T2_B_BYTES;
+constexpr int T2_OFF_BH = T2_A_BYTES;
+constexpr int T2_OFF_AR = T2_OFF_BH + T2_B_BYTES;
+constexpr int T2_OFF_BR = T2_OFF_AR + T2_A_BYTES;
 constexpr int T2_OFF_BC = T2_OFF_BR + T2_B_BYTES;
 constexpr int T2_PHI_BYTES = T2_OFF_BC + T2_B_BYTES;   // 75776
+constexpr int T2_H2R = T2_OFF_AR - T2_OFF_AH;          // == T2_OFF_BR - T2_OFF_BH
+constexpr int T2_H2C = T2_OFF_BC - T2_OFF_BH;
+static_assert(T2_OFF_BR - T2_OFF_BH == T2_H2R, "image layout");
 constexpr int T2_W_BYTES = 128 * 128;            // one tf32 image of the W tile
 constexpr int T2_X_BYTES = 32 * 128;             // one tf32 image of the X half slab
 constexpr int T2_SMEM_PHI = 0;
@@ -79,13 +84,32 @@ constexpr int T2_TMEM_AUX = T2_NCOL;
 constexpr int T2_TMEM_U = 2 * T2_NCOL;           // 448 .. 511
 
 constexpr int T2_EPI_WARPS = 4;                  // warps 0..3
-constexpr int T2_GEN_WARPS = 8;                  // warps 4..11
-constexpr int T2_WARP_MMA = 12;
-constexpr int T2_WARP_LOAD = 13;
-constexpr int T2_THREADS = 14 * 32;
+constexpr int T2_GROWS = 16;                     // slab rows per generator thread
+constexpr int T2_GSPLIT = T2_SLAB / T2_GROWS;    // generator warps per TMEM lane quadrant
+constexpr int T2_GEN_WARPS = 4 * T2_GSPLIT;      // warps 4..19: four per SM sub-partition, so
+                                                 // MUFU and FMA-pipe phases of different warps overlap
+constexpr int T2_WARP_MMA = T2_EPI_WARPS + T2_GEN_WARPS;
+constexpr int T2_WARP_LOAD = T2_WARP_MMA + 1;
+constexpr int T2_THREADS = (T2_WARP_LOAD + 1) * 32;
+constexpr int T2_GPAIRS = T2_GROWS / 2;          // packed row pairs per generator thread
+constexpr int T2_GCHUNKS = T2_GROWS / 8;         // 16-byte chunks per image row per thread
 
 static_assert(T2_PHI_BYTES % 1024 == 0, "operand tiles must stay 1024-byte aligned");
 static_assert(T2_TMEM_U + 64 == 512, "TMEM budget");
+
+// ---- optional event trace (debug builds only: -DRR_T2_TRACE) ---------------------
+#ifdef RR_T2_TRACE
+constexpr int T2_TR_SLAB0 = 200, T2_TR_NSLAB = 48, T2_TR_SLOTS = 32;
+__device__ long long g_t2_trace[T2_TR_NSLAB * T2_TR_SLOTS];
+#define T2_TRACE(cond, slab, slot)                                                     \
+  do {                                                                                 \
+    if ((cond) && blockIdx.x == 0 && (slab) >= T2_TR_SLAB0 &&                          \
+        (slab) < T2_TR_SLAB0 + T2_TR_NSLAB)                                            \
+      g_t2_trace[((slab) - T2_TR_SLAB0) * T2_TR_SLOTS + (slot)] = clock64();           \
+  } while (0)
+#else
+#define T2_TRACE(cond, slab, slot) do { } while (0)
+#endif
 
 struct T2Bars {
   uint64_t x_full[T2_XSTAGES];    // leader waits; count 2 (one loader per CTA)
@@ -99,9 +123,7 @@ struct T2Bars {
   uint64_t acc_empty;             // leader waits; count 8 (epilogue warps)
   uint32_t tmem_base;
   // epilogue column tables for the current item
-  int ecol[T2_NCOL];
-  int etheta[T2_NCOL];
-  float eamp[T2_NCOL];
+  int2 etab[T2_NCOL];   // {column * D (or -1), ordering key}
 };
 
 __host__ __device__ __forceinline__ int t2_jmin(int ib) {
@@ -142,11 +164,14 @@ __device__ __forceinline__ void t2_arrive_leader(uint64_t* bar, uint32_t my_rank
 }
 
 struct T2GenCtx {
-  uint32_t off_cos[4], off_sin[4];   // chunk offsets inside an operand image
-  uint32_t img_h, img_r;             // image offsets of this thread's tile (A or B)
+  uint32_t off_cos[T2_GCHUNKS], off_sin[T2_GCHUNKS];   // h1-image chunk offsets inside a Phi stage (tile base included)
   uint32_t base;                     // shared address of the current Phi stage
   uint64_t* empty_bar;               // stage-free barrier, waited before the first store
   uint32_t empty_parity;
+#ifdef RR_T2_TRACE
+  bool trw;
+  int trs, trb;
+#endif
 };
 
 // ---- packed fp32x2 arithmetic (FADD2 / FMUL2 / FFMA2): one issue slot per two
@@ -186,15 +211,19 @@ __device__ __forceinline__ uint32_t f2_to_h2(uint64_t v) {
   return *reinterpret_cast<uint32_t*>(&h);
 }
 
-// One generator thread, one slab: 32 projections (in turns) of its frequency
+// One generator thread, one slab: T2_GROWS projections (in turns) of its frequency
 // -> cos/sin -> fixed-point head / fp16 remainder images in shared memory.
-// A-tile threads write the images (h1, r), B-tile threads (h1, r, cf); the
-// tile kind, the store predicate and the Phi^T y request are runtime flags so
-// that ONE copy of this code serves every generator warp (the previous
-// six-way template expansion was 100 KB of SASS and spent half of its issue
-// slots waiting on instruction fetch).  MASKED: some of the 32 rows are dead
-// (tail slab, padded frequency) -- rare, kept out of the hot instance.
-template <bool MASKED>
+// A-tile threads write the images (h1, r), B-tile threads (h1, r, cf); tile
+// kind and store predicate are runtime flags so that ONE copy of this code
+// serves every generator warp (a six-way template expansion was 100 KB of SASS
+// and spent half of its issue slots waiting on instruction fetch).
+//   MASKED: some of the rows are dead (tail slab, padded frequency) -- rare.
+//   DO_P:   also accumulate (sum cos*y, sum sin*y) -- designated A tiles only.
+// The source order is a software pipeline over row pairs: the MUFU work of
+// pair i+2 is written before the FMA-pipe split of pair i so that the two
+// pipes overlap inside one warp (each SM sub-partition hosts only two
+// generator warps, and they run in lock step).
+template <bool MASKED, bool DO_P>
 __device__ __forceinline__ void t2_gen_slab(const T2GenCtx& cx, const float* u,
                                             uint32_t live, bool is_b, bool store,
                                             const float* yrow, uint64_t& pc2,
@@ -202,73 +231,80 @@ __device__ __forceinline__ void t2_gen_slab(const T2GenCtx& cx, const float* u,
   const uint64_t RM2 = f2_pack(T2_RINT_MAGIC, T2_RINT_MAGIC);
   const uint64_t GM2 = f2_pack(T2_GRID_MAGIC, T2_GRID_MAGIC);
   const uint64_t TP2 = f2_pack(T2_TWO_PI, T2_TWO_PI);
-#pragma unroll
-  for (int cg = 0; cg < 4; ++cg) {   // 8 rows per 16-byte chunk
-    uint64_t c2[4], s2[4];
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const uint64_t uu = f2_pack(u[8 * cg + 2 * j], u[8 * cg + 2 * j + 1]);
-      const uint64_t kk = f2_sub(f2_add(uu, RM2), RM2);
-      const uint64_t ang = f2_mul(f2_sub(uu, kk), TP2);
-      float a0, a1;
-      f2_unpack(ang, a0, a1);
-      float c0 = __cosf(a0), c1 = __cosf(a1), s0 = __sinf(a0), s1 = __sinf(a1);
-      if (MASKED) {
-        const bool on0 = (live >> (8 * cg + 2 * j)) & 1u;
-        const bool on1 = (live >> (8 * cg + 2 * j + 1)) & 1u;
-        c0 = on0 ? c0 : 0.0f;
-        s0 = on0 ? s0 : 0.0f;
-        c1 = on1 ? c1 : 0.0f;
-        s1 = on1 ? s1 : 0.0f;
+  uint64_t c2[T2_GPAIRS], s2[T2_GPAIRS];
+  uint4 hc, rc, hs, rs, cf, sf;
+  uint32_t* hcp = reinterpret_cast<uint32_t*>(&hc);
+  uint32_t* rcp = reinterpret_cast<uint32_t*>(&rc);
+  uint32_t* hsp = reinterpret_cast<uint32_t*>(&hs);
+  uint32_t* rsp = reinterpret_cast<uint32_t*>(&rs);
+  uint32_t* cfp = reinterpret_cast<uint32_t*>(&cf);
+  uint32_t* sfp = reinterpret_cast<uint32_t*>(&sf);
+
+  auto trig = [&](int i) {   // rows 2i, 2i+1
+    const uint64_t uu = f2_pack(u[2 * i], u[2 * i + 1]);
+    const uint64_t kk = f2_sub(f2_add(uu, RM2), RM2);
+    const uint64_t ang = f2_mul(f2_sub(uu, kk), TP2);
+    float a0, a1;
+    f2_unpack(ang, a0, a1);
+    float c0 = __cosf(a0), s0 = __sinf(a0), c1 = __cosf(a1), s1 = __sinf(a1);
+    if (MASKED) {
+      const bool on0 = (live >> (2 * i)) & 1u, on1 = (live >> (2 * i + 1)) & 1u;
+      c0 = on0 ? c0 : 0.0f;
+      s0 = on0 ? s0 : 0.0f;
+      c1 = on1 ? c1 : 0.0f;
+      s1 = on1 ? s1 : 0.0f;
+    }
+    c2[i] = f2_pack(c0, c1);
+    s2[i] = f2_pack(s0, s1);
+    if (DO_P) {
+      float y0 = 0.0f, y1 = 0.0f;
+      if (!MASKED || ((live >> (2 * i)) & 1u)) y0 = __ldg(yrow + 2 * i);
+      if (!MASKED || ((live >> (2 * i + 1)) & 1u)) y1 = __ldg(yrow + 2 * i + 1);
+      const uint64_t y2 = f2_pack(y0, y1);
+      pc2 = f2_fma(c2[i], y2, pc2);
+      ps2 = f2_fma(s2[i], y2, ps2);
+    }
+  };
+  auto split = [&](int i) {
+    const int j = i & 3;
+    const uint64_t h_c = f2_sub(f2_add(c2[i], GM2), GM2);
+    const uint64_t h_s = f2_sub(f2_add(s2[i], GM2), GM2);
+    hcp[j] = f2_to_h2(h_c);
+    hsp[j] = f2_to_h2(h_s);
+    rcp[j] = f2_to_h2(f2_sub(c2[i], h_c));
+    rsp[j] = f2_to_h2(f2_sub(s2[i], h_s));
+    cfp[j] = f2_to_h2(c2[i]);   // dead code for A tiles unless stored below
+    sfp[j] = f2_to_h2(s2[i]);
+    if (j == 3) {               // 8 rows complete: one 16-byte chunk per image
+      const int cg = i >> 2;
+      if (cg == 0) {
+        T2_TRACE(cx.trw, cx.trs, cx.trb + 5);
+        mbar_wait_cl(cx.empty_bar, cx.empty_parity);
+        T2_TRACE(cx.trw, cx.trs, cx.trb + 6);
       }
-      c2[j] = f2_pack(c0, c1);
-      s2[j] = f2_pack(s0, s1);
-    }
-    if (yrow != nullptr) {   // warp-uniform; designated A tiles only
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        float y0 = 0.0f, y1 = 0.0f;
-        if (!MASKED || ((live >> (8 * cg + 2 * j)) & 1u)) y0 = __ldg(yrow + 8 * cg + 2 * j);
-        if (!MASKED || ((live >> (8 * cg + 2 * j + 1)) & 1u)) y1 = __ldg(yrow + 8 * cg + 2 * j + 1);
-        const uint64_t y2 = f2_pack(y0, y1);
-        pc2 = f2_fma(c2[j], y2, pc2);
-        ps2 = f2_fma(s2[j], y2, ps2);
-      }
-    }
-    uint4 hc, rc, hs, rs;
-    uint32_t* hcp = reinterpret_cast<uint32_t*>(&hc);
-    uint32_t* rcp = reinterpret_cast<uint32_t*>(&rc);
-    uint32_t* hsp = reinterpret_cast<uint32_t*>(&hs);
-    uint32_t* rsp = reinterpret_cast<uint32_t*>(&rs);
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const uint64_t h_c = f2_sub(f2_add(c2[j], GM2), GM2);
-      const uint64_t h_s = f2_sub(f2_add(s2[j], GM2), GM2);
-      hcp[j] = f2_to_h2(h_c);
-      hsp[j] = f2_to_h2(h_s);
-      rcp[j] = f2_to_h2(f2_sub(c2[j], h_c));
-      rsp[j] = f2_to_h2(f2_sub(s2[j], h_s));
-    }
-    if (cg == 0) mbar_wait_cl(cx.empty_bar, cx.empty_parity);
-    if (store) {
-      const uint32_t oc = cx.base + cx.off_cos[cg], os = cx.base + cx.off_sin[cg];
-      st_shared_v4(oc + cx.img_h, hc);
-      st_shared_v4(os + cx.img_h, hs);
-      st_shared_v4(oc + cx.img_r, rc);
-      st_shared_v4(os + cx.img_r, rs);
-      if (is_b) {
-        uint4 cf, sf;
-        uint32_t* cfp = reinterpret_cast<uint32_t*>(&cf);
-        uint32_t* sfp = reinterpret_cast<uint32_t*>(&sf);
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          cfp[j] = f2_to_h2(c2[j]);
-          sfp[j] = f2_to_h2(s2[j]);
+#ifdef RR_T2_EXP_NOSTS     // experiment: generator cost without shared-memory stores
+      if (store && hcp[0] == 0x12345678u) {
+#else
+      if (store) {
+#endif
+        const uint32_t oc = cx.base + cx.off_cos[cg], os = cx.base + cx.off_sin[cg];
+        st_shared_v4(oc, hc);
+        st_shared_v4(os, hs);
+        st_shared_v4(oc + T2_H2R, rc);
+        st_shared_v4(os + T2_H2R, rs);
+        if (is_b) {
+          st_shared_v4(oc + T2_H2C, cf);
+          st_shared_v4(os + T2_H2C, sf);
         }
-        st_shared_v4(oc + T2_OFF_BC, cf);
-        st_shared_v4(os + T2_OFF_BC, sf);
       }
     }
+  };
+  trig(0);
+  trig(1);
+#pragma unroll
+  for (int i = 0; i < T2_GPAIRS; ++i) {
+    if (i + 2 < T2_GPAIRS) trig(i + 2);
+    split(i);
   }
 }
 
@@ -329,7 +365,7 @@ tc2_suffstats_kernel(rr_plan plan, const float* __restrict__ X,
         mbar_wait_cl(&sb.x_full[xs], (g / T2_XSTAGES) & 1);
         mbar_wait_cl(&sb.u_empty, (g & 1) ^ 1);
         tc_fence_after_sync();
-        if (lane == 0) {
+        if (elect_one()) {
           const uint32_t x_hi = smem_u32(smem + T2_SMEM_X + xs * 2 * T2_X_BYTES);
           const uint32_t x_lo = x_hi + T2_X_BYTES;
           const uint64_t dwh = make_desc_sw128(w_hi), dwl = make_desc_sw128(w_lo);
@@ -351,24 +387,39 @@ tc2_suffstats_kernel(rr_plan plan, const float* __restrict__ X,
         const int nsl = (int)((it.r1 - it.r0 + T2_SLAB - 1) / T2_SLAB);
         constexpr int SPC = T2_CHAIN / T2_SLAB;
         mbar_wait_cl(&sb.w_full, itc & 1);
+        // Tensor-pipe order  P(0) P(1) | P(2) G(0) | P(3) G(1) | ...  (P = projection,
+        // G = Gram update).  U is single-buffered, so P(t+2) can only be issued once
+        // the generators have pulled U(t+1) into registers -- which they do right
+        // after publishing Phi(t).  Issuing it BEFORE G(t) keeps the projection of
+        // the next slab off the critical path: with the order P(t+1) G(t-1) ... the
+        // generators could not start slab t+1 before G(t-1) had drained through the
+        // pipe, and the slab period became (generate + Gram + projection)/2.
         issue_mma1(gs);
+        if (nsl > 1) issue_mma1(gs + 1);
         for (int t = 0; t < nsl; ++t, ++gs) {
-          if (t + 1 < nsl) issue_mma1(gs + 1);
           const bool first = (t % SPC) == 0;
           const bool last = (t % SPC) == SPC - 1 || t == nsl - 1;
           if (first) mbar_wait_cl(&sb.acc_empty, (gc & 1) ^ 1);
           const uint32_t ps = gs % T2_PSTAGES;
+          T2_TRACE(lane == 0, gs, 8);
           mbar_wait_cl(&sb.phi_full[ps], (gs / T2_PSTAGES) & 1);
+          T2_TRACE(lane == 0, gs, 9);
+          if (t + 2 < nsl) issue_mma1(gs + 2);
+          T2_TRACE(lane == 0, gs, 10);
           tc_fence_after_sync();
-          if (lane == 0) {
+          if (elect_one()) {
             const uint32_t base = smem_u32(smem + T2_SMEM_PHI + ps * T2_PHI_BYTES);
             const uint64_t dah = make_desc_sw128(base + T2_OFF_AH);
             const uint64_t dar = make_desc_sw128(base + T2_OFF_AR);
             const uint64_t dbh = make_desc_sw128(base + T2_OFF_BH);
             const uint64_t dbr = make_desc_sw128(base + T2_OFF_BR);
             const uint64_t dbc = make_desc_sw128(base + T2_OFF_BC);
+#ifdef RR_T2_EXP_NOMMA2    // experiment: one Gram MMA instead of twelve
+            for (int k = 0; k < 1; ++k) {
+#else
 #pragma unroll
             for (int k = 0; k < T2_SLAB / 16; ++k) {
+#endif
               const uint64_t adv = (uint64_t)(2 * k);
               const uint32_t acc = (first && k == 0) ? 0u : 1u;
               umma2_f16_ss(tmem + T2_TMEM_MAIN, dah + adv, dbh + adv, idesc2, acc);
@@ -379,6 +430,7 @@ tc2_suffstats_kernel(rr_plan plan, const float* __restrict__ X,
             if (last) umma2_commit_mc(&sb.acc_full);
           }
           __syncwarp();
+          T2_TRACE(lane == 0, gs, 11);
           if (last) ++gc;
         }
       }
@@ -446,14 +498,10 @@ tc2_suffstats_kernel(rr_plan plan, const float* __restrict__ X,
       asm volatile("cp.async.wait_group %0;" ::"n"(T2_RAW_AHEAD) : "memory");
       __syncwarp();
       const uint32_t rrow = raw0 + (gs % T2_RAW_STAGES) * T2_RAW_BYTES + 4u * (uint32_t)(lane * d);
-      float v[32];
-#pragma unroll
-      for (int i = 0; i < 32; ++i) {
-        v[i] = 0.0f;
-        if (i < d) asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v[i]) : "r"(rrow + 4u * i));
-      }
       const uint32_t xs = gs % T2_XSTAGES;
+      T2_TRACE(lane == 0, gs, 12);
       mbar_wait_cl(&sb.x_empty[xs], ((gs / T2_XSTAGES) & 1) ^ 1);
+      T2_TRACE(lane == 0, gs, 13);
       const uint32_t x_hi = smem_u32(smem + T2_SMEM_X + xs * 2 * T2_X_BYTES);
       const uint32_t x_lo = x_hi + T2_X_BYTES;
 #pragma unroll
@@ -464,9 +512,11 @@ tc2_suffstats_kernel(rr_plan plan, const float* __restrict__ X,
           uint32_t* lp = reinterpret_cast<uint32_t*>(&lo);
 #pragma unroll
           for (int k = 0; k < 4; ++k) {
-            const uint32_t hb = __float_as_uint(v[4 * c + k]) & 0xFFFFE000u;
+            float v = 0.0f;
+            if (4 * c + k < d) asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(rrow + 4u * (4 * c + k)));
+            const uint32_t hb = __float_as_uint(v) & 0xFFFFE000u;
             hp[k] = hb;
-            lp[k] = __float_as_uint(v[4 * c + k] - __uint_as_float(hb));
+            lp[k] = __float_as_uint(v - __uint_as_float(hb));
           }
           const uint32_t off = sw128_off((uint32_t)lane, (uint32_t)c);
           st_shared_v4(x_hi + off, hi);
@@ -476,15 +526,16 @@ tc2_suffstats_kernel(rr_plan plan, const float* __restrict__ X,
       fence_proxy_async_smem();
       __syncwarp();
       if (lane == 0) t2_arrive_leader(&sb.x_full[xs], crank);
+      T2_TRACE(lane == 0, gs, 14);
       advance(cs);
       ++gs;
     }
     asm volatile("cp.async.wait_group 0;" ::: "memory");
   } else if (warp >= T2_EPI_WARPS) {
     // ============================ generators ======================================
-    const int gw = warp - T2_EPI_WARPS;       // 0..7
+    const int gw = warp - T2_EPI_WARPS;       // 0..T2_GEN_WARPS-1
     const int q = warp & 3;                   // TMEM lane quadrant of this warp
-    const int h = gw >> 2;                    // which half of the slab's rows
+    const int h = gw >> 2;                    // which T2_GROWS-row group of the slab
     const int fl = 32 * q + lane;             // local frequency row 0..127
     const bool is_a = q < 2;                  // warp-uniform: lanes 0..63 feed the A tile
     const bool has_row = fl < T2_NA + T2_NB;  // lanes 120..127 own no feature rows
@@ -496,12 +547,11 @@ tc2_suffstats_kernel(rr_plan plan, const float* __restrict__ X,
       const uint32_t row_cos = is_a ? (uint32_t)fl : (uint32_t)(fl - T2_NA);
       const uint32_t row_sin = row_cos + (is_a ? (uint32_t)T2_NA : (uint32_t)T2_NB);
 #pragma unroll
-      for (int cg = 0; cg < 4; ++cg) {
-        cx.off_cos[cg] = sw128_off(row_cos, (uint32_t)(4 * h + cg));
-        cx.off_sin[cg] = sw128_off(row_sin, (uint32_t)(4 * h + cg));
+      for (int cg = 0; cg < T2_GCHUNKS; ++cg) {
+        const uint32_t tile = is_a ? (uint32_t)T2_OFF_AH : (uint32_t)T2_OFF_BH;
+        cx.off_cos[cg] = tile + sw128_off(row_cos, (uint32_t)(T2_GCHUNKS * h + cg));
+        cx.off_sin[cg] = tile + sw128_off(row_sin, (uint32_t)(T2_GCHUNKS * h + cg));
       }
-      cx.img_h = is_a ? (uint32_t)T2_OFF_AH : (uint32_t)T2_OFF_BH;
-      cx.img_r = is_a ? (uint32_t)T2_OFF_AR : (uint32_t)T2_OFF_BR;
     }
     uint32_t gs = 0;
     for (int item = pair; item < nitems; item += npairs) {
@@ -514,7 +564,7 @@ tc2_suffstats_kernel(rr_plan plan, const float* __restrict__ X,
       const bool all_valid = __all_sync(0xffffffffu, valid || !has_row);
       // ---- W tile of this item (previous item's projections have all completed:
       //      this thread has consumed their U) -------------------------------------
-      if (h == 0) {
+      if (h == 0) {   // one warp per lane quadrant writes the W tile
         for (int i = 0; i < 32; ++i) {
           const float w = (valid && i < d) ? __ldg(plan.Wt + (int64_t)i * ktot + theta) : 0.0f;
           const float hi = __uint_as_float(__float_as_uint(w) & 0xFFFFE000u);
@@ -533,37 +583,54 @@ tc2_suffstats_kernel(rr_plan plan, const float* __restrict__ X,
       for (int t = 0; t < nsl; ++t, ++gs) {
         const int64_t row0 = it.r0 + (int64_t)t * T2_SLAB;
         const int vrows = (int)((it.r1 - row0) < T2_SLAB ? (it.r1 - row0) : T2_SLAB);
-        float u[32];
+        float u[T2_GROWS];
+        const bool trw = lane == 0 && (gw == 0 || gw == T2_GEN_WARPS - 1);
+        const int trb = gw == 0 ? 0 : 16;
+        T2_TRACE(trw, gs, trb + 0);
         mbar_wait_cl(&sb.u_full, gs & 1);
+        T2_TRACE(trw, gs, trb + 1);
         tc_fence_after_sync();
-        tmem_ld32(tmem + ((uint32_t)(32 * q) << 16) + (uint32_t)(T2_TMEM_U + 32 * h), u);
+        tmem_ld16_nowait(tmem + ((uint32_t)(32 * q) << 16) + (uint32_t)(T2_TMEM_U + T2_GROWS * h), u);
+        tmem_ld_wait();
         tc_fence_before_sync();
         __syncwarp();
         if (lane == 0) t2_arrive_leader(&sb.u_empty, crank);
+        T2_TRACE(trw, gs, trb + 2);
 
         const uint32_t ps = gs % T2_PSTAGES;
         cx.base = smem_u32(smem + T2_SMEM_PHI + ps * T2_PHI_BYTES);
         cx.empty_bar = &sb.phi_empty[ps];
         cx.empty_parity = ((gs / T2_PSTAGES) & 1) ^ 1;
+#ifdef RR_T2_TRACE
+        cx.trw = trw;
+        cx.trs = (int)gs;
+        cx.trb = trb;
+#endif
         // rows of this thread's half that are live (tail slab / padded frequency)
-        const int lim = vrows - 32 * h;
-        const uint32_t live = !valid ? 0u : (lim >= 32 ? 0xffffffffu
+        const int lim = vrows - T2_GROWS * h;
+        const uint32_t live = !valid ? 0u : (lim >= T2_GROWS ? 0xffffffffu
                                              : (lim <= 0 ? 0u : ((1u << lim) - 1u)));
         const bool masked = !(all_valid && vrows == T2_SLAB);   // warp-uniform
-        uint64_t pc2 = 0ull, ps2 = 0ull;   // (+0.0f, +0.0f)
-        const float* yrow = want_p ? y + row0 + 32 * h : nullptr;
-        if (masked) t2_gen_slab<true>(cx, u, has_row ? live : 0u, !is_a, has_row, yrow, pc2, ps2);
-        else t2_gen_slab<false>(cx, u, live, !is_a, has_row, yrow, pc2, ps2);
-        if (want_p) {
+        if (want_p) {   // warp-uniform, designated A tiles only
+          uint64_t pc2 = 0ull, ps2 = 0ull;   // (+0.0f, +0.0f)
+          const float* yrow = y + row0 + T2_GROWS * h;
+          if (masked) t2_gen_slab<true, true>(cx, u, live, false, true, yrow, pc2, ps2);
+          else t2_gen_slab<false, true>(cx, u, live, false, true, yrow, pc2, ps2);
           float a0, a1, b0, b1;
           f2_unpack(pc2, a0, a1);
           f2_unpack(ps2, b0, b1);
           pc_d += (double)a0 + (double)a1;
           ps_d += (double)b0 + (double)b1;
+        } else {
+          uint64_t dummy0 = 0ull, dummy1 = 0ull;
+          if (masked) t2_gen_slab<true, false>(cx, u, has_row ? live : 0u, !is_a, has_row, nullptr, dummy0, dummy1);
+          else t2_gen_slab<false, false>(cx, u, live, !is_a, has_row, nullptr, dummy0, dummy1);
         }
+        T2_TRACE(trw, gs, trb + 3);
         fence_proxy_async_smem();
         __syncwarp();
         if (lane == 0) t2_arrive_leader(&sb.phi_full[ps], crank);
+        T2_TRACE(trw, gs, trb + 4);
       }
       if (want_p && valid) {
         const double a = (double)plan.amp[theta];
@@ -589,33 +656,46 @@ tc2_suffstats_kernel(rr_plan plan, const float* __restrict__ X,
         const int ty = within / T2_NB;
         const int th = T2_JB * it.jb + T2_NB * cc + within % T2_NB;
         const bool ok = th < ktot;
-        sb.ecol[j] = ok ? (ty ? plan.col_sin[th] : plan.col_cos[th]) : -1;
-        sb.etheta[j] = 2 * th + ty;           // ordering key
-        sb.eamp[j] = ok ? plan.amp[th] : 0.0f;
+        const int col = ok ? (ty ? plan.col_sin[th] : plan.col_cos[th]) : -1;
+        // invalid columns get a key below every row key, so one compare decides
+        sb.etab[j] = make_int2(ok ? col * D : 0, ok ? 2 * th + ty : -1);
       }
       asm volatile("bar.sync 2, 128;" ::: "memory");
       const int theta_a = T2_IB * it.ib + T2_NA * (int)crank + (L & 63);
       const bool valid_a = theta_a < ktot;
-      const int ca = valid_a ? (type_a ? plan.col_sin[theta_a] : plan.col_cos[theta_a]) : -1;
-      const double amp_a = valid_a ? (double)plan.amp[theta_a] : 0.0;
-      const int key_a = 2 * theta_a + type_a;
+      const int ca = valid_a ? (type_a ? plan.col_sin[theta_a] : plan.col_cos[theta_a]) : 0;
+      // rows that own no feature never pass the key test
+      const int key_a = valid_a ? 2 * theta_a + type_a : 0x7fffffff;
+      double* Tca = T + ca;
       for (int ch = 0; ch < nch; ++ch, ++gc) {
         mbar_wait_cl(&sb.acc_full, gc & 1);
         tc_fence_after_sync();
-#pragma unroll 1
-        for (int c0 = 0; c0 < T2_NCOL; c0 += 32) {
-          float vm[32], vx[32];
-          const uint32_t ta = tmem + ((uint32_t)(32 * q) << 16) + (uint32_t)c0;
-          tmem_ld32_nowait(ta + T2_TMEM_MAIN, vm);
-          tmem_ld32_nowait(ta + T2_TMEM_AUX, vx);
+        // Drain MAIN + AUX: the two are added in fp32 (MAIN is an exact multiple of
+        // 2^-12 below 2^12, so the rounding is <= 2^-13 absolute per 4096-row chain,
+        // unbiased), widened to float64 with integer ops (F2F would queue on the XU
+        // pipe behind the generators' MUFU work) and added to the scratch image with
+        // RED.F64.  Amplitudes are applied by the finalize kernel.
+        float vm[2][8], vx[2][8];
+        const uint32_t ta = tmem + ((uint32_t)(32 * q) << 16);
+        tmem_ld8_nowait(ta + T2_TMEM_MAIN, vm[0]);
+        tmem_ld8_nowait(ta + T2_TMEM_AUX, vx[0]);
+#pragma unroll 2
+        for (int c0 = 0; c0 < T2_NCOL; c0 += 8) {
+          const int cur = (c0 >> 3) & 1;
           tmem_ld_wait();
+          if (c0 + 8 < T2_NCOL) {
+            tmem_ld8_nowait(ta + (uint32_t)(T2_TMEM_MAIN + c0 + 8), vm[cur ^ 1]);
+            tmem_ld8_nowait(ta + (uint32_t)(T2_TMEM_AUX + c0 + 8), vx[cur ^ 1]);
+          }
 #pragma unroll
-          for (int r = 0; r < 32; ++r) {
-            const int j = c0 + r;
-            const int cb = sb.ecol[j];
-            if (ca >= 0 && cb >= 0 && key_a <= sb.etheta[j]) {
-              const double val = ((double)vm[r] + (double)vx[r]) * amp_a * (double)sb.eamp[j];
-              atomicAdd(T + (int64_t)cb * D + ca, val);
+          for (int r = 0; r < 8; ++r) {
+            const int2 tb = sb.etab[c0 + r];
+            if (key_a <= tb.y) {
+              const uint32_t b = __float_as_uint(vm[cur][r] + vx[cur][r]);
+              // fp32 -> fp64 bit pattern (normal numbers; +-0 becomes +-2^-127)
+              const uint32_t hi = (b & 0x80000000u) | (((b & 0x7fffffffu) >> 3) + 0x38000000u);
+              const double val = __hiloint2double((int)hi, (int)(b << 29));
+              atomicAdd(Tca + tb.x, val);
             }
           }
         }
@@ -633,10 +713,21 @@ tc2_suffstats_kernel(rr_plan plan, const float* __restrict__ X,
   if (warp == T2_WARP_MMA) tmem_dealloc_2cta(tmem, 512);
 }
 
-// G[i][j] += T[i][j] + T[j][i] (i != j), G[i][i] += T[i][i]: every unordered
-// feature pair was accumulated exactly once, at either position.
+// camp[c] = amplitude of feature column c (both columns of a frequency share it).
+__global__ void t2_colamp_kernel(rr_plan plan, float* __restrict__ camp) {
+  const int th = blockIdx.x * blockDim.x + threadIdx.x;
+  if (th < plan.ktot) {
+    const float a = plan.amp[th];
+    camp[plan.col_cos[th]] = a;
+    camp[plan.col_sin[th]] = a;
+  }
+}
+
+// G[i][j] += a_i a_j (T[i][j] + T[j][i]) (i != j), G[i][i] += a_i^2 T[i][i]: every
+// unordered feature pair was accumulated exactly once, at either position.
 __global__ void __launch_bounds__(256)
-t2_finalize_kernel(const double* __restrict__ T, double* __restrict__ G, int D) {
+t2_finalize_kernel(const double* __restrict__ T, const float* __restrict__ camp,
+                   double* __restrict__ G, int D) {
   __shared__ double tile[32][33];
   const int bx = blockIdx.x, by = blockIdx.y;
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
@@ -651,7 +742,8 @@ t2_finalize_kernel(const double* __restrict__ T, double* __restrict__ G, int D) 
     if (i < D && j < D) {
       const double a = T[(int64_t)i * D + j];
       const double b = tile[tx][r];            // T[j][i]
-      G[(int64_t)i * D + j] += (i == j) ? a : a + b;
+      const double w = (double)camp[i] * (double)camp[j];
+      G[(int64_t)i * D + j] += w * ((i == j) ? a : a + b);
     }
   }
 }
@@ -665,7 +757,8 @@ int tc_suffstats_supported(const rr_plan* pl) {
 }
 
 size_t tc_suffstats_workspace(const rr_plan* pl, int64_t) {
-  return align_up((size_t)pl->D * pl->D * sizeof(double), 256) + 256;
+  return align_up((size_t)pl->D * pl->D * sizeof(double), 256) +
+         align_up((size_t)pl->D * sizeof(float), 256) + 256;
 }
 
 int tc_suffstats(const rr_plan* pl, const float* X, const float* y, int64_t N,
@@ -673,12 +766,15 @@ int tc_suffstats(const rr_plan* pl, const float* X, const float* y, int64_t N,
   const int D = pl->D;
   Workspace W(ws, ws_bytes);
   double* T = W.take<double>((size_t)D * D);
-  if (!T) {
+  float* camp = W.take<float>((size_t)D);
+  if (!T || !camp) {
     set_error("tcgen05 suffstats workspace too small (need %zu bytes)",
               tc_suffstats_workspace(pl, N));
     return RR_ERR_WORKSPACE;
   }
   RR_CUDA_CHECK(cudaMemsetAsync(T, 0, (size_t)D * D * sizeof(double), st));
+  t2_colamp_kernel<<<(pl->ktot + 255) / 256, 256, 0, st>>>(*pl, camp);
+  RR_LAUNCH_CHECK("t2_colamp_kernel");
   const int NIB = (pl->ktot + T2_IB - 1) / T2_IB;
   const int NJB = (pl->ktot + T2_JB - 1) / T2_JB;
   int ntiles = 0;
@@ -708,9 +804,17 @@ int tc_suffstats(const rr_plan* pl, const float* X, const float* y, int64_t N,
                                    NJB, ntiles, (int)nitems, rpi));
   RR_LAUNCH_CHECK("tc2_suffstats_kernel");
   dim3 fg((D + 31) / 32, (D + 31) / 32);
-  t2_finalize_kernel<<<fg, 256, 0, st>>>(T, G, D);
+  t2_finalize_kernel<<<fg, 256, 0, st>>>(T, camp, G, D);
   RR_LAUNCH_CHECK("t2_finalize_kernel");
   return RR_OK;
 }
 
 }  // namespace rr
+
+#ifdef RR_T2_TRACE
+extern "C" int rr_debug_t2_trace(long long* out, int n) {
+  const int m = rr::T2_TR_NSLAB * rr::T2_TR_SLOTS;
+  cudaDeviceSynchronize();
+  return cudaMemcpyFromSymbol(out, rr::g_t2_trace, sizeof(long long) * (n < m ? n : m)) == cudaSuccess ? m : -1;
+}
+#endif
