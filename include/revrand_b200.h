@@ -141,18 +141,20 @@ int rr_slm_residual(const rr_plan* plan, const float* X, const float* y,
                     void* stream);
 
 /*
- * Gradient pass of StandardLinearModel._elbo wrt the basis hyper-parameters
- * (slm.py:193-197 with basis_functions.py:888-901 and apply_grad :109-152),
- * restated so that dPhi is never formed:
+ * Residual + gradient pass of StandardLinearModel._elbo wrt the basis
+ * hyper-parameters (slm.py:161-162 and :193-197 with basis_functions.py:888-901
+ * and apply_grad :109-152), restated so that dPhi is never formed:
+ *   Err = y - Phi m,  sqerr += sum Err^2,
  *   T = Err (x) m - Phi C,  Q[n,k] = -Phi_sin[n,k] T[n,col_cos k] + Phi_cos[n,k] T[n,col_sin k],
  *   R += X^T Q     (d, ktot) float64.
  * The caller turns R into d(-ELBO)/d lenscale_i = sum_k W[i,k] R[i,k] / (var * l_i^2).
- * err are the residuals from rr_slm_residual; m (D) and C (D,D) float32.
+ * m (D) and C (D,D) are float32; the residuals are computed from the same
+ * trigonometric values that feed the Phi C product (one pass over the rows).
  */
-int rr_slm_gradpass(const rr_plan* plan, const float* X, const float* err,
+int rr_slm_gradpass(const rr_plan* plan, const float* X, const float* y,
                     int64_t N, const float* m, const float* C, double* R,
-                    void* workspace, size_t workspace_bytes, int32_t engine,
-                    void* stream);
+                    double* sqerr, void* workspace, size_t workspace_bytes,
+                    int32_t engine, void* stream);
 
 /*
  * Predictive moments (slm.py:239-242): Ey = Phi m, Vf = rowsum((Phi C) * Phi).

@@ -50,7 +50,7 @@ SIGNATURES = {
     "rr_slm_suffstats": (C.c_int, [_PLAN, _P, _P, _I64, _P, _P, _P, _P, _SZ,
                                    _I32, _P]),
     "rr_slm_residual": (C.c_int, [_PLAN, _P, _P, _I64, _P, _P, _P, _P]),
-    "rr_slm_gradpass": (C.c_int, [_PLAN, _P, _P, _I64, _P, _P, _P, _P, _SZ,
+    "rr_slm_gradpass": (C.c_int, [_PLAN, _P, _P, _I64, _P, _P, _P, _P, _P, _SZ,
                                   _I32, _P]),
     "rr_slm_predict": (C.c_int, [_PLAN, _P, _I64, _P, _P, _P, _P, _P, _SZ, _P]),
     "rr_glm_step": (C.c_int, [_PLAN, _P, _P, _P, _I64, _P, _P, _I32, _P, _I32,

@@ -300,14 +300,16 @@ def slm_residual(plan, Xd, yd, m32, err=None, sqerr=None):
     return sqerr
 
 
-def slm_gradpass(plan, Xd, err, m32, C32, R, engine=_cabi.RR_ENGINE_AUTO):
+def slm_gradpass(plan, Xd, yd, m32, C32, R, sqerr,
+                 engine=_cabi.RR_ENGINE_AUTO):
+    """Residual + gradient pass: sqerr += sum (y - Phi m)^2, R += X^T Q."""
     lib = _cabi.load()
     N = Xd.shape[0]
     nb = _ws_bytes(_cabi.RR_OP_GRADPASS, N, plan, engine=engine)
     ws = workspace(nb)
-    check(lib.rr_slm_gradpass(C.byref(plan.struct), _ptr(Xd), _ptr(err), N,
-                              _ptr(m32), _ptr(C32), _ptr(R), _ptr(ws),
-                              ws.numel(), engine, _stream_ptr()),
+    check(lib.rr_slm_gradpass(C.byref(plan.struct), _ptr(Xd), _ptr(yd), N,
+                              _ptr(m32), _ptr(C32), _ptr(R), _ptr(sqerr),
+                              _ptr(ws), ws.numel(), engine, _stream_ptr()),
           "rr_slm_gradpass")
 
 

@@ -50,50 +50,6 @@ sumsq_kernel(const float* __restrict__ y, int64_t n, double* __restrict__ out) {
   if ((threadIdx.x & 31) == 0) atomicAdd(out, acc);
 }
 
-// One warp per row: f = phi_n . m computed from X directly (no Phi in HBM).
-// Lanes stride over frequencies; extras handled by lane 0.
-__global__ void __launch_bounds__(256)
-residual_kernel(rr_plan plan, const float* __restrict__ X,
-                const float* __restrict__ y, int64_t N,
-                const float* __restrict__ m, float* __restrict__ err,
-                double* __restrict__ sqerr) {
-  extern __shared__ float xs[];  // warps x d
-  const int warps = blockDim.x >> 5;
-  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int d = plan.d;
-  float* xr = xs + w * d;
-  double local = 0.0;
-  for (int64_t n = (int64_t)blockIdx.x * warps + w; n < N;
-       n += (int64_t)gridDim.x * warps) {
-    for (int i = lane; i < d; i += 32) xr[i] = X[n * d + i];
-    __syncwarp();
-    float f = 0.0f;
-    for (int k = lane; k < plan.ktot; k += 32) {
-      float u = 0.0f;
-      for (int i = 0; i < d; ++i)
-        u = fmaf(xr[i], __ldg(plan.Wt + (int64_t)i * plan.ktot + k), u);
-      float s, c;
-      sincos_turns(u, &s, &c);
-      float a = plan.amp[k];
-      f = fmaf(a * c, m[plan.col_cos[k]], f);
-      f = fmaf(a * s, m[plan.col_sin[k]], f);
-    }
-    for (int j = lane; j < plan.next; j += 32) {
-      int src = plan.ext_src[j];
-      float v = src >= 0 ? xr[src] : plan.ext_val[j];
-      f = fmaf(v, m[plan.ext_col[j]], f);
-    }
-    f = warp_sum(f);
-    float e = y[n] - f;
-    if (lane == 0) {
-      if (err) err[n] = e;
-      local += (double)e * (double)e;
-    }
-    __syncwarp();
-  }
-  if (lane == 0 && local != 0.0) atomicAdd(sqerr, local);
-}
-
 // T <- Err (x) m - T   restricted to what Q needs, then
 // Q[r,k] = -Phi_sin[r,k] * T[r,col_cos k] + Phi_cos[r,k] * T[r,col_sin k].
 // (amp and 1/sqrt(K) are already inside Phi.)
@@ -141,7 +97,7 @@ static size_t simt_ws(int op, int64_t N, const rr_plan* pl) {
   size_t q = align_up((size_t)R * (pl->ktot > 0 ? pl->ktot : 1) * 4, 256);
   switch (op) {
     case RR_OP_SUFFSTATS: return phi + 256;
-    case RR_OP_GRADPASS: return 2 * phi + q + 1024;
+    case RR_OP_GRADPASS: return 2 * phi + q + align_up((size_t)(N > 0 ? N : 1) * 4, 256) + 1024;
     case RR_OP_PREDICT: return 2 * phi + 1024;
     default: return 0;
   }
@@ -171,16 +127,21 @@ static int simt_suffstats(const rr_plan* pl, const float* X, const float* y,
   return RR_OK;
 }
 
-static int simt_gradpass(const rr_plan* pl, const float* X, const float* err,
+static int simt_gradpass(const rr_plan* pl, const float* X, const float* y,
                          int64_t N, const float* m, const float* C, double* Rout,
-                         void* ws, size_t wsb, cudaStream_t st) {
+                         double* sqerr, void* ws, size_t wsb, cudaStream_t st) {
   Workspace W(ws, wsb);
   int64_t R = N < SIMT_CHUNK ? N : SIMT_CHUNK;
   const int D = pl->D, d = pl->d, kt = pl->ktot;
   float* Phi = W.take<float>((size_t)R * D);
   float* T = W.take<float>((size_t)R * D);
   float* Q = W.take<float>((size_t)R * kt);
-  if (!Phi || !T || !Q) { set_error("gradpass workspace too small"); return RR_ERR_WORKSPACE; }
+  float* err = W.take<float>((size_t)N);
+  if (!Phi || !T || !Q || !err) { set_error("gradpass workspace too small"); return RR_ERR_WORKSPACE; }
+  {
+    int rc = phi_residual(pl, X, y, N, m, err, sqerr, st);
+    if (rc) return rc;
+  }
   for (int64_t s = 0; s < N; s += R) {
     int rows = (int)((N - s) < R ? (N - s) : R);
     int rc = launch_features(pl, X + s * d, rows, Phi, D, st);
@@ -230,32 +191,26 @@ extern "C" int rr_slm_residual(const rr_plan* plan, const float* X,
                                float* err, double* sqerr, void* stream) {
   RR_REQUIRE(plan && X && y && m && sqerr, "null pointer");
   if (N == 0) return RR_OK;
-  int warps = 8;
-  size_t smem = (size_t)warps * plan->d * sizeof(float);
-  int64_t want = (N + warps - 1) / warps;
-  int grid = (int)(want < (int64_t)sm_count() * 8 ? want : (int64_t)sm_count() * 8);
-  residual_kernel<<<grid, warps * 32, smem, (cudaStream_t)stream>>>(
-      *plan, X, y, N, m, err, sqerr);
-  RR_LAUNCH_CHECK("residual_kernel");
-  return RR_OK;
+  return phi_residual(plan, X, y, N, m, err, sqerr, (cudaStream_t)stream);
 }
 
 extern "C" int rr_slm_gradpass(const rr_plan* plan, const float* X,
-                               const float* err, int64_t N, const float* m,
-                               const float* C, double* R, void* workspace,
-                               size_t workspace_bytes, int32_t engine,
-                               void* stream) {
-  RR_REQUIRE(plan && X && err && m && C && R, "null pointer");
-  if (N == 0 || plan->ktot == 0) return RR_OK;
+                               const float* y, int64_t N, const float* m,
+                               const float* C, double* R, double* sqerr,
+                               void* workspace, size_t workspace_bytes,
+                               int32_t engine, void* stream) {
+  RR_REQUIRE(plan && X && y && m && C && R && sqerr, "null pointer");
+  if (N == 0) return RR_OK;
   cudaStream_t st = (cudaStream_t)stream;
+  if (plan->ktot == 0) return phi_residual(plan, X, y, N, m, nullptr, sqerr, st);
   const int use_tc = pick_engine(engine, plan, N);
   if (use_tc < 0) {
     set_error("tcgen05 engine does not support this plan");
     return RR_ERR_UNSUPPORTED;
   }
   if (use_tc)
-    return tc_gradpass(plan, X, err, N, m, C, R, workspace, workspace_bytes, st);
-  return simt_gradpass(plan, X, err, N, m, C, R, workspace, workspace_bytes, st);
+    return tc_gradpass(plan, X, y, N, m, C, R, sqerr, workspace, workspace_bytes, st);
+  return simt_gradpass(plan, X, y, N, m, C, R, sqerr, workspace, workspace_bytes, st);
 }
 
 extern "C" int rr_slm_predict(const rr_plan* plan, const float* X, int64_t N,

@@ -1,20 +1,30 @@
-// Gradient pass of the SLM log marginal likelihood on tcgen05.
+// Residual + gradient pass of the SLM log marginal likelihood on tcgen05.
 //
-//   T = Err (x) m - Phi C,   Q[n,k] = -Phi_sin[n,k] T[n,cos k] + Phi_cos[n,k] T[n,sin k],
-//   R += X^T Q                                            (d x ktot, float64)
+//   Err = y - Phi m,   sqerr = sum Err^2                        (slm.py:161-162)
+//   T = Err (x) m - Phi C,
+//   Q[n,k] = amp_k (-sin_nk T[n,cos k] + cos_nk T[n,sin k]),
+//   R += X^T Q                                                  (d x ktot, float64)
 //
 // dPhi (N x 2K x d in the reference, basis_functions.py:888-901) is never
 // formed, and Phi only ever exists as an fp16 row chunk in a scratch buffer
-// sized to stay L2-resident together with the fp16 image of C:
-//   1. prep   : Bt[fo][fj] = s * amp_fj * C[col fo][col fj]  (fp16, internal
-//               feature order = blocks of [64 cos | 64 sin]), s = 1/max|C|.
-//   2. per row chunk: phi kernel writes trig values (fp16) for the chunk;
-//      the GEMM kernel computes T' = Phi_chunk Bt^T on tcgen05 (cp.async ->
-//      128B-swizzled smem -> UMMA, fp32 accumulators in TMEM, 256 rows x 256
-//      output features per CTA) and its epilogue forms Q in registers, stages
-//      it through shared memory and contracts it with X, adding X^T Q to R.
+// sized to stay L2-resident together with the fp16 image of C.  Per row chunk:
 //
-// Replaces: revrand/slm.py:193-197 + basis_functions.py:109-152, 888-901.
+//   1. phi_err_kernel: one pass over the chunk's (row, frequency) pairs on the
+//      CUDA cores: fp32 projection, exact range reduction, MUFU sin/cos.  It
+//      accumulates f = Phi m in fp32 from the very same trig values (so the
+//      residuals cost no extra transcendental work) and writes the fp16 Phi
+//      chunk TILE-MAJOR: every (256 rows x 64 features) block is one contiguous
+//      32 KB image already in the 128-byte-swizzled K-major layout tcgen05
+//      wants, so that the GEMM below loads an operand stage with a single
+//      cp.async.bulk instead of thousands of per-thread copies.
+//   2. gp2_kernel: persistent CTA pairs (cta_group::2, M = 256 rows, N = 256
+//      output features, K = all features) stream those images through a
+//      5-stage bulk-copy ring; accumulators are double-buffered in TMEM
+//      (2 x 256 columns) so that the epilogue of one tile (Q in registers,
+//      X^T Q on the CUDA cores, float64 atomics into R) overlaps the tensor
+//      work of the next.
+//
+// Replaces: revrand/slm.py:161-162, 193-197 + basis_functions.py:109-152, 888-901.
 #include "rr_common.cuh"
 #include "rr_tc.cuh"
 
@@ -22,25 +32,26 @@ namespace rr {
 
 using namespace tc;
 
-constexpr int GP_RM = 256;        // rows per CTA tile (two 128-lane accumulators)
-constexpr int GP_RN = 256;        // output features per CTA tile
-constexpr int GP_KT = 64;         // K extent per stage (one 128-byte line)
-constexpr int GP_STAGES = 3;
-constexpr int GP_TILE_BYTES = 256 * 128;
-constexpr int GP_STAGE_BYTES = 2 * GP_TILE_BYTES;
-constexpr int GP_THREADS = 32 + 128;
-constexpr int64_t GP_SCRATCH_BYTES = 32ll << 20;  // Phi chunk budget (L2 resident)
+constexpr int G2_TM = 256;              // rows per tile (128 per CTA of the pair)
+constexpr int G2_TN = 256;              // output features per tile
+constexpr int G2_KT = 64;               // reduction extent per stage (one 128-byte line)
+constexpr int G2_IMG = G2_TM * 128;     // one tile-major operand image: 32 KB
+constexpr int G2_HALF = G2_IMG / 2;     // what one CTA of the pair loads of it
+constexpr int G2_STAGES = 5;
+constexpr int G2_STAGE_BYTES = 2 * G2_HALF;   // A half + B half
+constexpr int G2_THREADS = 6 * 32;      // producer, MMA / relay, 4 epilogue warps
+constexpr int G2_QLD = 33;              // padded row length of the Q staging buffer
+constexpr int64_t G2_SCRATCH_BYTES = 40ll << 20;  // Phi chunk budget (L2 resident)
 
-__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) {
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src)
-               : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() {
-  asm volatile("cp.async.commit_group;" ::: "memory");
-}
-template <int N>
-__device__ __forceinline__ void cp_async_wait() {
-  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+// internal feature f -> (frequency, is_sin): blocks of [64 cos | 64 sin]
+__device__ __forceinline__ int feat_theta(int f) { return 64 * (f >> 7) + (f & 63); }
+__device__ __forceinline__ int feat_is_sin(int f) { return (f >> 6) & 1; }
+
+// byte offset of element (row, col) inside the tile-major image array whose
+// tiles are [row block of 256][k block of 64]
+__device__ __forceinline__ int64_t tile_off(int row, int col, int nkb) {
+  const int rb = row >> 8, r = row & 255, kb = col >> 6, c = col & 63;
+  return ((int64_t)rb * nkb + kb) * G2_IMG + sw128_off((uint32_t)r, (uint32_t)(c >> 3)) + (c & 7) * 2;
 }
 
 // ---- prep kernels -----------------------------------------------------------
@@ -55,13 +66,10 @@ __global__ void absmax_kernel(const float* __restrict__ C, int64_t n,
   if ((threadIdx.x & 31) == 0) atomicMax(out_bits, __float_as_uint(mx));
 }
 
-// internal feature f -> (frequency, is_sin)
-__device__ __forceinline__ int feat_theta(int f) { return 64 * (f >> 7) + (f & 63); }
-__device__ __forceinline__ int feat_is_sin(int f) { return (f >> 6) & 1; }
-
+// Bt[fo][fj] = s * amp_fj * C[col fo][col fj] as fp16, tile-major, s = 1/max|C|.
 __global__ void __launch_bounds__(256)
 prep_c_kernel(rr_plan plan, const float* __restrict__ C, int Dp,
-              const unsigned int* __restrict__ cmax_bits, __half* __restrict__ Bt) {
+              const unsigned int* __restrict__ cmax_bits, uint8_t* __restrict__ BtT) {
   const int fj = blockIdx.x * blockDim.x + threadIdx.x;
   const int fo = blockIdx.y;
   if (fj >= Dp) return;
@@ -74,206 +82,288 @@ prep_c_kernel(rr_plan plan, const float* __restrict__ C, int Dp,
     const int co = feat_is_sin(fo) ? plan.col_sin[to] : plan.col_cos[to];
     v = s * plan.amp[tj] * C[(int64_t)co * plan.D + cj];
   }
-  Bt[(int64_t)fo * Dp + fj] = __float2half_rn(v);
+  *reinterpret_cast<__half*>(BtT + tile_off(fo, fj, Dp / G2_KT)) = __float2half_rn(v);
 }
 
-// Phi chunk (raw trig, no amplitude) in internal order, fp16, rows padded with
-// zeros up to rows_pad.
-constexpr int PH_ROWS = 16;
+// ---- Phi chunk + residuals ----------------------------------------------------
+constexpr int PE_ROWS = 32;
+// One block = PE_ROWS rows; threads stride over frequencies.  STORE: write the
+// fp16 trig values tile-major (rows >= rows and padded frequencies as zeros).
+template <bool STORE>
 __global__ void __launch_bounds__(256)
-phi_half_kernel(rr_plan plan, const float* __restrict__ X, int rows, int rows_pad,
-                int Dp, __half* __restrict__ Ph) {
-  extern __shared__ float xs[];
-  const int d = plan.d;
-  const int n0 = blockIdx.x * PH_ROWS;
-  for (int t = threadIdx.x; t < PH_ROWS * d; t += blockDim.x) {
-    int r = t / d;
-    xs[t] = (n0 + r < rows) ? X[(int64_t)(n0 + r) * d + (t - r * d)] : 0.0f;
+phi_err_kernel(rr_plan plan, const float* __restrict__ X, const float* __restrict__ y,
+               int rows, int Dp, const float* __restrict__ m, uint8_t* __restrict__ PhT,
+               float* __restrict__ err, double* __restrict__ sqerr) {
+  extern __shared__ float xs[];            // PE_ROWS x d, then 8 x PE_ROWS partial sums
+  __shared__ float part[8][PE_ROWS];
+  const int d = plan.d, ktot = plan.ktot;
+  const int n0 = blockIdx.x * PE_ROWS;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  for (int t = tid; t < PE_ROWS * d; t += blockDim.x) {
+    const int r = t / d;
+    xs[t] = (n0 + r < rows) ? X[(int64_t)n0 * d + t] : 0.0f;
   }
   __syncthreads();
-  const int nth = Dp / 2;  // padded frequency count
-  for (int th = threadIdx.x; th < nth; th += blockDim.x) {
-    float u[PH_ROWS];
+  float f[PE_ROWS];
 #pragma unroll
-    for (int r = 0; r < PH_ROWS; ++r) u[r] = 0.0f;
-    const bool valid = th < plan.ktot;
+  for (int r = 0; r < PE_ROWS; ++r) f[r] = 0.0f;
+  const int nth = STORE ? Dp / 2 : ktot;   // padded frequency count when storing
+  const int nkb = Dp / G2_KT;
+  for (int th = tid; th < nth; th += blockDim.x) {
+    float u[PE_ROWS];
+#pragma unroll
+    for (int r = 0; r < PE_ROWS; ++r) u[r] = 0.0f;
+    const bool valid = th < ktot;
+    float mc = 0.0f, ms = 0.0f;
     if (valid) {
       for (int i = 0; i < d; ++i) {
-        float w = __ldg(plan.Wt + (int64_t)i * plan.ktot + th);
+        const float w = __ldg(plan.Wt + (int64_t)i * ktot + th);
 #pragma unroll
-        for (int r = 0; r < PH_ROWS; ++r) u[r] = fmaf(xs[r * d + i], w, u[r]);
+        for (int r = 0; r < PE_ROWS; ++r) u[r] = fmaf(xs[r * d + i], w, u[r]);
       }
+      const float a = plan.amp[th];
+      mc = a * m[plan.col_cos[th]];
+      ms = a * m[plan.col_sin[th]];
     }
     const int fc = 128 * (th >> 6) + (th & 63);
 #pragma unroll
-    for (int r = 0; r < PH_ROWS; ++r) {
-      if (n0 + r >= rows_pad) break;
+    for (int r = 0; r < PE_ROWS; ++r) {
       float s = 0.0f, c = 0.0f;
       if (valid && n0 + r < rows) {
-        float fr = (u[r] - rintf(u[r])) * 6.283185307179586f;
+        const float fr = (u[r] - rintf(u[r])) * 6.283185307179586f;
         s = __sinf(fr);
         c = __cosf(fr);
       }
-      Ph[(int64_t)(n0 + r) * Dp + fc] = __float2half_rn(c);
-      Ph[(int64_t)(n0 + r) * Dp + fc + 64] = __float2half_rn(s);
+      f[r] = fmaf(c, mc, fmaf(s, ms, f[r]));
+      if (STORE) {
+        *reinterpret_cast<__half*>(PhT + tile_off(n0 + r, fc, nkb)) = __float2half_rn(c);
+        *reinterpret_cast<__half*>(PhT + tile_off(n0 + r, fc + 64, nkb)) = __float2half_rn(s);
+      }
     }
+  }
+  // extra (non-trigonometric) columns: Linear / Bias bases
+  for (int j = tid; j < plan.next; j += blockDim.x) {
+    const int src = plan.ext_src[j];
+    const float mj = m[plan.ext_col[j]];
+#pragma unroll
+    for (int r = 0; r < PE_ROWS; ++r)
+      f[r] = fmaf(src >= 0 ? xs[r * d + src] : plan.ext_val[j], mj, f[r]);
+  }
+#pragma unroll
+  for (int r = 0; r < PE_ROWS; ++r) {
+    float v = f[r];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if (lane == 0) part[warp][r] = v;
+  }
+  __syncthreads();
+  if (warp == 0) {
+    float v = 0.0f;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) v += part[w][lane];
+    double e2 = 0.0;
+    if (n0 + lane < rows) {
+      const float e = y[n0 + lane] - v;
+      if (err) err[n0 + lane] = e;
+      e2 = (double)e * (double)e;
+    }
+    e2 = warp_sum(e2);
+    if (lane == 0 && sqerr) atomicAdd(sqerr, e2);
   }
 }
 
-// ---- GEMM + epilogue ---------------------------------------------------------
-template <int DP>
-__global__ void __launch_bounds__(GP_THREADS, 1)
-tc_gradpass_kernel(rr_plan plan, const float* __restrict__ X,
-                   const float* __restrict__ err, int rows,
-                   const __half* __restrict__ Ph, const __half* __restrict__ Bt,
-                   int Dp, const float* __restrict__ m,
-                   const unsigned int* __restrict__ cmax_bits,
-                   double* __restrict__ R) {
+// ---- GEMM + fused epilogue ------------------------------------------------------
+struct G2Bars {
+  uint64_t full[G2_STAGES];        // own bulk copies landed (complete_tx)
+  uint64_t peer_full[G2_STAGES];   // leader only: the peer CTA's copies landed
+  uint64_t empty[G2_STAGES];       // multicast commit: stage consumed by the MMAs
+  uint64_t acc_full[2];            // multicast commit: accumulator buffer complete
+  uint64_t acc_empty[2];           // leader waits; count 8 (epilogue warps of both CTAs)
+  uint32_t tmem_base;
+};
+
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)),
+               "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes,
+                                         uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::
+          "r"(dst),
+      "l"(src), "r"(bytes), "r"(smem_u32(bar))
+      : "memory");
+}
+
+template <int IG>   // input dimensions per reducing warp: d <= 4 * IG
+__global__ void __launch_bounds__(G2_THREADS, 1)
+gp2_kernel(rr_plan plan, const float* __restrict__ X, const float* __restrict__ err,
+           int rows, int RB, int FB, const uint8_t* __restrict__ PhT,
+           const uint8_t* __restrict__ BtT, const float* __restrict__ m,
+           const unsigned int* __restrict__ cmax_bits, double* __restrict__ R) {
+  constexpr int DPAD = 4 * IG;
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* tiles = reinterpret_cast<uint8_t*>(
+  uint8_t* smem = reinterpret_cast<uint8_t*>(
       (reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  __shared__ uint64_t full[GP_STAGES], empty[GP_STAGES], acc_full;
-  __shared__ uint32_t tmem_slot;
-  __shared__ float m_loc[GP_RN];
-  __shared__ float amp_loc[GP_RN / 2];
-  __shared__ float err_loc[GP_RM];
+  __shared__ G2Bars sb;
+  __shared__ float m_loc[G2_TN];
+  __shared__ float amp_loc[G2_TN / 2];
+  __shared__ float err_loc[G2_TM / 2];
+  float* Qs = reinterpret_cast<float*>(smem + G2_STAGES * G2_STAGE_BYTES);   // [2][128][33]
+  float* xs = Qs + 2 * 128 * G2_QLD;                                          // [128][DPAD]
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int ob = blockIdx.x;            // output feature block
-  const int rb = blockIdx.y;            // row block
-  const int row0 = rb * GP_RM;
-  const int nk = Dp / GP_KT;
+  const uint32_t crank = cluster_ctarank();
+  const int pair = blockIdx.x >> 1, npairs = gridDim.x >> 1;
+  const int nkb = FB * (G2_TN / G2_KT);     // k blocks over all Dp features
+  const int ntiles = RB * FB;
   const int d = plan.d, ktot = plan.ktot;
 
   if (tid == 0) {
-    for (int s = 0; s < GP_STAGES; ++s) {
-      mbar_init(&full[s], 128);
-      mbar_init(&empty[s], 1);
+    for (int s = 0; s < G2_STAGES; ++s) {
+      mbar_init(&sb.full[s], 1);
+      mbar_init(&sb.peer_full[s], 1);
+      mbar_init(&sb.empty[s], 1);
     }
-    mbar_init(&acc_full, 1);
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(&sb.acc_full[b], 1);
+      mbar_init(&sb.acc_empty[b], 8);
+    }
     mbar_fence_init();
   }
-  if (warp == 0) tmem_alloc(&tmem_slot, 512);
+  if (warp == 1) tmem_alloc_2cta(&sb.tmem_base, 512);
   tc_fence_before_sync();
   __syncthreads();
+  cluster_sync_all();
   tc_fence_after_sync();
-  const uint32_t tmem = tmem_slot;
+  const uint32_t tmem = sb.tmem_base;
 
   if (warp == 0) {
-    // ---------------- MMA issuer ------------------------------------------------
-    const uint32_t idesc = make_idesc_f16(128, GP_RN);
-    for (int kt = 0; kt < nk; ++kt) {
-      const int s = kt % GP_STAGES;
-      mbar_wait(&full[s], (kt / GP_STAGES) & 1);
-      tc_fence_after_sync();
-      if (lane == 0) {
-        const uint32_t a0 = smem_u32(tiles + s * GP_STAGE_BYTES);
-        const uint32_t b0 = a0 + GP_TILE_BYTES;
-        const uint64_t da0 = make_desc_sw128(a0);
-        const uint64_t da1 = make_desc_sw128(a0 + 128 * 128);
-        const uint64_t db = make_desc_sw128(b0);
-#pragma unroll
-        for (int k = 0; k < GP_KT / 16; ++k) {
-          const uint64_t adv = (uint64_t)(2 * k);
-          umma_f16_ss(tmem, da0 + adv, db + adv, idesc, (kt | k) != 0);
-          umma_f16_ss(tmem + GP_RN, da1 + adv, db + adv, idesc, (kt | k) != 0);
+    // ============================ producer (both CTAs) ============================
+    if (elect_one()) {
+      uint32_t g = 0;
+      for (int t = pair; t < ntiles; t += npairs) {
+        const int rb = t / FB, fb = t - rb * FB;
+        const uint8_t* a_src = PhT + ((int64_t)rb * nkb) * G2_IMG + (int64_t)crank * G2_HALF;
+        const uint8_t* b_src = BtT + ((int64_t)fb * nkb) * G2_IMG + (int64_t)crank * G2_HALF;
+        for (int kb = 0; kb < nkb; ++kb, ++g) {
+          const uint32_t s = g % G2_STAGES;
+          mbar_wait_cl(&sb.empty[s], ((g / G2_STAGES) & 1) ^ 1);
+          const uint32_t dst = smem_u32(smem + s * G2_STAGE_BYTES);
+          mbar_expect_tx(&sb.full[s], G2_STAGE_BYTES);
+          bulk_g2s(dst, a_src + (int64_t)kb * G2_IMG, G2_HALF, &sb.full[s]);
+          bulk_g2s(dst + G2_HALF, b_src + (int64_t)kb * G2_IMG, G2_HALF, &sb.full[s]);
         }
-        umma_commit(&empty[s]);
-        if (kt == nk - 1) umma_commit(&acc_full);
       }
-      __syncwarp();
+    }
+  } else if (warp == 1) {
+    if (crank == 0) {
+      // ========================== MMA issuer (leader CTA) ==========================
+      const uint32_t idesc = make_idesc(0, G2_TM, G2_TN);
+      uint32_t g = 0, it = 0;
+      for (int t = pair; t < ntiles; t += npairs, ++it) {
+        const uint32_t buf = it & 1;
+        mbar_wait_cl(&sb.acc_empty[buf], ((it >> 1) & 1) ^ 1);
+        for (int kb = 0; kb < nkb; ++kb, ++g) {
+          const uint32_t s = g % G2_STAGES;
+          const uint32_t ph = (g / G2_STAGES) & 1;
+          mbar_wait_cl(&sb.full[s], ph);
+          mbar_wait_cl(&sb.peer_full[s], ph);
+          tc_fence_after_sync();
+          if (elect_one()) {
+            const uint32_t a0 = smem_u32(smem + s * G2_STAGE_BYTES);
+            const uint64_t da = make_desc_sw128(a0);
+            const uint64_t db = make_desc_sw128(a0 + G2_HALF);
+#pragma unroll
+            for (int k = 0; k < G2_KT / 16; ++k) {
+              const uint64_t adv = (uint64_t)(2 * k);
+              umma2_f16_ss(tmem + buf * G2_TN, da + adv, db + adv, idesc, (kb | k) != 0);
+            }
+            umma2_commit_mc(&sb.empty[s]);
+            if (kb == nkb - 1) umma2_commit_mc(&sb.acc_full[buf]);
+          }
+          __syncwarp();
+        }
+      }
+    } else {
+      // ===================== relay (peer CTA): my stage landed =====================
+      uint32_t g = 0;
+      for (int t = pair; t < ntiles; t += npairs) {
+        for (int kb = 0; kb < nkb; ++kb, ++g) {
+          const uint32_t s = g % G2_STAGES;
+          mbar_wait_cl(&sb.full[s], (g / G2_STAGES) & 1);
+          if (lane == 0) mbar_arrive_cluster(mapa_u32(smem_u32(&sb.peer_full[s]), 0));
+          __syncwarp();
+        }
+      }
     }
   } else {
-    // ---------------- loaders, then epilogue -----------------------------------
-    const int lt = tid - 32;  // 0..127
-    const __half* Abase = Ph + (int64_t)row0 * Dp;
-    const __half* Bbase = Bt + (int64_t)ob * GP_RN * Dp;
-    // tables for the epilogue
-    for (int j = lt; j < GP_RN; j += 128) {
-      int f = ob * GP_RN + j;
-      int th = feat_theta(f);
-      float mv = 0.0f;
-      if (th < ktot) mv = m[feat_is_sin(f) ? plan.col_sin[th] : plan.col_cos[th]];
-      m_loc[j] = mv;
-    }
-    {
-      int th = ob * (GP_RN / 2) + lt;
-      amp_loc[lt] = th < ktot ? plan.amp[th] : 0.0f;
-    }
-    for (int j = lt; j < GP_RM; j += 128)
-      err_loc[j] = (row0 + j < rows) ? err[row0 + j] : 0.0f;
-
-    auto issue_stage = [&](int kt) {
-      const int s = kt % GP_STAGES;
-      const uint32_t a0 = smem_u32(tiles + s * GP_STAGE_BYTES);
-      const uint32_t b0 = a0 + GP_TILE_BYTES;
-      const int k0 = kt * GP_KT;
-#pragma unroll 4
-      for (int j = 0; j < 16; ++j) {
-        const int idx = lt + 128 * j;       // 0..2047
-        const int row = idx >> 3, ch = idx & 7;
-        cp_async16(a0 + sw128_off(row, ch), Abase + (int64_t)row * Dp + k0 + ch * 8);
-        cp_async16(b0 + sw128_off(row, ch), Bbase + (int64_t)row * Dp + k0 + ch * 8);
-      }
-      cp_async_commit();
-    };
-
-    // software pipeline: keep GP_STAGES-1 stages of loads in flight
-    for (int kt = 0; kt < nk + GP_STAGES - 1; ++kt) {
-      if (kt < nk) {
-        const int s = kt % GP_STAGES;
-        mbar_wait(&empty[s], ((kt / GP_STAGES) & 1) ^ 1);
-        issue_stage(kt);
-      } else {
-        cp_async_commit();  // empty group keeps the wait arithmetic uniform
-      }
-      const int done = kt - (GP_STAGES - 1);
-      if (done >= 0) {
-        cp_async_wait<GP_STAGES - 1>();
-        fence_proxy_async_smem();
-        mbar_arrive(&full[done % GP_STAGES]);
-      }
-    }
-
-    // ---------------- epilogue ---------------------------------------------------
-    mbar_wait(&acc_full, 0);
-    tc_fence_after_sync();
-    // all MMAs have completed: stage memory is free for Q and X staging
-    float* Qs = reinterpret_cast<float*>(tiles);                       // [256][33]
-    float* xs = reinterpret_cast<float*>(tiles + 2 * GP_STAGE_BYTES);  // [256][DP]
-    for (int e = lt; e < GP_RM * DP; e += 128) {
-      int r = e / DP, i = e - r * DP;
-      xs[e] = (i < d && row0 + r < rows) ? X[(int64_t)(row0 + r) * d + i] : 0.0f;
-    }
+    // ============================ epilogue (warps 2..5) ============================
+    const int et = tid - 64;              // 0..127
+    const int q = warp & 3;               // TMEM lane quadrant this warp may read
+    const int rl = 32 * q + lane;         // accumulator lane = row inside this CTA's half
+    const int ew = warp - 2;              // which group of input dims this warp reduces
     const float cmax = __uint_as_float(*cmax_bits);
-    const int q = warp & 3;
-    constexpr int IG = DP / 4;  // input dims per reducing warp
-    const int ew = warp - 1;    // 0..3 : which group of input dims this warp reduces
-    for (int bb = 0; bb < 2; ++bb) {
-      for (int c = 0; c < 2; ++c) {
-        const int fcol = 128 * bb + 32 * c;  // first cos column of this chunk (tile-local)
-        for (int h = 0; h < 2; ++h) {
-          const int rl = 128 * h + 32 * q + lane;
-          float tcv[32], tsv[32];
-          const uint32_t taddr = tmem + ((uint32_t)(32 * q) << 16) + (uint32_t)(h * GP_RN + fcol);
-          tmem_ld32(taddr, tcv);
-          tmem_ld32(taddr + 64, tsv);
-          const __half* prow = Ph + (int64_t)(row0 + rl) * Dp + ob * GP_RN + fcol;
-          const float e_n = err_loc[rl];
+    uint32_t it = 0;
+    for (int t = pair; t < ntiles; t += npairs, ++it) {
+      const int rb = t / FB, fb = t - rb * FB;
+      const uint32_t buf = it & 1;
+      const int row0 = rb * G2_TM + 128 * (int)crank;       // first row of this CTA's half
+      // tables for this tile (the previous tile's readers are past their last barrier)
+      for (int j = et; j < G2_TN; j += 128) {
+        const int fo = fb * G2_TN + j;
+        const int th = feat_theta(fo);
+        float mv = 0.0f;
+        if (th < ktot) mv = m[feat_is_sin(fo) ? plan.col_sin[th] : plan.col_cos[th]];
+        m_loc[j] = mv;
+      }
+      {
+        const int th = fb * (G2_TN / 2) + et;
+        amp_loc[et] = th < ktot ? plan.amp[th] : 0.0f;
+        err_loc[et] = (row0 + et < rows) ? err[row0 + et] : 0.0f;
+      }
+      for (int e = et; e < 128 * DPAD; e += 128) {
+        const int r = e / DPAD, i = e - r * DPAD;
+        xs[e] = (i < d && row0 + r < rows) ? X[(int64_t)(row0 + r) * d + i] : 0.0f;
+      }
+      mbar_wait_cl(&sb.acc_full[buf], (it >> 1) & 1);
+      tc_fence_after_sync();
+      named_bar_sync(1, 128);
+      const float e_n = err_loc[rl];
+      const uint32_t tacc = tmem + ((uint32_t)(32 * q) << 16) + buf * G2_TN;
+      // Phi values of this row: tile-major images of k blocks 4 fb .. 4 fb + 3
+      const uint8_t* prow = PhT + ((int64_t)rb * nkb + 4 * fb) * G2_IMG;
+      const uint32_t prl = (uint32_t)(128 * (int)crank + rl);   // row inside the 256-row image
+#pragma unroll 1
+      for (int ch = 0; ch < 4; ++ch) {      // (bb, c): 32 frequencies per pass
+        const int bb = ch >> 1, c = ch & 1;
+        const int fcol = 128 * bb + 32 * c;            // first cos column (tile-local)
+        float tcv[32], tsv[32];
+        tmem_ld32_nowait(tacc + fcol, tcv);
+        tmem_ld32_nowait(tacc + fcol + 64, tsv);
+        tmem_ld_wait();
+        if (ch == 3) {                      // all TMEM reads of this tile are done
+          tc_fence_before_sync();
+          __syncwarp();
+          if (lane == 0) mbar_arrive_cluster(mapa_u32(smem_u32(&sb.acc_empty[buf]), 0));
+        }
+        float* Qb = Qs + (ch & 1) * 128 * G2_QLD;
+        const uint8_t* pc_img = prow + (int64_t)(2 * bb) * G2_IMG;       // cos k block
+        const uint8_t* ps_img = pc_img + G2_IMG;                         // sin k block
 #pragma unroll
-          for (int v4 = 0; v4 < 4; ++v4) {
-            uint4 pc = *reinterpret_cast<const uint4*>(prow + 8 * v4);
-            uint4 ps = *reinterpret_cast<const uint4*>(prow + 64 + 8 * v4);
-            const __half* hc = reinterpret_cast<const __half*>(&pc);
-            const __half* hs = reinterpret_cast<const __half*>(&ps);
+        for (int v4 = 0; v4 < 4; ++v4) {
+          const uint32_t off = sw128_off(prl, (uint32_t)(4 * c + v4));
+          const uint4 pc = *reinterpret_cast<const uint4*>(pc_img + off);
+          const uint4 ps = *reinterpret_cast<const uint4*>(ps_img + off);
+          const __half* hc = reinterpret_cast<const __half*>(&pc);
+          const __half* hs = reinterpret_cast<const __half*>(&ps);
 #pragma unroll
-            for (int r8 = 0; r8 < 8; ++r8) {
-              const int r = 8 * v4 + r8;
-              const float Tc = e_n * m_loc[fcol + r] - tcv[r] * cmax;
-              const float Ts = e_n * m_loc[fcol + 64 + r] - tsv[r] * cmax;
-              const float a = amp_loc[64 * bb + 32 * c + r];
-              Qs[rl * 33 + r] = a * (-__half2float(hs[r8]) * Tc + __half2float(hc[r8]) * Ts);
-            }
+          for (int r8 = 0; r8 < 8; ++r8) {
+            const int r = 8 * v4 + r8;
+            const float Tc = e_n * m_loc[fcol + r] - tcv[r] * cmax;
+            const float Ts = e_n * m_loc[fcol + 64 + r] - tsv[r] * cmax;
+            const float a = amp_loc[64 * bb + 32 * c + r];
+            Qb[rl * G2_QLD + r] = a * (-__half2float(hs[r8]) * Tc + __half2float(hc[r8]) * Ts);
           }
         }
         named_bar_sync(1, 128);
@@ -281,12 +371,13 @@ tc_gradpass_kernel(rr_plan plan, const float* __restrict__ X,
         float acc[IG];
 #pragma unroll
         for (int j = 0; j < IG; ++j) acc[j] = 0.0f;
-        for (int row = 0; row < GP_RM; ++row) {
-          const float qv = Qs[row * 33 + lane];
+#pragma unroll 4
+        for (int row = 0; row < 128; ++row) {
+          const float qv = Qb[row * G2_QLD + lane];
 #pragma unroll
-          for (int j = 0; j < IG; ++j) acc[j] = fmaf(xs[row * DP + ew * IG + j], qv, acc[j]);
+          for (int j = 0; j < IG; ++j) acc[j] = fmaf(xs[row * DPAD + ew * IG + j], qv, acc[j]);
         }
-        const int th = ob * (GP_RN / 2) + 64 * bb + 32 * c + lane;
+        const int th = fb * (G2_TN / 2) + 64 * bb + 32 * c + lane;
         if (th < ktot) {
 #pragma unroll
           for (int j = 0; j < IG; ++j) {
@@ -294,86 +385,137 @@ tc_gradpass_kernel(rr_plan plan, const float* __restrict__ X,
             if (i < d) atomicAdd(R + (int64_t)i * ktot + th, (double)acc[j]);
           }
         }
-        named_bar_sync(1, 128);
+        // The two Q buffers alternate, so the single barrier of the next pass already
+        // orders its writes after these reads.
       }
+      named_bar_sync(1, 128);   // tables and xs are rewritten by the next tile
     }
   }
   tc_fence_before_sync();
   __syncthreads();
-  if (warp == 0) tmem_dealloc(tmem, 512);
+  cluster_sync_all();
+  if (warp == 1) tmem_dealloc_2cta(tmem, 512);
 }
 
 // ---- host ---------------------------------------------------------------------
 // padded feature count: whole 256-feature output tiles (= 128 frequencies)
 static int gp_dp(const rr_plan* pl) { return ((pl->ktot + 127) / 128) * 256; }
 
-static int64_t gp_chunk_rows(const rr_plan* pl, int64_t N) {
-  const int Dp = gp_dp(pl);
-  int64_t rc = GP_SCRATCH_BYTES / ((int64_t)Dp * 2);
-  rc = rc / GP_RM * GP_RM;
-  if (rc < GP_RM) rc = GP_RM;
-  int64_t npad = (N + GP_RM - 1) / GP_RM * GP_RM;
-  return rc < npad ? rc : npad;
+// Row blocks (of 256 rows) per chunk: as many as the scratch budget allows, then
+// trimmed so that the tile count fills whole rounds of the persistent CTA pairs.
+static int gp_chunk_blocks(const rr_plan* pl, int64_t N) {
+  const int Dp = gp_dp(pl), FB = Dp / G2_TN;
+  int rbmax = (int)(G2_SCRATCH_BYTES / ((int64_t)G2_TM * Dp * 2));
+  if (rbmax < 1) rbmax = 1;
+  const int64_t need = (N + G2_TM - 1) / G2_TM;
+  if (need <= rbmax) return (int)need;
+  const int npairs = sm_count() / 2;
+  int best = rbmax;
+  double beste = 0.0;
+  for (int rb = rbmax; rb >= (rbmax + 1) / 2; --rb) {
+    const int tiles = rb * FB;
+    const double eff = (double)tiles / ((double)((tiles + npairs - 1) / npairs) * npairs);
+    if (eff > beste + 1e-9) {
+      beste = eff;
+      best = rb;
+    }
+  }
+  return best;
 }
 
 size_t tc_gradpass_workspace(const rr_plan* pl, int64_t N) {
   const int64_t Dp = gp_dp(pl);
-  return align_up((size_t)gp_chunk_rows(pl, N) * Dp * 2, 256) +
-         align_up((size_t)Dp * Dp * 2, 256) + 1024;
+  return align_up((size_t)gp_chunk_blocks(pl, N) * G2_TM * Dp * 2, 1024) +
+         align_up((size_t)Dp * Dp * 2, 1024) + align_up((size_t)N * 4, 256) + 8192;
 }
 
-template <int DP>
-static int launch_gp(const rr_plan* pl, const float* X, const float* err, int rows,
-                     const __half* Ph, const __half* Bt, int Dp, const float* m,
-                     const unsigned int* cmax, double* R, cudaStream_t st) {
-  size_t smem = GP_STAGES * GP_STAGE_BYTES + 1024;
-  RR_CUDA_CHECK(cudaFuncSetAttribute(tc_gradpass_kernel<DP>,
-                                     cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     (int)smem));
-  dim3 grid(Dp / GP_RN, (rows + GP_RM - 1) / GP_RM);
-  tc_gradpass_kernel<DP><<<grid, GP_THREADS, smem, st>>>(*pl, X, err, rows, Ph, Bt,
-                                                        Dp, m, cmax, R);
-  RR_LAUNCH_CHECK("tc_gradpass_kernel");
+template <int IG>
+static int launch_gp2(const rr_plan* pl, const float* X, const float* err, int rows,
+                      int RB, int FB, const uint8_t* PhT, const uint8_t* BtT,
+                      const float* m, const unsigned int* cmax, double* R,
+                      cudaStream_t st) {
+  const size_t smem = (size_t)G2_STAGES * G2_STAGE_BYTES + 2 * 128 * G2_QLD * 4 +
+                      128 * 4 * IG * 4 + 1024;
+  RR_CUDA_CHECK(cudaFuncSetAttribute(gp2_kernel<IG>,
+                                     cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int npairs = sm_count() / 2;
+  if (RB * FB < npairs) npairs = RB * FB;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(2 * npairs);
+  cfg.blockDim = dim3(G2_THREADS);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  RR_CUDA_CHECK(cudaLaunchKernelEx(&cfg, gp2_kernel<IG>, *pl, X, err, rows, RB, FB, PhT, BtT,
+                                   m, cmax, R));
+  RR_LAUNCH_CHECK("gp2_kernel");
   return RR_OK;
 }
 
-int tc_gradpass(const rr_plan* pl, const float* X, const float* err, int64_t N,
-                const float* m, const float* C, double* R, void* ws, size_t wsb,
-                cudaStream_t st) {
-  const int Dp = gp_dp(pl);
-  const int64_t RC = gp_chunk_rows(pl, N);
+// Residuals only (value-only evaluations; any feature plan):
+// sqerr += sum (y - Phi m)^2, optionally the N residuals.
+int phi_residual(const rr_plan* pl, const float* X, const float* y, int64_t N,
+                const float* m, float* err, double* sqerr, cudaStream_t st) {
+  const int64_t CH = 1 << 20;
+  for (int64_t s = 0; s < N; s += CH) {
+    const int rows = (int)((N - s) < CH ? (N - s) : CH);
+    phi_err_kernel<false><<<(rows + PE_ROWS - 1) / PE_ROWS, 256,
+                            PE_ROWS * pl->d * sizeof(float), st>>>(
+        *pl, X + s * pl->d, y + s, rows, 0, m, nullptr, err ? err + s : nullptr, sqerr);
+    RR_LAUNCH_CHECK("phi_err_kernel");
+  }
+  return RR_OK;
+}
+
+int tc_gradpass(const rr_plan* pl, const float* X, const float* y, int64_t N,
+                const float* m, const float* C, double* R, double* sqerr, void* ws,
+                size_t wsb, cudaStream_t st) {
+  const int Dp = gp_dp(pl), FB = Dp / G2_TN;
+  const int RBc = gp_chunk_blocks(pl, N);
+  const int64_t RC = (int64_t)RBc * G2_TM;
   Workspace W(ws, wsb);
-  __half* Ph = W.take<__half>((size_t)RC * Dp);
-  __half* Bt = W.take<__half>((size_t)Dp * Dp);
+  uint8_t* PhT = W.take<uint8_t>(align_up((size_t)RC * Dp * 2, 1024) + 1024);
+  uint8_t* BtT = W.take<uint8_t>(align_up((size_t)Dp * Dp * 2, 1024) + 1024);
+  float* err = W.take<float>((size_t)N);
   unsigned int* cmax = W.take<unsigned int>(1);
-  if (!Ph || !Bt || !cmax) {
-    set_error("tcgen05 gradpass workspace too small");
+  if (!PhT || !BtT || !err || !cmax) {
+    set_error("tcgen05 gradpass workspace too small (need %zu bytes)",
+              tc_gradpass_workspace(pl, N));
     return RR_ERR_WORKSPACE;
   }
+  // the bulk copies need 16-byte aligned images
+  PhT = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(PhT) + 1023) & ~(uintptr_t)1023);
+  BtT = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(BtT) + 1023) & ~(uintptr_t)1023);
   RR_CUDA_CHECK(cudaMemsetAsync(cmax, 0, sizeof(unsigned int), st));
   absmax_kernel<<<sm_count() * 4, 256, 0, st>>>(C, (int64_t)pl->D * pl->D, cmax);
   RR_LAUNCH_CHECK("absmax_kernel");
   {
     dim3 grid((Dp + 255) / 256, Dp);
-    prep_c_kernel<<<grid, 256, 0, st>>>(*pl, C, Dp, cmax, Bt);
+    prep_c_kernel<<<grid, 256, 0, st>>>(*pl, C, Dp, cmax, BtT);
     RR_LAUNCH_CHECK("prep_c_kernel");
   }
   const int d = pl->d;
   for (int64_t s = 0; s < N; s += RC) {
     const int rows = (int)((N - s) < RC ? (N - s) : RC);
-    const int rows_pad = (rows + GP_RM - 1) / GP_RM * GP_RM;
-    phi_half_kernel<<<(rows_pad + PH_ROWS - 1) / PH_ROWS, 256,
-                      PH_ROWS * d * sizeof(float), st>>>(*pl, X + s * d, rows,
-                                                         rows_pad, Dp, Ph);
-    RR_LAUNCH_CHECK("phi_half_kernel");
+    const int RB = (rows + G2_TM - 1) / G2_TM;
+    const int rows_pad = RB * G2_TM;
+    phi_err_kernel<true><<<rows_pad / PE_ROWS, 256, PE_ROWS * d * sizeof(float), st>>>(
+        *pl, X + s * d, y + s, rows, Dp, m, PhT, err + s, sqerr);
+    RR_LAUNCH_CHECK("phi_err_kernel");
     int rc;
     const float* Xc = X + s * d;
     const float* ec = err + s;
-    if (d <= 4) rc = launch_gp<4>(pl, Xc, ec, rows, Ph, Bt, Dp, m, cmax, R, st);
-    else if (d <= 8) rc = launch_gp<8>(pl, Xc, ec, rows, Ph, Bt, Dp, m, cmax, R, st);
-    else if (d <= 16) rc = launch_gp<16>(pl, Xc, ec, rows, Ph, Bt, Dp, m, cmax, R, st);
-    else if (d <= 24) rc = launch_gp<24>(pl, Xc, ec, rows, Ph, Bt, Dp, m, cmax, R, st);
-    else rc = launch_gp<32>(pl, Xc, ec, rows, Ph, Bt, Dp, m, cmax, R, st);
+    if (d <= 4) rc = launch_gp2<1>(pl, Xc, ec, rows, RB, FB, PhT, BtT, m, cmax, R, st);
+    else if (d <= 8) rc = launch_gp2<2>(pl, Xc, ec, rows, RB, FB, PhT, BtT, m, cmax, R, st);
+    else if (d <= 16) rc = launch_gp2<4>(pl, Xc, ec, rows, RB, FB, PhT, BtT, m, cmax, R, st);
+    else if (d <= 24) rc = launch_gp2<6>(pl, Xc, ec, rows, RB, FB, PhT, BtT, m, cmax, R, st);
+    else rc = launch_gp2<8>(pl, Xc, ec, rows, RB, FB, PhT, BtT, m, cmax, R, st);
     if (rc) return rc;
   }
   return RR_OK;

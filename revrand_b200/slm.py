@@ -54,7 +54,6 @@ class _SLMProblem(object):
         self.D = self.plan.D
         self.stats = eng.SuffStats(self.D)
         self.first = True
-        self.err = t.empty(self.Xd.shape[0], dtype=t.float32, device=self.Xd.device)
         nfl = self.plan.d * max(self.plan.ktot, 1) + 1
         self.rflat = t.zeros(nfl, dtype=t.float64, device=self.Xd.device)
         self.R = self.rflat[:nfl - 1].view(self.plan.d, max(self.plan.ktot, 1))
@@ -84,13 +83,13 @@ class _SLMProblem(object):
         out = {"m": m, "C": Cm, "slices": slices, "lam": lam_np}
         m32 = m.float().contiguous()
         self.rflat.zero_()
-        eng.slm_residual(plan, self.Xd, self.yd, m32, err=self.err,
-                         sqerr=self.sqerr)
         g = None
         if want_grad and plan.ktot:
             C32 = Cm.float().contiguous()
-            eng.slm_gradpass(plan, self.Xd, self.err, m32, C32, self.R,
-                             engine=self.engine)
+            eng.slm_gradpass(plan, self.Xd, self.yd, m32, C32, self.R,
+                             self.sqerr, engine=self.engine)
+        else:
+            eng.slm_residual(plan, self.Xd, self.yd, m32, sqerr=self.sqerr)
         eng.allreduce_sum_(self.rflat)
         parts = [logdet.reshape(1), trgc.reshape(1), self.sqerr, q]
         if want_grad and plan.ktot:

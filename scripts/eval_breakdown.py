@@ -43,10 +43,10 @@ res["solve_ms"], (Cm, logdet, m) = timed(lambda: eng.solve_posterior(st.G, st.p,
 res["trgc_ms"], _ = timed(lambda: (st.G * Cm).sum().item())
 m32 = m.float().contiguous(); C32 = Cm.float().contiguous()
 def f_res():
-    prob.rflat.zero_(); return eng.slm_residual(plan, prob.Xd, prob.yd, m32, err=prob.err, sqerr=prob.sqerr)
+    prob.rflat.zero_(); return eng.slm_residual(plan, prob.Xd, prob.yd, m32, sqerr=prob.sqerr)
 res["residual_ms"], _ = timed(f_res)
 def f_grad():
-    prob.rflat.zero_(); eng.slm_gradpass(plan, prob.Xd, prob.err, m32, C32, prob.R, engine=prob.engine)
+    prob.rflat.zero_(); eng.slm_gradpass(plan, prob.Xd, prob.yd, m32, C32, prob.R, prob.sqerr, engine=prob.engine)
 res["gradpass_ms"], _ = timed(f_grad)
 res["full_eval_ms"], _ = timed(lambda: prob.evaluate(0.02, [1.0], [4.0], want_grad=True))
 res["shape"] = dict(N=N, d=d, K=K)
