@@ -134,11 +134,11 @@ int rr_slm_suffstats(const rr_plan* plan, const float* X, const float* y,
 
 /*
  * Residual pass: sqerr += sum_n (y_n - phi_n^T m)^2 (slm.py:161-162);
- * if err != NULL also writes the N residuals.
+ * if err != NULL also writes the N residuals (and no workspace is needed).
  */
 int rr_slm_residual(const rr_plan* plan, const float* X, const float* y,
                     int64_t N, const float* m, float* err, double* sqerr,
-                    void* stream);
+                    void* workspace, size_t workspace_bytes, void* stream);
 
 /*
  * Residual + gradient pass of StandardLinearModel._elbo wrt the basis
@@ -199,6 +199,7 @@ int rr_glm_predict(const rr_plan* plan, const float* X, int64_t N,
 #define RR_OP_PREDICT 3
 #define RR_OP_GLM_STEP 4
 #define RR_OP_GLM_PREDICT 5
+#define RR_OP_RESIDUAL 6
 size_t rr_workspace_bytes(int32_t op, int64_t N, int32_t d, int32_t ktot,
                           int32_t D, int32_t aux0, int32_t aux1,
                           int32_t engine);

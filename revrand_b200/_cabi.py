@@ -16,7 +16,7 @@ LIB_PATH = os.path.join(_HERE, "lib", "librevrand_b200.so")
 
 RR_ENGINE_AUTO, RR_ENGINE_SIMT, RR_ENGINE_TCGEN05 = 0, 1, 2
 RR_OP_SUFFSTATS, RR_OP_GRADPASS, RR_OP_PREDICT = 1, 2, 3
-RR_OP_GLM_STEP, RR_OP_GLM_PREDICT = 4, 5
+RR_OP_GLM_STEP, RR_OP_GLM_PREDICT, RR_OP_RESIDUAL = 4, 5, 6
 (RR_LIK_GAUSSIAN, RR_LIK_BERNOULLI, RR_LIK_BINOMIAL, RR_LIK_POISSON_EXP,
  RR_LIK_POISSON_SOFTPLUS) = range(5)
 
@@ -49,7 +49,7 @@ SIGNATURES = {
                                        _P, _P, _P, _P]),
     "rr_slm_suffstats": (C.c_int, [_PLAN, _P, _P, _I64, _P, _P, _P, _P, _SZ,
                                    _I32, _P]),
-    "rr_slm_residual": (C.c_int, [_PLAN, _P, _P, _I64, _P, _P, _P, _P]),
+    "rr_slm_residual": (C.c_int, [_PLAN, _P, _P, _I64, _P, _P, _P, _P, _SZ, _P]),
     "rr_slm_gradpass": (C.c_int, [_PLAN, _P, _P, _I64, _P, _P, _P, _P, _P, _SZ,
                                   _I32, _P]),
     "rr_slm_predict": (C.c_int, [_PLAN, _P, _I64, _P, _P, _P, _P, _P, _SZ, _P]),

@@ -294,9 +294,10 @@ def slm_residual(plan, Xd, yd, m32, err=None, sqerr=None):
     N = Xd.shape[0]
     if sqerr is None:
         sqerr = t.zeros(1, dtype=t.float64, device=Xd.device)
+    ws = workspace(_ws_bytes(_cabi.RR_OP_RESIDUAL, N, plan))
     check(lib.rr_slm_residual(C.byref(plan.struct), _ptr(Xd), _ptr(yd), N,
-                              _ptr(m32), _ptr(err), _ptr(sqerr),
-                              _stream_ptr()), "rr_slm_residual")
+                              _ptr(m32), _ptr(err), _ptr(sqerr), _ptr(ws),
+                              ws.numel(), _stream_ptr()), "rr_slm_residual")
     return sqerr
 
 

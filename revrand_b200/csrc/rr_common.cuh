@@ -103,6 +103,7 @@ int tc_gradpass(const rr_plan* plan, const float* X, const float* y, int64_t N,
                 const float* m, const float* C, double* R, double* sqerr, void* ws,
                 size_t ws_bytes, cudaStream_t st);
 int phi_residual(const rr_plan* plan, const float* X, const float* y, int64_t N,
-                 const float* m, float* err, double* sqerr, cudaStream_t st);
+                 const float* m, float* err, double* sqerr, float* fbuf,
+                 cudaStream_t st);
 
 }  // namespace rr

@@ -99,6 +99,7 @@ static size_t simt_ws(int op, int64_t N, const rr_plan* pl) {
     case RR_OP_SUFFSTATS: return phi + 256;
     case RR_OP_GRADPASS: return 2 * phi + q + align_up((size_t)(N > 0 ? N : 1) * 4, 256) + 1024;
     case RR_OP_PREDICT: return 2 * phi + 1024;
+    case RR_OP_RESIDUAL: return align_up((size_t)(N > 0 ? N : 1) * 4, 256) + 512;
     default: return 0;
   }
 }
@@ -139,7 +140,7 @@ static int simt_gradpass(const rr_plan* pl, const float* X, const float* y,
   float* err = W.take<float>((size_t)N);
   if (!Phi || !T || !Q || !err) { set_error("gradpass workspace too small"); return RR_ERR_WORKSPACE; }
   {
-    int rc = phi_residual(pl, X, y, N, m, err, sqerr, st);
+    int rc = phi_residual(pl, X, y, N, m, err, sqerr, err, st);
     if (rc) return rc;
   }
   for (int64_t s = 0; s < N; s += R) {
@@ -188,10 +189,14 @@ extern "C" int rr_slm_suffstats(const rr_plan* plan, const float* X,
 
 extern "C" int rr_slm_residual(const rr_plan* plan, const float* X,
                                const float* y, int64_t N, const float* m,
-                               float* err, double* sqerr, void* stream) {
+                               float* err, double* sqerr, void* workspace,
+                               size_t workspace_bytes, void* stream) {
   RR_REQUIRE(plan && X && y && m && sqerr, "null pointer");
   if (N == 0) return RR_OK;
-  return phi_residual(plan, X, y, N, m, err, sqerr, (cudaStream_t)stream);
+  Workspace W(workspace, workspace_bytes);
+  float* fbuf = err ? err : W.take<float>((size_t)N);
+  if (!fbuf) { set_error("residual workspace too small"); return RR_ERR_WORKSPACE; }
+  return phi_residual(plan, X, y, N, m, err, sqerr, fbuf, (cudaStream_t)stream);
 }
 
 extern "C" int rr_slm_gradpass(const rr_plan* plan, const float* X,
@@ -202,7 +207,12 @@ extern "C" int rr_slm_gradpass(const rr_plan* plan, const float* X,
   RR_REQUIRE(plan && X && y && m && C && R && sqerr, "null pointer");
   if (N == 0) return RR_OK;
   cudaStream_t st = (cudaStream_t)stream;
-  if (plan->ktot == 0) return phi_residual(plan, X, y, N, m, nullptr, sqerr, st);
+  if (plan->ktot == 0) {
+    Workspace W(workspace, workspace_bytes);
+    float* fbuf = W.take<float>((size_t)N);
+    if (!fbuf) { set_error("gradpass workspace too small"); return RR_ERR_WORKSPACE; }
+    return phi_residual(plan, X, y, N, m, nullptr, sqerr, fbuf, st);
+  }
   const int use_tc = pick_engine(engine, plan, N);
   if (use_tc < 0) {
     set_error("tcgen05 engine does not support this plan");
@@ -246,7 +256,7 @@ extern "C" int rr_slm_predict(const rr_plan* plan, const float* X, int64_t N,
 namespace rr {
 size_t slm_workspace_bytes(int op, int64_t N, const rr_plan* pl, int engine) {
   size_t s = simt_ws(op, N, pl);
-  if (op != RR_OP_PREDICT && pick_engine(engine, pl, N) == 1) {
+  if (op != RR_OP_PREDICT && op != RR_OP_RESIDUAL && pick_engine(engine, pl, N) == 1) {
     size_t t = op == RR_OP_SUFFSTATS ? tc_suffstats_workspace(pl, N)
                                      : tc_gradpass_workspace(pl, N);
     return t > 256 ? t : 256;

@@ -85,69 +85,101 @@ prep_c_kernel(rr_plan plan, const float* __restrict__ C, int Dp,
   *reinterpret_cast<__half*>(BtT + tile_off(fo, fj, Dp / G2_KT)) = __float2half_rn(v);
 }
 
-// ---- Phi chunk + residuals ----------------------------------------------------
-constexpr int PE_ROWS = 32;
-// One block = PE_ROWS rows; threads stride over frequencies.  STORE: write the
-// fp16 trig values tile-major (rows >= rows and padded frequencies as zeros).
+// ---- Phi chunk + fitted values --------------------------------------------------
+// Block = PE_ROWS rows x PE_PAIRS frequency pairs; thread = one pair (2p, 2p+1)
+// for all rows of the block: every X value read from shared memory feeds two
+// FMAs, and the fp16 results leave as half2 so that a warp writes one whole
+// 128-byte line of the tile-major image per instruction.  The grid's y dimension
+// splits the frequencies, which gives a 4608-row chunk ~2300 blocks (the first
+// version ran one 8-warp block per SM and was latency bound); partial fitted
+// values f = Phi m are combined with float atomics in fbuf.
+constexpr int PE_ROWS = 16;
+constexpr int PE_PAIRS = 128;
 template <bool STORE>
-__global__ void __launch_bounds__(256)
-phi_err_kernel(rr_plan plan, const float* __restrict__ X, const float* __restrict__ y,
-               int rows, int Dp, const float* __restrict__ m, uint8_t* __restrict__ PhT,
-               float* __restrict__ err, double* __restrict__ sqerr) {
-  extern __shared__ float xs[];            // PE_ROWS x d, then 8 x PE_ROWS partial sums
-  __shared__ float part[8][PE_ROWS];
+__global__ void __launch_bounds__(PE_PAIRS)
+phi_fit_kernel(rr_plan plan, const float* __restrict__ X, int rows, int Dp,
+               const float* __restrict__ m, uint8_t* __restrict__ PhT,
+               float* __restrict__ fbuf) {
+  extern __shared__ float xs[];            // PE_ROWS x d
+  __shared__ float part[PE_PAIRS / 32][PE_ROWS];
   const int d = plan.d, ktot = plan.ktot;
   const int n0 = blockIdx.x * PE_ROWS;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  for (int t = tid; t < PE_ROWS * d; t += blockDim.x) {
+  for (int t = tid; t < PE_ROWS * d; t += PE_PAIRS) {
     const int r = t / d;
     xs[t] = (n0 + r < rows) ? X[(int64_t)n0 * d + t] : 0.0f;
   }
   __syncthreads();
-  float f[PE_ROWS];
+  const int th0 = 2 * (blockIdx.y * PE_PAIRS + tid);   // even frequency of this pair
+  const bool v0 = th0 < ktot, v1 = th0 + 1 < ktot;
+  float u0[PE_ROWS], u1[PE_ROWS];
 #pragma unroll
-  for (int r = 0; r < PE_ROWS; ++r) f[r] = 0.0f;
-  const int nth = STORE ? Dp / 2 : ktot;   // padded frequency count when storing
-  const int nkb = Dp / G2_KT;
-  for (int th = tid; th < nth; th += blockDim.x) {
-    float u[PE_ROWS];
+  for (int r = 0; r < PE_ROWS; ++r) u0[r] = u1[r] = 0.0f;
+  float mc0 = 0.0f, ms0 = 0.0f, mc1 = 0.0f, ms1 = 0.0f;
+  if (v0) {
+    for (int i = 0; i < d; ++i) {
+      const float w0 = __ldg(plan.Wt + (int64_t)i * ktot + th0);
+      const float w1 = v1 ? __ldg(plan.Wt + (int64_t)i * ktot + th0 + 1) : 0.0f;
 #pragma unroll
-    for (int r = 0; r < PE_ROWS; ++r) u[r] = 0.0f;
-    const bool valid = th < ktot;
-    float mc = 0.0f, ms = 0.0f;
-    if (valid) {
-      for (int i = 0; i < d; ++i) {
-        const float w = __ldg(plan.Wt + (int64_t)i * ktot + th);
-#pragma unroll
-        for (int r = 0; r < PE_ROWS; ++r) u[r] = fmaf(xs[r * d + i], w, u[r]);
+      for (int r = 0; r < PE_ROWS; ++r) {
+        const float x = xs[r * d + i];
+        u0[r] = fmaf(x, w0, u0[r]);
+        u1[r] = fmaf(x, w1, u1[r]);
       }
-      const float a = plan.amp[th];
-      mc = a * m[plan.col_cos[th]];
-      ms = a * m[plan.col_sin[th]];
     }
-    const int fc = 128 * (th >> 6) + (th & 63);
-#pragma unroll
-    for (int r = 0; r < PE_ROWS; ++r) {
-      float s = 0.0f, c = 0.0f;
-      if (valid && n0 + r < rows) {
-        const float fr = (u[r] - rintf(u[r])) * 6.283185307179586f;
-        s = __sinf(fr);
-        c = __cosf(fr);
-      }
-      f[r] = fmaf(c, mc, fmaf(s, ms, f[r]));
-      if (STORE) {
-        *reinterpret_cast<__half*>(PhT + tile_off(n0 + r, fc, nkb)) = __float2half_rn(c);
-        *reinterpret_cast<__half*>(PhT + tile_off(n0 + r, fc + 64, nkb)) = __float2half_rn(s);
-      }
+    const float a0 = plan.amp[th0];
+    mc0 = a0 * m[plan.col_cos[th0]];
+    ms0 = a0 * m[plan.col_sin[th0]];
+    if (v1) {
+      const float a1 = plan.amp[th0 + 1];
+      mc1 = a1 * m[plan.col_cos[th0 + 1]];
+      ms1 = a1 * m[plan.col_sin[th0 + 1]];
     }
   }
-  // extra (non-trigonometric) columns: Linear / Bias bases
-  for (int j = tid; j < plan.next; j += blockDim.x) {
-    const int src = plan.ext_src[j];
-    const float mj = m[plan.ext_col[j]];
+  // tile-major addresses: rows n0.. lie in one 256-row image (n0 % 16 == 0), the
+  // pair occupies 4 bytes of chunk (c >> 3) of the cos image and of the sin image
+  // (the next k block); the 16-byte chunk index is XORed with (row & 7).
+  uint8_t* img = nullptr;
+  uint32_t inner = 0, c4 = 0;
+  if (STORE) {
+    const int fc = 128 * (th0 >> 6) + (th0 & 63);     // internal cos column of th0
+    const int nkb = Dp / G2_KT;
+    img = PhT + ((int64_t)(n0 >> 8) * nkb + (fc >> 6)) * G2_IMG + (int64_t)(n0 & 255) * 128;
+    c4 = (uint32_t)((fc & 63) >> 3) << 4;
+    inner = (uint32_t)(fc & 7) * 2;
+  }
+  float f[PE_ROWS];
 #pragma unroll
-    for (int r = 0; r < PE_ROWS; ++r)
-      f[r] = fmaf(src >= 0 ? xs[r * d + src] : plan.ext_val[j], mj, f[r]);
+  for (int r = 0; r < PE_ROWS; ++r) {
+    float c0 = 0.0f, s0 = 0.0f, c1 = 0.0f, s1 = 0.0f;
+    const bool live = n0 + r < rows;
+    if (v0 && live) {
+      const float fr = (u0[r] - rintf(u0[r])) * 6.283185307179586f;
+      s0 = __sinf(fr);
+      c0 = __cosf(fr);
+    }
+    if (v1 && live) {
+      const float fr = (u1[r] - rintf(u1[r])) * 6.283185307179586f;
+      s1 = __sinf(fr);
+      c1 = __cosf(fr);
+    }
+    f[r] = fmaf(c0, mc0, fmaf(s0, ms0, fmaf(c1, mc1, s1 * ms1)));
+    if (STORE) {
+      // (n0 + r) & 7 == r & 7 because n0 is a multiple of 16
+      uint8_t* p = img + r * 128 + (c4 ^ ((uint32_t)(r & 7) << 4)) + inner;
+      *reinterpret_cast<__half2*>(p) = __floats2half2_rn(c0, c1);
+      *reinterpret_cast<__half2*>(p + G2_IMG) = __floats2half2_rn(s0, s1);
+    }
+  }
+  // extra (non-trigonometric) columns: Linear / Bias bases (first frequency slice only)
+  if (blockIdx.y == 0) {
+    for (int j = tid; j < plan.next; j += PE_PAIRS) {
+      const int src = plan.ext_src[j];
+      const float mj = m[plan.ext_col[j]];
+#pragma unroll
+      for (int r = 0; r < PE_ROWS; ++r)
+        f[r] = fmaf(src >= 0 ? xs[r * d + src] : plan.ext_val[j], mj, f[r]);
+    }
   }
 #pragma unroll
   for (int r = 0; r < PE_ROWS; ++r) {
@@ -157,18 +189,40 @@ phi_err_kernel(rr_plan plan, const float* __restrict__ X, const float* __restric
     if (lane == 0) part[warp][r] = v;
   }
   __syncthreads();
-  if (warp == 0) {
+  if (tid < PE_ROWS && n0 + tid < rows) {
     float v = 0.0f;
-    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) v += part[w][lane];
-    double e2 = 0.0;
-    if (n0 + lane < rows) {
-      const float e = y[n0 + lane] - v;
-      if (err) err[n0 + lane] = e;
-      e2 = (double)e * (double)e;
-    }
-    e2 = warp_sum(e2);
-    if (lane == 0 && sqerr) atomicAdd(sqerr, e2);
+#pragma unroll
+    for (int w = 0; w < PE_PAIRS / 32; ++w) v += part[w][tid];
+    atomicAdd(fbuf + n0 + tid, v);
   }
+}
+
+// err = y - f (optional), sqerr += sum (y - f)^2.
+__global__ void __launch_bounds__(256)
+resid_finish_kernel(const float* __restrict__ y, const float* __restrict__ fbuf, int64_t n,
+                    float* __restrict__ err, double* __restrict__ sqerr) {
+  double acc = 0.0;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    const float e = y[i] - fbuf[i];
+    if (err) err[i] = e;
+    acc += (double)e * (double)e;
+  }
+  acc = warp_sum(acc);
+  if ((threadIdx.x & 31) == 0 && acc != 0.0) atomicAdd(sqerr, acc);
+}
+
+static int launch_phi_fit(const rr_plan* pl, const float* X, int rows, int rows_pad, int Dp,
+                          const float* m, uint8_t* PhT, float* fbuf, cudaStream_t st) {
+  const int nth = PhT ? Dp / 2 : pl->ktot;             // padded frequency count when storing
+  int gy = (nth + 2 * PE_PAIRS - 1) / (2 * PE_PAIRS);
+  if (gy < 1) gy = 1;                                  // plans with no trig block: extras only
+  dim3 grid((PhT ? rows_pad : rows + PE_ROWS - 1) / PE_ROWS, gy);
+  const size_t smem = PE_ROWS * pl->d * sizeof(float);
+  if (PhT) phi_fit_kernel<true><<<grid, PE_PAIRS, smem, st>>>(*pl, X, rows, Dp, m, PhT, fbuf);
+  else phi_fit_kernel<false><<<grid, PE_PAIRS, smem, st>>>(*pl, X, rows, Dp, m, nullptr, fbuf);
+  RR_LAUNCH_CHECK("phi_fit_kernel");
+  return RR_OK;
 }
 
 // ---- GEMM + fused epilogue ------------------------------------------------------
@@ -459,17 +513,20 @@ static int launch_gp2(const rr_plan* pl, const float* X, const float* err, int r
 }
 
 // Residuals only (value-only evaluations; any feature plan):
-// sqerr += sum (y - Phi m)^2, optionally the N residuals.
+// sqerr += sum (y - Phi m)^2, optionally the N residuals.  fbuf: N floats of
+// scratch (overwritten).
 int phi_residual(const rr_plan* pl, const float* X, const float* y, int64_t N,
-                const float* m, float* err, double* sqerr, cudaStream_t st) {
+                 const float* m, float* err, double* sqerr, float* fbuf,
+                 cudaStream_t st) {
+  RR_CUDA_CHECK(cudaMemsetAsync(fbuf, 0, (size_t)N * sizeof(float), st));
   const int64_t CH = 1 << 20;
   for (int64_t s = 0; s < N; s += CH) {
     const int rows = (int)((N - s) < CH ? (N - s) : CH);
-    phi_err_kernel<false><<<(rows + PE_ROWS - 1) / PE_ROWS, 256,
-                            PE_ROWS * pl->d * sizeof(float), st>>>(
-        *pl, X + s * pl->d, y + s, rows, 0, m, nullptr, err ? err + s : nullptr, sqerr);
-    RR_LAUNCH_CHECK("phi_err_kernel");
+    int rc = launch_phi_fit(pl, X + s * pl->d, rows, rows, 0, m, nullptr, fbuf + s, st);
+    if (rc) return rc;
   }
+  resid_finish_kernel<<<sm_count() * 4, 256, 0, st>>>(y, fbuf, N, err, sqerr);
+  RR_LAUNCH_CHECK("resid_finish_kernel");
   return RR_OK;
 }
 
@@ -482,7 +539,7 @@ int tc_gradpass(const rr_plan* pl, const float* X, const float* y, int64_t N,
   Workspace W(ws, wsb);
   uint8_t* PhT = W.take<uint8_t>(align_up((size_t)RC * Dp * 2, 1024) + 1024);
   uint8_t* BtT = W.take<uint8_t>(align_up((size_t)Dp * Dp * 2, 1024) + 1024);
-  float* err = W.take<float>((size_t)N);
+  float* err = W.take<float>((size_t)N);      // fitted values, then residuals
   unsigned int* cmax = W.take<unsigned int>(1);
   if (!PhT || !BtT || !err || !cmax) {
     set_error("tcgen05 gradpass workspace too small (need %zu bytes)",
@@ -493,6 +550,7 @@ int tc_gradpass(const rr_plan* pl, const float* X, const float* y, int64_t N,
   PhT = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(PhT) + 1023) & ~(uintptr_t)1023);
   BtT = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(BtT) + 1023) & ~(uintptr_t)1023);
   RR_CUDA_CHECK(cudaMemsetAsync(cmax, 0, sizeof(unsigned int), st));
+  RR_CUDA_CHECK(cudaMemsetAsync(err, 0, (size_t)N * sizeof(float), st));
   absmax_kernel<<<sm_count() * 4, 256, 0, st>>>(C, (int64_t)pl->D * pl->D, cmax);
   RR_LAUNCH_CHECK("absmax_kernel");
   {
@@ -505,10 +563,11 @@ int tc_gradpass(const rr_plan* pl, const float* X, const float* y, int64_t N,
     const int rows = (int)((N - s) < RC ? (N - s) : RC);
     const int RB = (rows + G2_TM - 1) / G2_TM;
     const int rows_pad = RB * G2_TM;
-    phi_err_kernel<true><<<rows_pad / PE_ROWS, 256, PE_ROWS * d * sizeof(float), st>>>(
-        *pl, X + s * d, y + s, rows, Dp, m, PhT, err + s, sqerr);
-    RR_LAUNCH_CHECK("phi_err_kernel");
-    int rc;
+    int rc = launch_phi_fit(pl, X + s * d, rows, rows_pad, Dp, m, PhT, err + s, st);
+    if (rc) return rc;
+    // fitted values -> residuals (in place) + their sum of squares
+    resid_finish_kernel<<<(rows + 1023) / 1024, 256, 0, st>>>(y + s, err + s, rows, err + s, sqerr);
+    RR_LAUNCH_CHECK("resid_finish_kernel");
     const float* Xc = X + s * d;
     const float* ec = err + s;
     if (d <= 4) rc = launch_gp2<1>(pl, Xc, ec, rows, RB, FB, PhT, BtT, m, cmax, R, st);

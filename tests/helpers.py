@@ -69,3 +69,14 @@ def oracle_blocks(bases, hypers):
 def relerr(a, b):
     a, b = np.asarray(a, float), np.asarray(b, float)
     return np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-300)
+
+
+def max_phase(basis, X, ls):
+    """max |x . W / l| over the batch (radians) for a random-frequency basis;
+    0 for bases without an explicit frequency matrix (FastFood: Gaussian-like
+    phases of O(10) rad).  Used to scale fp32 phase tolerances."""
+    W = getattr(basis, "W", None)
+    if W is None:
+        return 0.0
+    lsf = np.broadcast_to(np.atleast_1d(np.asarray(ls, dtype=float)), (W.shape[0],))
+    return float(np.max(np.abs(np.asarray(X, dtype=float).dot(W / lsf[:, None]))))

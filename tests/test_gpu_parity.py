@@ -45,8 +45,7 @@ def test_transform_and_grad_vs_reference(golden, cls):
                 # carries a few fp32 ulps of ITS OWN magnitude (heavy-tailed
                 # Cauchy / Student-t frequencies reach |theta| ~ 1e4 rad):
                 # tolerance = 5e-6 on O(1/sqrt(K)) values + 4 ulp(theta_max).
-                ls_full = np.broadcast_to(np.atleast_1d(ls), (d,))
-                tmax = np.max(np.abs(X.dot(b.W / ls_full[:, None])))
+                tmax = helpers.max_phase(b, X, ls)
                 tol = 5e-6 + 2.4e-7 * tmax
                 assert np.max(np.abs(Phi - ref)) < tol, key
                 dPhi = b.grad(X, ls)
