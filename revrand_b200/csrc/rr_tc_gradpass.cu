@@ -40,7 +40,7 @@ constexpr int G2_HALF = G2_IMG / 2;     // what one CTA of the pair loads of it
 constexpr int G2_STAGES = 5;
 constexpr int G2_STAGE_BYTES = 2 * G2_HALF;   // A half + B half
 constexpr int G2_THREADS = 6 * 32;      // producer, MMA / relay, 4 epilogue warps
-constexpr int G2_QLD = 33;              // padded row length of the Q staging buffer
+constexpr int G2_RED = 4 * 32 * 32;     // floats of one cross-warp reduction buffer
 constexpr int64_t G2_SCRATCH_BYTES = 40ll << 20;  // Phi chunk budget (L2 resident)
 
 // internal feature f -> (frequency, is_sin): blocks of [64 cos | 64 sin]
@@ -263,8 +263,8 @@ gp2_kernel(rr_plan plan, const float* __restrict__ X, const float* __restrict__ 
   __shared__ float m_loc[G2_TN];
   __shared__ float amp_loc[G2_TN / 2];
   __shared__ float err_loc[G2_TM / 2];
-  float* Qs = reinterpret_cast<float*>(smem + G2_STAGES * G2_STAGE_BYTES);   // [2][128][33]
-  float* xs = Qs + 2 * 128 * G2_QLD;                                          // [128][DPAD]
+  float* red = reinterpret_cast<float*>(smem + G2_STAGES * G2_STAGE_BYTES);  // [2][4][DPAD][32]
+  float* xs = red + 2 * G2_RED;                                               // [128][DPAD]
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const uint32_t crank = cluster_ctarank();
@@ -401,7 +401,7 @@ gp2_kernel(rr_plan plan, const float* __restrict__ X, const float* __restrict__ 
           __syncwarp();
           if (lane == 0) mbar_arrive_cluster(mapa_u32(smem_u32(&sb.acc_empty[buf]), 0));
         }
-        float* Qb = Qs + (ch & 1) * 128 * G2_QLD;
+        // Q for this thread's row, 32 frequencies, in registers (reusing tcv)
         const uint8_t* pc_img = prow + (int64_t)(2 * bb) * G2_IMG;       // cos k block
         const uint8_t* ps_img = pc_img + G2_IMG;                         // sin k block
 #pragma unroll
@@ -417,30 +417,64 @@ gp2_kernel(rr_plan plan, const float* __restrict__ X, const float* __restrict__ 
             const float Tc = e_n * m_loc[fcol + r] - tcv[r] * cmax;
             const float Ts = e_n * m_loc[fcol + 64 + r] - tsv[r] * cmax;
             const float a = amp_loc[64 * bb + 32 * c + r];
-            Qb[rl * G2_QLD + r] = a * (-__half2float(hs[r8]) * Tc + __half2float(hc[r8]) * Ts);
+            tcv[r] = a * (-__half2float(hs[r8]) * Tc + __half2float(hc[r8]) * Ts);
           }
         }
-        named_bar_sync(1, 128);
-        // R[i, theta] += sum_rows x[row, i] * Q[row, theta]; lane = theta, warp = dim group
-        float acc[IG];
+        // 32 x 32 transpose inside the warp (5 butterfly stages of shuffles): lane =
+        // row, register = frequency  ->  lane = frequency, register = row.  The
+        // contraction over rows then needs only broadcast reads of X from shared
+        // memory; staging Q through shared memory cost more bandwidth than the
+        // tensor core's own operand reads.
 #pragma unroll
-        for (int j = 0; j < IG; ++j) acc[j] = 0.0f;
-#pragma unroll 4
-        for (int row = 0; row < 128; ++row) {
-          const float qv = Qb[row * G2_QLD + lane];
+        for (int b = 16; b >= 1; b >>= 1) {
+          const bool up = (lane & b) != 0;
 #pragma unroll
-          for (int j = 0; j < IG; ++j) acc[j] = fmaf(xs[row * DPAD + ew * IG + j], qv, acc[j]);
+          for (int k = 0; k < 32; ++k) {
+            if (!(k & b)) {
+              const float send = up ? tcv[k] : tcv[k | b];
+              const float recv = __shfl_xor_sync(0xffffffffu, send, b);
+              if (up) tcv[k] = recv;
+              else tcv[k | b] = recv;
+            }
+          }
         }
+        // acc[i] = sum over this warp's 32 rows of x[row, i] * Q[row, theta = lane]
+        float acc[DPAD];
+#pragma unroll
+        for (int i = 0; i < DPAD; ++i) acc[i] = 0.0f;
+        const float4* xq = reinterpret_cast<const float4*>(xs + (32 * q) * DPAD);
+#pragma unroll
+        for (int n = 0; n < 32; ++n) {
+#pragma unroll
+          for (int g4 = 0; g4 < IG; ++g4) {
+            const float4 xv = xq[n * IG + g4];
+            acc[4 * g4 + 0] = fmaf(xv.x, tcv[n], acc[4 * g4 + 0]);
+            acc[4 * g4 + 1] = fmaf(xv.y, tcv[n], acc[4 * g4 + 1]);
+            acc[4 * g4 + 2] = fmaf(xv.z, tcv[n], acc[4 * g4 + 2]);
+            acc[4 * g4 + 3] = fmaf(xv.w, tcv[n], acc[4 * g4 + 3]);
+          }
+        }
+        // cross-warp (row quadrant) reduction through shared memory, then one
+        // float64 atomic per (dimension, frequency) of the pass
+        float* rb_ = red + (ch & 1) * G2_RED + ew * (32 * 32);
+#pragma unroll
+        for (int i = 0; i < DPAD; ++i) rb_[i * 32 + lane] = acc[i];
+        named_bar_sync(1, 128);
         const int th = fb * (G2_TN / 2) + 64 * bb + 32 * c + lane;
         if (th < ktot) {
+          const float* r0_ = red + (ch & 1) * G2_RED;
 #pragma unroll
           for (int j = 0; j < IG; ++j) {
             const int i = ew * IG + j;
-            if (i < d) atomicAdd(R + (int64_t)i * ktot + th, (double)acc[j]);
+            if (i < d) {
+              const float v = r0_[i * 32 + lane] + r0_[1024 + i * 32 + lane] +
+                              r0_[2048 + i * 32 + lane] + r0_[3072 + i * 32 + lane];
+              atomicAdd(R + (int64_t)i * ktot + th, (double)v);
+            }
           }
         }
-        // The two Q buffers alternate, so the single barrier of the next pass already
-        // orders its writes after these reads.
+        // The two reduction buffers alternate, so the barrier of the next pass
+        // already orders its writes after these reads.
       }
       named_bar_sync(1, 128);   // tables and xs are rewritten by the next tile
     }
@@ -488,7 +522,7 @@ static int launch_gp2(const rr_plan* pl, const float* X, const float* err, int r
                       int RB, int FB, const uint8_t* PhT, const uint8_t* BtT,
                       const float* m, const unsigned int* cmax, double* R,
                       cudaStream_t st) {
-  const size_t smem = (size_t)G2_STAGES * G2_STAGE_BYTES + 2 * 128 * G2_QLD * 4 +
+  const size_t smem = (size_t)G2_STAGES * G2_STAGE_BYTES + 2 * G2_RED * 4 +
                       128 * 4 * IG * 4 + 1024;
   RR_CUDA_CHECK(cudaFuncSetAttribute(gp2_kernel<IG>,
                                      cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
