@@ -10,8 +10,8 @@
 //         256 frequencies (128 per CTA) x 64 rows, accumulators in TMEM.
 //   generator warps: tcgen05.ld U, exact range reduction in turns, sin/cos,
 //         and split every trigonometric value c into
-//             h1 = c rounded to the 2^-6 grid   (7-bit fixed point)
-//             r  = fp16(c - h1)                  (|r| <= 2^-7)
+//             h1 = c rounded to the 2^-5 grid   (6-bit fixed point)
+//             r  = fp16(c - h1)                  (|r| <= 2^-6)
 //             cf = fp16(c)
 //         written straight into 128B-swizzled K-major fp16 operand tiles.
 //   MMA#2 (kind::f16):   MAIN += H1_a H1_b^T                      (exact)
@@ -21,11 +21,11 @@
 // with truncation (measured with rr_tcgen05_accum_probe: aligned to the
 // accumulator exponent with two guard bits, then rounded toward zero), which
 // biases long all-positive sums such as the diagonal of G by ~1e-5 after a few
-// thousand rows.  Products of 2^-6-grid values are multiples of 2^-12 and their
-// running sum stays below 2^12 for 4096 rows, so every partial sum of MAIN is
+// thousand rows.  Products of 2^-5-grid values are multiples of 2^-10 and their
+// running sum stays below 2^14 for 16384 rows, so every partial sum of MAIN is
 // exactly representable and nothing is ever truncated; AUX only holds terms
-// <= 2^-7 whose truncation is far below fp32 resolution of the result.  Every
-// 4096 rows the two accumulators are drained, combined in float64 and added to
+// <= 2^-6 whose truncation is far below fp32 resolution of the result.  Every
+// 16384 rows the two accumulators are drained, combined and added to
 // a float64 scratch image of G.
 //
 // The tile set covers every unordered feature pair exactly once (rows = 128
@@ -49,9 +49,9 @@ constexpr int T2_JB = 2 * T2_NB;     // frequencies per column block (pair)
 constexpr int T2_NCOL = 4 * T2_NB;   // 224 accumulator columns
 constexpr int T2_XSTAGES = 3;
 constexpr int T2_PSTAGES = 2;
-constexpr int T2_CHAIN = 4096;       // rows per exact accumulation chain
-constexpr int T2_SUPER = 32768;      // rows per work item (8 chains)
-constexpr float T2_GRID_MAGIC = 196608.0f;  // 1.5 * 2^17: (c + M) - M rounds to 2^-6
+constexpr int T2_CHAIN = 16384;      // rows per exact accumulation chain
+constexpr int T2_SUPER = 32768;      // rows per work item (2 chains)
+constexpr float T2_GRID_MAGIC = 393216.0f;  // 1.5 * 2^18: (c + M) - M rounds to 2^-5
 constexpr float T2_RINT_MAGIC = 12582912.0f;  // 1.5 * 2^23
 constexpr float T2_TWO_PI = 6.283185307179586f;
 
@@ -117,8 +117,11 @@ struct T2Bars {
   uint64_t w_full;                // leader waits; count 8 (4 writer warps per CTA)
   uint64_t u_full;                // multicast commit
   uint64_t u_empty;               // leader waits; count 16 (generator warps)
-  uint64_t phi_full[T2_PSTAGES];  // leader waits; count 16
-  uint64_t phi_empty[T2_PSTAGES]; // multicast commit
+  // one barrier per (stage, 16-row k-step): generator group h writes exactly the
+  // K = 16 columns that MMA k-step h reads, so the tensor pipe can start on a slab
+  // as soon as its first group is done and no group waits for another's slot
+  uint64_t phi_full[T2_PSTAGES][T2_GSPLIT];   // leader waits; count 8 (4 warps x 2 CTAs)
+  uint64_t phi_empty[T2_PSTAGES][T2_GSPLIT];  // multicast commit
   uint64_t acc_full;              // multicast commit
   uint64_t acc_empty;             // leader waits; count 8 (epilogue warps)
   uint32_t tmem_base;
@@ -337,8 +340,10 @@ tc2_suffstats_kernel(rr_plan plan, const float* __restrict__ X,
     mbar_init(&sb.u_full, 1);
     mbar_init(&sb.u_empty, 2 * T2_GEN_WARPS);
     for (int s = 0; s < T2_PSTAGES; ++s) {
-      mbar_init(&sb.phi_full[s], 2 * T2_GEN_WARPS);
-      mbar_init(&sb.phi_empty[s], 1);
+      for (int h = 0; h < T2_GSPLIT; ++h) {
+        mbar_init(&sb.phi_full[s][h], 2 * 4);
+        mbar_init(&sb.phi_empty[s][h], 1);
+      }
     }
     mbar_init(&sb.acc_full, 1);
     mbar_init(&sb.acc_empty, 2 * T2_EPI_WARPS);
@@ -401,34 +406,39 @@ tc2_suffstats_kernel(rr_plan plan, const float* __restrict__ X,
           const bool last = (t % SPC) == SPC - 1 || t == nsl - 1;
           if (first) mbar_wait_cl(&sb.acc_empty, (gc & 1) ^ 1);
           const uint32_t ps = gs % T2_PSTAGES;
+          const uint32_t base = smem_u32(smem + T2_SMEM_PHI + ps * T2_PHI_BYTES);
+          const uint64_t dah = make_desc_sw128(base + T2_OFF_AH);
+          const uint64_t dar = make_desc_sw128(base + T2_OFF_AR);
+          const uint64_t dbh = make_desc_sw128(base + T2_OFF_BH);
+          const uint64_t dbr = make_desc_sw128(base + T2_OFF_BR);
+          const uint64_t dbc = make_desc_sw128(base + T2_OFF_BC);
           T2_TRACE(lane == 0, gs, 8);
-          mbar_wait_cl(&sb.phi_full[ps], (gs / T2_PSTAGES) & 1);
-          T2_TRACE(lane == 0, gs, 9);
-          if (t + 2 < nsl) issue_mma1(gs + 2);
-          T2_TRACE(lane == 0, gs, 10);
-          tc_fence_after_sync();
-          if (elect_one()) {
-            const uint32_t base = smem_u32(smem + T2_SMEM_PHI + ps * T2_PHI_BYTES);
-            const uint64_t dah = make_desc_sw128(base + T2_OFF_AH);
-            const uint64_t dar = make_desc_sw128(base + T2_OFF_AR);
-            const uint64_t dbh = make_desc_sw128(base + T2_OFF_BH);
-            const uint64_t dbr = make_desc_sw128(base + T2_OFF_BR);
-            const uint64_t dbc = make_desc_sw128(base + T2_OFF_BC);
-#ifdef RR_T2_EXP_NOMMA2    // experiment: one Gram MMA instead of twelve
-            for (int k = 0; k < 1; ++k) {
+#ifdef RR_T2_EXP_NOMMA2    // experiment: one Gram k-step instead of four
+          constexpr int KSTEPS = 1;
 #else
-#pragma unroll
-            for (int k = 0; k < T2_SLAB / 16; ++k) {
+          constexpr int KSTEPS = T2_SLAB / 16;
 #endif
+          static_assert(T2_GROWS == 16, "one generator group per MMA k-step");
+#pragma unroll
+          for (int k = 0; k < T2_SLAB / 16; ++k) {
+            mbar_wait_cl(&sb.phi_full[ps][k], (gs / T2_PSTAGES) & 1);
+            if (k == 0) T2_TRACE(lane == 0, gs, 9);
+            tc_fence_after_sync();
+            if (elect_one()) {
               const uint64_t adv = (uint64_t)(2 * k);
               const uint32_t acc = (first && k == 0) ? 0u : 1u;
-              umma2_f16_ss(tmem + T2_TMEM_MAIN, dah + adv, dbh + adv, idesc2, acc);
-              umma2_f16_ss(tmem + T2_TMEM_AUX, dar + adv, dbc + adv, idesc2, acc);
-              umma2_f16_ss(tmem + T2_TMEM_AUX, dah + adv, dbr + adv, idesc2, 1);
+              if (k < KSTEPS) {
+                umma2_f16_ss(tmem + T2_TMEM_MAIN, dah + adv, dbh + adv, idesc2, acc);
+                umma2_f16_ss(tmem + T2_TMEM_AUX, dar + adv, dbc + adv, idesc2, acc);
+                umma2_f16_ss(tmem + T2_TMEM_AUX, dah + adv, dbr + adv, idesc2, 1);
+              }
+              umma2_commit_mc(&sb.phi_empty[ps][k]);
+              if (last && k == T2_SLAB / 16 - 1) umma2_commit_mc(&sb.acc_full);
             }
-            umma2_commit_mc(&sb.phi_empty[ps]);
-            if (last) umma2_commit_mc(&sb.acc_full);
+            __syncwarp();
           }
+          T2_TRACE(lane == 0, gs, 10);
+          if (t + 2 < nsl) issue_mma1(gs + 2);
           __syncwarp();
           T2_TRACE(lane == 0, gs, 11);
           if (last) ++gc;
@@ -599,7 +609,7 @@ tc2_suffstats_kernel(rr_plan plan, const float* __restrict__ X,
 
         const uint32_t ps = gs % T2_PSTAGES;
         cx.base = smem_u32(smem + T2_SMEM_PHI + ps * T2_PHI_BYTES);
-        cx.empty_bar = &sb.phi_empty[ps];
+        cx.empty_bar = &sb.phi_empty[ps][h];
         cx.empty_parity = ((gs / T2_PSTAGES) & 1) ^ 1;
 #ifdef RR_T2_TRACE
         cx.trw = trw;
@@ -629,7 +639,7 @@ tc2_suffstats_kernel(rr_plan plan, const float* __restrict__ X,
         T2_TRACE(trw, gs, trb + 3);
         fence_proxy_async_smem();
         __syncwarp();
-        if (lane == 0) t2_arrive_leader(&sb.phi_full[ps], crank);
+        if (lane == 0) t2_arrive_leader(&sb.phi_full[ps][h], crank);
         T2_TRACE(trw, gs, trb + 4);
       }
       if (want_p && valid) {
@@ -671,7 +681,7 @@ tc2_suffstats_kernel(rr_plan plan, const float* __restrict__ X,
         mbar_wait_cl(&sb.acc_full, gc & 1);
         tc_fence_after_sync();
         // Drain MAIN + AUX: the two are added in fp32 (MAIN is an exact multiple of
-        // 2^-12 below 2^12, so the rounding is <= 2^-13 absolute per 4096-row chain,
+        // 2^-10 below 2^14, so the rounding is <= 2^-11 absolute per 16384-row chain,
         // unbiased), widened to float64 with integer ops (F2F would queue on the XU
         // pipe behind the generators' MUFU work) and added to the scratch image with
         // RED.F64.  Amplitudes are applied by the finalize kernel.
