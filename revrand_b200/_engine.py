@@ -381,32 +381,71 @@ def tcgen05_selftest():
 # Posterior solve on one GPU (library dense linear algebra, float64)
 # ---------------------------------------------------------------------------
 
-def solve_posterior(G, p, var, lam):
-    """C = (diag(1/lam) + G/var)^-1, logdet(iC), m = C p / var.
+class Posterior(object):
+    """Result of the one-GPU solve.  ``C`` (float64, D x D) is formed lazily:
+    an evaluation only needs diag(C), m, logdet and -- for the gradient pass --
+    a float32 image of C."""
 
-    Semantics of ``solve_posdef`` (revrand/mathfun/linalg.py:84-125): upper
-    Cholesky; if it fails or any diagonal of the factor is < CHOLTHRESH fall
-    back to the clamped-spectrum solve (:128-179) with logdet = sum log s.
+    def __init__(self, m, diagC, logdet, trgc, Linv=None, C=None):
+        self.m, self.diagC, self.logdet, self.trgc = m, diagC, logdet, trgc
+        self._Linv, self._C = Linv, C
+
+    @property
+    def C(self):
+        if self._C is None:
+            self._C = self._Linv.T @ self._Linv
+        return self._C
+
+    def C32(self):
+        """float32 image of C for the gradient pass."""
+        return self.C.float().contiguous()
+
+
+def solve_posterior(G, p, var, lam, need_C=True):
+    """C = (diag(1/lam) + G/var)^-1, logdet(iC), m = C p / var, tr(G C).
+
+    Semantics of ``solve_posdef`` (revrand/mathfun/linalg.py:84-125): Cholesky;
+    if it fails or any diagonal of the factor is < CHOLTHRESH fall back to the
+    clamped-spectrum solve (:128-179) with logdet = sum log s.
     ``G``, ``p`` float64 device tensors; ``lam`` float64 device vector.
+
+    Because G = var (iC - diag(1/lam)),  tr(G C) = var (D - sum_j C_jj / lam_j):
+    only diag(C) is needed for the value.  ``need_C=False`` (value-only
+    evaluations, e.g. the random-start phase) therefore skips the explicit
+    inverse: with iC = L L^T,  diag C = column sums of (L^-1)^2 and
+    m = L^-T (L^-1 p) / var from one triangular solve.  The gradient pass needs
+    all of C; it is then formed by potri in float64 (forming it as
+    (L^-1)^T (L^-1) in reduced precision loses the small entries of C to
+    cancellation and derails the optimiser).
     """
     t = torch()
+    D = G.shape[0]
     iC = G / var
     iC.diagonal().add_(1.0 / lam)
     L, info = t.linalg.cholesky_ex(iC)
-    ok = int(info.item()) == 0
-    if ok:
-        dg = L.diagonal()
-        ok = bool((dg >= CHOLTHRESH).all().item())
-    if ok:
+    dg = L.diagonal()
+    ok = bool(((info == 0) & (dg >= CHOLTHRESH).all()).item())
+    if ok and need_C:
         Cm = t.cholesky_inverse(L)
+        diagC = Cm.diagonal().clone()
+        m = (Cm @ p) / var
         logdet = 2.0 * t.log(dg).sum()
-    else:
-        U, s, Vh = t.linalg.svd(iC)
-        sc = t.clamp(s, min=SVD_FLOOR)
-        Cm = (U / sc) @ Vh
-        logdet = t.log(s).sum()
+        trgc = var * (D - (diagC / lam).sum())
+        return Posterior(m, diagC, logdet, trgc, C=Cm)
+    if ok:
+        eye = t.eye(D, dtype=G.dtype, device=G.device)
+        Linv = t.linalg.solve_triangular(L, eye, upper=False)
+        diagC = (Linv * Linv).sum(dim=0)
+        m = (Linv.T @ (Linv @ p)) / var
+        logdet = 2.0 * t.log(dg).sum()
+        trgc = var * (D - (diagC / lam).sum())
+        return Posterior(m, diagC, logdet, trgc, Linv=Linv)
+    U, s, Vh = t.linalg.svd(iC)
+    sc = t.clamp(s, min=SVD_FLOOR)
+    Cm = (U / sc) @ Vh
+    logdet = t.log(s).sum()
     m = (Cm @ p) / var
-    return Cm, logdet, m
+    return Posterior(m, Cm.diagonal().clone(), logdet, (G * Cm).sum(), C=Cm)
 
 
 # ---------------------------------------------------------------------------

@@ -102,7 +102,9 @@ def _flat_bounds(parameters):
 def _random_starts(fun, parameters, jac, args, nstarts, random_state,
                    data_gen=None):
     """Best of ``nstarts`` draws from the parameters' distributions
-    (decorators.py:541-583); every candidate costs one objective call."""
+    (decorators.py:541-583); every candidate costs one objective call.  Only
+    the objective VALUE of a candidate is used, so an objective may offer a
+    cheaper ``fun.value_only(*params)`` (no gradients) for this phase."""
     if nstarts < 1:
         raise ValueError("nstarts has to be greater than or equal to 1")
     flags = flatten_values(_map_params(lambda p: float(p.is_random), parameters))
@@ -111,11 +113,15 @@ def _random_starts(fun, parameters, jac, args, nstarts, random_state,
         return _map_params(lambda p: p.value, parameters)
     log.info("Evaluating random starts...")
     best_obj, best = None, None
+    value_only = getattr(fun, "value_only", None) if data_gen is None else None
     for _ in range(nstarts):
         batch = next(data_gen) if data_gen else ()
         cand = _map_params(lambda p: p.rvs(random_state), parameters)
-        out = fun(*chain(cand, batch, args))
-        obj = out[0] if jac is True else out
+        if value_only is not None:
+            obj = value_only(*chain(cand, args))
+        else:
+            out = fun(*chain(cand, batch, args))
+            obj = out[0] if jac is True else out
         if best_obj is None or obj < best_obj:
             best_obj, best = obj, cand
     log.info("Best start found with objective = {}".format(best_obj))

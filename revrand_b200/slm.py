@@ -76,17 +76,17 @@ class _SLMProblem(object):
         lam_np, slices = self.basis.regularizer_diagonal(self.Xhost_probe, *regs)
         slices = slices if isinstance(slices, list) else [slice(0, self.D)]
         lam = eng.to_device(lam_np, t.float64)
-        Cm, logdet, m = eng.solve_posterior(st.G, st.p, float(var), lam)
-        trgc = (st.G * Cm).sum()
-        mc = m * m + Cm.diagonal()
+        post = eng.solve_posterior(st.G, st.p, float(var), lam,
+                                   need_C=bool(want_grad and plan.ktot))
+        m, logdet, trgc = post.m, post.logdet, post.trgc
+        mc = m * m + post.diagC
         q = t.stack([mc[s].sum() for s in slices])
-        out = {"m": m, "C": Cm, "slices": slices, "lam": lam_np}
+        out = {"m": m, "post": post, "slices": slices, "lam": lam_np}
         m32 = m.float().contiguous()
         self.rflat.zero_()
         g = None
         if want_grad and plan.ktot:
-            C32 = Cm.float().contiguous()
-            eng.slm_gradpass(plan, self.Xd, self.yd, m32, C32, self.R,
+            eng.slm_gradpass(plan, self.Xd, self.yd, m32, post.C32(), self.R,
                              self.sqerr, engine=self.engine)
         else:
             eng.slm_residual(plan, self.Xd, self.yd, m32, sqerr=self.sqerr)
@@ -149,6 +149,10 @@ class StandardLinearModel(BaseEstimator, RegressorMixin):
         def elbo(var, reg, hypers):
             return self._elbo(X, y, var, reg, hypers)
 
+        # random starts only compare objective values: skip the gradient pass
+        elbo.value_only = lambda var, reg, hypers: self._elbo(
+            X, y, var, reg, hypers, want_grad=False)[0]
+
         res = nmin(elbo, params, method='L-BFGS-B', jac=True, tol=self.tol,
                    options={'maxiter': self.maxiter, 'maxcor': 100},
                    random_state=self.random_, nstarts=self.nstarts)
@@ -173,9 +177,10 @@ class StandardLinearModel(BaseEstimator, RegressorMixin):
             self._problem_key = key
         return self._cached_problem
 
-    def _elbo(self, X, y, var, reg, hypers):
+    def _elbo(self, X, y, var, reg, hypers, want_grad=True):
         """(-ELBO, [-dvar, dreg, dhypers]) at the given hyper-parameters; same
-        contract as slm.py:142-199."""
+        contract as slm.py:142-199.  ``want_grad=False`` returns
+        ``(-ELBO, None)`` without the gradient pass."""
         prob = self._get_problem(X, y)
         t = eng.torch()
         if prob.world > 1:  # keep ranks in lockstep on identical parameters
@@ -201,7 +206,7 @@ class StandardLinearModel(BaseEstimator, RegressorMixin):
         hyps = [h for h in _aslist(hypers)]
         if len(hyps) == 1 and np.size(hyps[0]) == 0:
             hyps = []
-        r = prob.evaluate(var, regs, hyps, want_grad=True)
+        r = prob.evaluate(var, regs, hyps, want_grad=want_grad)
         N, D = prob.N_total, prob.D
         lam, slices = r["lam"], r["slices"]
         lam_s = np.array([lam[s][0] for s in slices])
@@ -210,13 +215,15 @@ class StandardLinearModel(BaseEstimator, RegressorMixin):
                        + r["trgc"] / var + (r["q"] / lam_s).sum() + r["logdet"]
                        + np.log(lam).sum() - D)
         if ELBO > self.obj_:
-            self._m_dev, self._C_dev = r["m"], r["C"]
+            self._m_dev, self._post = r["m"], r["post"]
             self.obj_ = ELBO
             if getattr(self, "_problem", None) is None:
                 self._sync_posterior()
         if log.isEnabledFor(logging.INFO):
             log.info("ELBO = {}, var = {}, reg = {}, hypers = {}."
                      .format(ELBO, var, reg, hypers))
+        if not want_grad:
+            return -ELBO, None
         dvar = 0.5 * (-N + (r["sqerr"] + r["trgc"]) / var) / var
         dregs = [-0.5 * (qs / ls ** 2 - ns / ls)
                  for qs, ls, ns in zip(r["q"], lam_s, n_s)]
@@ -240,7 +247,7 @@ class StandardLinearModel(BaseEstimator, RegressorMixin):
         """Materialise the cached best posterior as numpy attributes."""
         if getattr(self, "_m_dev", None) is not None:
             self.weights_ = self._m_dev.cpu().numpy()
-            self.covariance_ = self._C_dev.cpu().numpy()
+            self.covariance_ = self._post.C.cpu().numpy()
 
     # -- prediction ------------------------------------------------------------------
     def predict(self, X):
@@ -267,7 +274,7 @@ class StandardLinearModel(BaseEstimator, RegressorMixin):
     def __getstate__(self):
         state = dict(self.__dict__)
         for k in ("_problem", "_cached_problem", "_problem_key", "_m_dev",
-                  "_C_dev"):
+                  "_post"):
             state.pop(k, None)
         return state
 
