@@ -253,7 +253,7 @@ def run_ours(args):
     flops = 2.0 * n_local * D * D + 2.0 * n_local * d * K   # algorithmic, per launch
     pk = peaks()
     achieved = flops / (k_ms * 1e-3) / 1e12
-    roofline = {"bound": "tensor", "kernel": "tc_suffstats_kernel (fused Phi^T Phi)",
+    roofline = {"bound": "tensor", "kernel": "tc2_suffstats_kernel (fused Phi^T Phi, value pass)",
                 "achieved": achieved, "peak": pk["tflops"], "unit": "TFLOP/s",
                 "frac": achieved / pk["tflops"], "traffic": None,
                 "peak_source": pk["src"] + " bf16 sustained",
@@ -302,7 +302,8 @@ def run_ours(args):
         "metric": METRIC, "value": value, "unit": "evals/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
-        "dtype": "fp16x3-split tensor-core products, fp32 accumulate, f64 solve",
+        "dtype": "f16 (tcgen05 kind::f16 fixed-point-split products, tf32 projection, "
+                 "fp32 accumulate in TMEM, f64 statistics and solve)",
         "data": "synthetic",
         "config": {"workload": "config2: SLM + RandomMatern32(nbases=%d), N=%d, d=%d, "
                                "value+grad eval, isotropic lengthscale" % (K, N, d),

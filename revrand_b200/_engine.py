@@ -401,6 +401,30 @@ class Posterior(object):
         return self.C.float().contiguous()
 
 
+def _inverse_from_factor(L):
+    """C = (L L^T)^-1.  One process: potri.  Row-sharded job (every rank holds
+    the same L after the allreduce): rank r solves L L^T X = I[:, block_r] for
+    its block of columns and the blocks are all-gathered as ROWS of the
+    symmetric C -- the O(D^3) inverse, the serial part of an evaluation, then
+    scales with the number of GPUs like the row passes do."""
+    t = torch()
+    rank, ws = world()
+    D = L.shape[0]
+    if ws == 1 or D < 2 * ws:
+        return t.cholesky_inverse(L)
+    per = (D + ws - 1) // ws            # equal blocks (all_gather_into_tensor)
+    lo = min(rank * per, D)
+    hi = min(lo + per, D)
+    E = t.zeros((D, per), dtype=L.dtype, device=L.device)
+    if hi > lo:
+        E[lo:hi, :hi - lo] = t.eye(hi - lo, dtype=L.dtype, device=L.device)
+    Xb = t.cholesky_solve(E, L)          # D x per: columns lo..hi of C (rest: zeros)
+    rows = Xb.T.contiguous()             # per x D: rows lo..hi of C
+    full = t.empty((ws * per, D), dtype=L.dtype, device=L.device)
+    t.distributed.all_gather_into_tensor(full, rows)
+    return full[:D]
+
+
 def solve_posterior(G, p, var, lam, need_C=True):
     """C = (diag(1/lam) + G/var)^-1, logdet(iC), m = C p / var, tr(G C).
 
@@ -426,7 +450,7 @@ def solve_posterior(G, p, var, lam, need_C=True):
     dg = L.diagonal()
     ok = bool(((info == 0) & (dg >= CHOLTHRESH).all()).item())
     if ok and need_C:
-        Cm = t.cholesky_inverse(L)
+        Cm = _inverse_from_factor(L)
         diagC = Cm.diagonal().clone()
         m = (Cm @ p) / var
         logdet = 2.0 * t.log(dg).sum()

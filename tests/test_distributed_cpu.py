@@ -40,6 +40,16 @@ def _worker(rank, world, port, ret):
         ok = (np.allclose(flat[:D * D].numpy().reshape(D, D), Pf.T.dot(Pf))
               and np.allclose(flat[D * D:D * D + D].numpy(), Pf.T.dot(y))
               and np.isclose(flat[-1].item(), y.dot(y)))
+        # the posterior solve with the inverse distributed over the ranks
+        # must equal the one-process float64 inverse on every rank
+        A = Pf.T.dot(Pf)
+        lam = np.full(D, 1.7)
+        post = _engine.solve_posterior(torch.from_numpy(A), torch.from_numpy(Pf.T.dot(y)),
+                                       0.3, torch.from_numpy(lam))
+        Cref = np.linalg.inv(np.diag(1.0 / lam) + A / 0.3)
+        ok = ok and np.allclose(post.C.numpy(), Cref, rtol=1e-9, atol=1e-12)
+        ok = ok and np.allclose(post.m.numpy(), Cref.dot(Pf.T.dot(y)) / 0.3)
+        ok = ok and np.isclose(post.trgc.item(), np.sum(A * Cref))
         ret[rank] = bool(ok)
     finally:
         dist.destroy_process_group()
