@@ -155,7 +155,8 @@ def run_reference(args):
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": 1e3 * t, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "config2: SLM + RandomMatern32(nbases=%d), N=%d, d=%d"
+        "config": {"workload": "config2: SLM + RandomMatern32(nbases=%d), N=%d, d=%d, "
+                               "value+grad eval, isotropic lengthscale"
                    % (args.K, args.N, args.d)},
         "cpu_baseline": {"value": val, "unit": "evals/s", "cores": cpu_threads(),
                          "kind": "port", "sample": desc},
