@@ -74,8 +74,9 @@ constexpr int T2_SMEM_PHI = 0;
 constexpr int T2_SMEM_W = T2_PSTAGES * T2_PHI_BYTES;
 constexpr int T2_SMEM_X = T2_SMEM_W + 2 * T2_W_BYTES;
 constexpr int T2_SMEM_RAW = T2_SMEM_X + T2_XSTAGES * 2 * T2_X_BYTES;
-constexpr int T2_RAW_AHEAD = 3;                  // slabs of X in flight (cp.async)
-constexpr int T2_RAW_STAGES = T2_RAW_AHEAD + 1;
+constexpr int T2_LOAD_WARPS = 2;                 // loader warps; warp li takes slabs = li (mod 2)
+constexpr int T2_RAW_AHEAD = 1;                  // own slabs of X in flight per loader warp
+constexpr int T2_RAW_STAGES = T2_LOAD_WARPS * (T2_RAW_AHEAD + 1);
 constexpr int T2_RAW_BYTES = 32 * 32 * 4;        // 32 rows x d <= 32 floats, as in HBM
 constexpr int T2_SMEM_BYTES = T2_SMEM_RAW + T2_RAW_STAGES * T2_RAW_BYTES;
 
@@ -90,7 +91,7 @@ constexpr int T2_GEN_WARPS = 4 * T2_GSPLIT;      // warps 4..19: four per SM sub
                                                  // MUFU and FMA-pipe phases of different warps overlap
 constexpr int T2_WARP_MMA = T2_EPI_WARPS + T2_GEN_WARPS;
 constexpr int T2_WARP_LOAD = T2_WARP_MMA + 1;
-constexpr int T2_THREADS = (T2_WARP_LOAD + 1) * 32;
+constexpr int T2_THREADS = (T2_WARP_LOAD + T2_LOAD_WARPS) * 32;
 constexpr int T2_GPAIRS = T2_GROWS / 2;          // packed row pairs per generator thread
 constexpr int T2_GCHUNKS = T2_GROWS / 8;         // 16-byte chunks per image row per thread
 
@@ -120,7 +121,8 @@ struct T2Bars {
   // one barrier per (stage, 16-row k-step): generator group h writes exactly the
   // K = 16 columns that MMA k-step h reads, so the tensor pipe can start on a slab
   // as soon as its first group is done and no group waits for another's slot
-  uint64_t phi_full[T2_PSTAGES][T2_GSPLIT];   // leader waits; count 8 (4 warps x 2 CTAs)
+  uint64_t phi_full[T2_PSTAGES][T2_GSPLIT];   // LOCAL to each CTA; count 4 (warps of the group)
+  uint64_t peer_full[T2_PSTAGES];             // leader only: the peer CTA's slab is done; count 1
   uint64_t phi_empty[T2_PSTAGES][T2_GSPLIT];  // multicast commit
   uint64_t acc_full;              // multicast commit
   uint64_t acc_empty;             // leader waits; count 8 (epilogue warps)
@@ -302,6 +304,16 @@ __device__ __forceinline__ void t2_gen_slab(const T2GenCtx& cx, const float* u,
       }
     }
   };
+#ifdef RR_T2_EXP_HALFGEN   // experiment: half of the generator work per slab
+  trig(0);
+  trig(1);
+#pragma unroll
+  for (int i = 0; i < T2_GPAIRS / 2; ++i) {
+    if (i + 2 < T2_GPAIRS / 2) trig(i + 2);
+    split(i);
+  }
+  c2[T2_GPAIRS - 1] = c2[0];
+#else
   trig(0);
   trig(1);
 #pragma unroll
@@ -309,6 +321,7 @@ __device__ __forceinline__ void t2_gen_slab(const T2GenCtx& cx, const float* u,
     if (i + 2 < T2_GPAIRS) trig(i + 2);
     split(i);
   }
+#endif
 }
 
 __global__ void __launch_bounds__(T2_THREADS, 1)
@@ -341,9 +354,10 @@ tc2_suffstats_kernel(rr_plan plan, const float* __restrict__ X,
     mbar_init(&sb.u_empty, 2 * T2_GEN_WARPS);
     for (int s = 0; s < T2_PSTAGES; ++s) {
       for (int h = 0; h < T2_GSPLIT; ++h) {
-        mbar_init(&sb.phi_full[s][h], 2 * 4);
+        mbar_init(&sb.phi_full[s][h], 4);
         mbar_init(&sb.phi_empty[s][h], 1);
       }
+      mbar_init(&sb.peer_full[s], 1);
     }
     mbar_init(&sb.acc_full, 1);
     mbar_init(&sb.acc_empty, 2 * T2_EPI_WARPS);
@@ -375,12 +389,19 @@ tc2_suffstats_kernel(rr_plan plan, const float* __restrict__ X,
           const uint32_t x_lo = x_hi + T2_X_BYTES;
           const uint64_t dwh = make_desc_sw128(w_hi), dwl = make_desc_sw128(w_lo);
           const uint64_t dxh = make_desc_sw128(x_hi), dxl = make_desc_sw128(x_lo);
+#ifdef RR_T2_EXP_NOPROJ   // experiment: one projection MMA instead of 3 * nk1
+          for (int k = 0; k < 1; ++k) {
+            const uint64_t adv = (uint64_t)(2 * k);
+            umma2_tf32_ss(tmem + T2_TMEM_U, dwh + adv, dxh + adv, idesc1, k != 0);
+          }
+#else
           for (int k = 0; k < nk1; ++k) {
             const uint64_t adv = (uint64_t)(2 * k);
             umma2_tf32_ss(tmem + T2_TMEM_U, dwh + adv, dxh + adv, idesc1, k != 0);
             umma2_tf32_ss(tmem + T2_TMEM_U, dwl + adv, dxh + adv, idesc1, 1);
             umma2_tf32_ss(tmem + T2_TMEM_U, dwh + adv, dxl + adv, idesc1, 1);
           }
+#endif
           umma2_commit_mc(&sb.u_full);
           umma2_commit_mc(&sb.x_empty[xs]);
         }
@@ -420,11 +441,20 @@ tc2_suffstats_kernel(rr_plan plan, const float* __restrict__ X,
 #endif
           static_assert(T2_GROWS == 16, "one generator group per MMA k-step");
 #pragma unroll
-          for (int k = 0; k < T2_SLAB / 16; ++k) {
+          for (int k = 0; k < T2_GSPLIT; ++k)
             mbar_wait_cl(&sb.phi_full[ps][k], (gs / T2_PSTAGES) & 1);
-            if (k == 0) T2_TRACE(lane == 0, gs, 9);
-            tc_fence_after_sync();
-            if (elect_one()) {
+          mbar_wait_cl(&sb.peer_full[ps], (gs / T2_PSTAGES) & 1);
+          T2_TRACE(lane == 0, gs, 9);
+          // The generators publish their st.shared writes with a plain (release)
+          // mbarrier arrive; the generic -> async proxy fence is executed HERE, once
+          // per slab by the consumer (and by the relay warp in the peer CTA for its
+          // shared memory), instead of once per generator warp: in lock step the 16
+          // per-warp fences cost ~280 cycles of every slab.
+          fence_proxy_async_smem();
+          tc_fence_after_sync();
+          if (elect_one()) {
+#pragma unroll
+            for (int k = 0; k < T2_SLAB / 16; ++k) {
               const uint64_t adv = (uint64_t)(2 * k);
               const uint32_t acc = (first && k == 0) ? 0u : 1u;
               if (k < KSTEPS) {
@@ -433,10 +463,10 @@ tc2_suffstats_kernel(rr_plan plan, const float* __restrict__ X,
                 umma2_f16_ss(tmem + T2_TMEM_AUX, dah + adv, dbr + adv, idesc2, 1);
               }
               umma2_commit_mc(&sb.phi_empty[ps][k]);
-              if (last && k == T2_SLAB / 16 - 1) umma2_commit_mc(&sb.acc_full);
             }
-            __syncwarp();
+            if (last) umma2_commit_mc(&sb.acc_full);
           }
+          __syncwarp();
           T2_TRACE(lane == 0, gs, 10);
           if (t + 2 < nsl) issue_mma1(gs + 2);
           __syncwarp();
@@ -445,9 +475,30 @@ tc2_suffstats_kernel(rr_plan plan, const float* __restrict__ X,
         }
       }
     }
-  } else if (warp == T2_WARP_LOAD) {
-    // ============================ X slab loader ===================================
-    // Two steps per slab, both by this one warp.  (1) cp.async: the CTA's 32 rows
+    else {
+      // ===================== relay (peer CTA's otherwise idle MMA warp) =============
+      // waits for this CTA's generator groups, makes their writes visible to the
+      // async proxy of THIS SM and tells the leader.
+      uint32_t gs = 0;
+      for (int item = pair; item < nitems; item += npairs) {
+        const T2Item it = t2_decode(item, ntiles, NIB, NJB, N, rpi);
+        const int nsl = (int)((it.r1 - it.r0 + T2_SLAB - 1) / T2_SLAB);
+        for (int t = 0; t < nsl; ++t, ++gs) {
+          const uint32_t ps = gs % T2_PSTAGES;
+#pragma unroll
+          for (int k = 0; k < T2_GSPLIT; ++k)
+            mbar_wait_cl(&sb.phi_full[ps][k], (gs / T2_PSTAGES) & 1);
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) mbar_arrive_cluster(mapa_u32(smem_u32(&sb.peer_full[ps]), 0));
+        }
+      }
+    }
+  } else if (warp >= T2_WARP_LOAD) {
+    // ============================ X slab loaders ==================================
+    // Two warps, each taking every other slab (one warp needed ~2300 cycles per slab
+    // and would cap the kernel once the generators speed up).
+    // Two steps per slab, both by one warp.  (1) cp.async: the CTA's 32 rows
     // are one contiguous block of X; lanes copy it word by word (coalesced, any
     // 4-byte alignment, zero fill past the last row) into a raw staging ring,
     // T2_RAW_AHEAD slabs ahead, so HBM latency never sits on the slab period.
@@ -472,7 +523,8 @@ tc2_suffstats_kernel(rr_plan plan, const float* __restrict__ X,
         load_item(si);
       }
     };
-    const uint32_t raw0 = smem_u32(smem + T2_SMEM_RAW);
+    const int li = warp - T2_WARP_LOAD;
+    const uint32_t raw0 = smem_u32(smem + T2_SMEM_RAW) + (uint32_t)li * (T2_RAW_AHEAD + 1) * T2_RAW_BYTES;
     auto prefetch = [&](const SlabIter& si, uint32_t stage) {
       if (si.item < nitems) {
         const int64_t row0 = si.r0 + (int64_t)si.t * T2_SLAB + 32 * (int64_t)crank;
@@ -496,18 +548,22 @@ tc2_suffstats_kernel(rr_plan plan, const float* __restrict__ X,
     pf.item = cs.item = pair;
     load_item(pf);
     load_item(cs);
+    for (int i = 0; i < li; ++i) {      // first own slab
+      advance(pf);
+      advance(cs);
+    }
     for (int i = 0; i < T2_RAW_AHEAD; ++i) {
       prefetch(pf, (uint32_t)i);
-      advance(pf);
+      for (int j = 0; j < T2_LOAD_WARPS; ++j) advance(pf);
     }
     const int nch = 2 * nk1;   // 16-byte chunks of a tile row that MMA#1 reads
-    uint32_t gs = 0;
+    uint32_t gs = (uint32_t)li, own = 0;
     while (cs.item < nitems) {
-      prefetch(pf, (gs + T2_RAW_AHEAD) % T2_RAW_STAGES);
-      advance(pf);
+      prefetch(pf, (own + T2_RAW_AHEAD) % (T2_RAW_AHEAD + 1));
+      for (int j = 0; j < T2_LOAD_WARPS; ++j) advance(pf);
       asm volatile("cp.async.wait_group %0;" ::"n"(T2_RAW_AHEAD) : "memory");
       __syncwarp();
-      const uint32_t rrow = raw0 + (gs % T2_RAW_STAGES) * T2_RAW_BYTES + 4u * (uint32_t)(lane * d);
+      const uint32_t rrow = raw0 + (own % (T2_RAW_AHEAD + 1)) * T2_RAW_BYTES + 4u * (uint32_t)(lane * d);
       const uint32_t xs = gs % T2_XSTAGES;
       T2_TRACE(lane == 0, gs, 12);
       mbar_wait_cl(&sb.x_empty[xs], ((gs / T2_XSTAGES) & 1) ^ 1);
@@ -537,8 +593,9 @@ tc2_suffstats_kernel(rr_plan plan, const float* __restrict__ X,
       __syncwarp();
       if (lane == 0) t2_arrive_leader(&sb.x_full[xs], crank);
       T2_TRACE(lane == 0, gs, 14);
-      advance(cs);
-      ++gs;
+      for (int j = 0; j < T2_LOAD_WARPS; ++j) advance(cs);
+      gs += T2_LOAD_WARPS;
+      ++own;
     }
     asm volatile("cp.async.wait_group 0;" ::: "memory");
   } else if (warp >= T2_EPI_WARPS) {
@@ -637,9 +694,8 @@ tc2_suffstats_kernel(rr_plan plan, const float* __restrict__ X,
           else t2_gen_slab<false, false>(cx, u, live, !is_a, has_row, nullptr, dummy0, dummy1);
         }
         T2_TRACE(trw, gs, trb + 3);
-        fence_proxy_async_smem();
         __syncwarp();
-        if (lane == 0) t2_arrive_leader(&sb.phi_full[ps][h], crank);
+        if (lane == 0) mbar_arrive(&sb.phi_full[ps][h]);
         T2_TRACE(trw, gs, trb + 4);
       }
       if (want_p && valid) {
@@ -700,7 +756,11 @@ tc2_suffstats_kernel(rr_plan plan, const float* __restrict__ X,
 #pragma unroll
           for (int r = 0; r < 8; ++r) {
             const int2 tb = sb.etab[c0 + r];
+#ifdef RR_T2_EXP_NODRAIN
+            if (key_a <= tb.y && vm[cur][r] == 123.456f) {
+#else
             if (key_a <= tb.y) {
+#endif
               const uint32_t b = __float_as_uint(vm[cur][r] + vx[cur][r]);
               // fp32 -> fp64 bit pattern (normal numbers; +-0 becomes +-2^-127)
               const uint32_t hi = (b & 0x80000000u) | (((b & 0x7fffffffu) >> 3) + 0x38000000u);

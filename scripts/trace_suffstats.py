@@ -17,7 +17,8 @@ LIB = os.path.join(ROOT, "revrand_b200", "lib", "librevrand_b200_trace.so")
 os.makedirs(os.path.dirname(LIB), exist_ok=True)
 if not os.path.exists(LIB) or "--rebuild" in sys.argv:
     subprocess.check_call(["nvcc", "-O3", "-std=c++17", "-gencode",
-                           "arch=compute_100a,code=sm_100a", "-lineinfo", "-DRR_T2_TRACE",
+                           "arch=compute_100a,code=sm_100a", "-lineinfo", "-DRR_T2_TRACE"]
+                          + [a for a in sys.argv[1:] if a.startswith("-D")] + [
                            "-Xcompiler", "-fPIC", "-shared", "-o", LIB]
                           + sorted(glob.glob(os.path.join(CSRC, "*.cu"))), cwd=CSRC)
 if "--build-only" in sys.argv:

@@ -99,6 +99,9 @@ __global__ void __launch_bounds__(1024, 1) gen_kernel(const float* __restrict__ 
     }
 #pragma unroll
     for (int i = 0; i < 16; ++i) u[i] += 0.37f;   // new inputs every pass
+    if (SPIN == 4) asm volatile("bar.sync 1, %0;" ::"r"(gen_warps * 32));          // lock step
+    if (SPIN == 5) asm volatile("bar.sync %0, 128;" ::"r"(2 + (warp >> 2)));         // per group of 4 warps
+    if (SPIN == 6) { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); asm volatile("bar.sync 1, %0;" ::"r"(gen_warps * 32)); }
   }
   const long long t1 = clock64();
   if (tid == 0) cyc[blockIdx.x] = t1 - t0;
@@ -109,7 +112,7 @@ __global__ void __launch_bounds__(1024, 1) gen_kernel(const float* __restrict__ 
 template <int MODE, int SPIN = 0>
 void run(int warps, const float* in, float* out, long long* cyc, const char* name) {
   const int iters = 2000;
-  const int tot = warps + (SPIN ? 4 : 0);
+  const int tot = warps + ((SPIN >= 1 && SPIN <= 3) ? 4 : 0);
   cudaFuncSetAttribute(gen_kernel<MODE, SPIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
   gen_kernel<MODE, SPIN><<<148, tot * 32, 96 * 1024>>>(in, out, 10, cyc, warps);
   gen_kernel<MODE, SPIN><<<148, tot * 32, 96 * 1024>>>(in, out, iters, cyc, warps);
@@ -128,9 +131,10 @@ int main() {
   cudaMalloc(&out, 148 * 1024 * 4);
   cudaMalloc(&cyc, 148 * 8);
   cudaMemset(in, 0, 148 * 1024 * 16 * 4);
-  run<4 | 1 | 2 | 8, 1>(16, in, out, cyc, "packed mufu sts B + 4 spin try_wait");
-  run<4 | 1 | 2 | 8, 2>(16, in, out, cyc, "packed mufu sts B + 4 spin hint");
-  run<4 | 1 | 2 | 8, 3>(16, in, out, cyc, "packed mufu sts B + 4 spin sleep");
+  run<4 | 1 | 2 | 8, 4>(16, in, out, cyc, "packed mufu sts B lock-step 16");
+  run<4 | 1 | 2 | 8, 5>(16, in, out, cyc, "packed mufu sts B lock-step groups");
+  run<4 | 1 | 2 | 8, 6>(16, in, out, cyc, "packed mufu sts B fence+lockstep");
+  run<4 | 1 | 2 | 8, 4>(8, in, out, cyc, "packed mufu sts B lock-step 8w");
   for (int w : {16}) {
     run<4 | 1 | 2 | 8>(w, in, out, cyc, "packed mufu sts B");
     run<4 | 1 | 2>(w, in, out, cyc, "packed mufu sts A");
