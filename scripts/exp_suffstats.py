@@ -3,8 +3,8 @@ macro (results are garbage; only the timing matters)."""
 import glob, os, subprocess, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 CSRC = os.path.join(ROOT, "revrand_b200", "csrc")
-VARIANTS = {"base": [], "halfgen": ["-DRR_T2_EXP_HALFGEN"], "nodrain": ["-DRR_T2_EXP_NODRAIN"],
-            "noproj": ["-DRR_T2_EXP_NOPROJ"], "nomma2": ["-DRR_T2_EXP_NOMMA2"],
+VARIANTS = {"base": [], "halfgen": ["-DRR_T2_EXP_HALFGEN"],
+            "nomma2": ["-DRR_T2_EXP_NOMMA2"],
             "halfgen_nomma2": ["-DRR_T2_EXP_HALFGEN", "-DRR_T2_EXP_NOMMA2"],
             "all_off": ["-DRR_T2_EXP_HALFGEN", "-DRR_T2_EXP_NOMMA2", "-DRR_T2_EXP_NOPROJ",
                         "-DRR_T2_EXP_NODRAIN", "-DRR_T2_EXP_NOSTS", "-DRR_T2_EXP_NOMUFU"]}
