@@ -47,6 +47,7 @@ constexpr int T2_NB = 56;            // column-block frequencies per CTA
 constexpr int T2_IB = 2 * T2_NA;     // frequencies per row block (pair)
 constexpr int T2_JB = 2 * T2_NB;     // frequencies per column block (pair)
 constexpr int T2_NCOL = 4 * T2_NB;   // 224 accumulator columns
+constexpr int T2_TILE_GROUP = 74;    // tiles whose scratch images are hot together
 constexpr int T2_XSTAGES = 3;
 constexpr int T2_PSTAGES = 2;
 constexpr int T2_CHAIN = 16384;      // rows per exact accumulation chain
@@ -144,9 +145,20 @@ struct T2Item {
 
 __device__ __forceinline__ T2Item t2_decode(int item, int ntiles, int NIB, int NJB,
                                             int64_t N, int64_t rpi) {
+  // Item order: tiles are taken in groups of T2_TILE_GROUP; inside a group the
+  // row super-chunks are the outer loop.  At any time the CTA pairs then share ONE
+  // super-chunk of X (2.75 MB) and add into one group of tiles of the float64
+  // scratch image (34 MB), both L2-resident.  (Super-chunk-major over all 173 tiles
+  // wrote the 134 MB image back to DRAM on every round: 1.1 GB per launch;
+  // tile-major re-read X from DRAM for every tile: 3.2 GB.)
   T2Item it;
-  int t = item % ntiles;
-  const int sc = item / ntiles;
+  const int nsuper = (int)((N + rpi - 1) / rpi);
+  const int grp = item / (T2_TILE_GROUP * nsuper);
+  const int rem = item - grp * (T2_TILE_GROUP * nsuper);
+  const int left = ntiles - grp * T2_TILE_GROUP;
+  const int ntg = left < T2_TILE_GROUP ? left : T2_TILE_GROUP;
+  const int sc = rem / ntg;
+  int t = grp * T2_TILE_GROUP + (rem - sc * ntg);
   int ib = 0;
   for (; ib < NIB; ++ib) {
     const int cnt = NJB - t2_jmin(ib);
