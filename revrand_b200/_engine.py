@@ -401,6 +401,56 @@ class Posterior(object):
         return self.C.float().contiguous()
 
 
+_BLOCK_INV_MIN = 1024   # below this potri is as fast
+_BLOCK_INV_LEAF = 512
+
+
+def _tri_inv_lower(L, out):
+    """out = L^-1 for lower-triangular L, recursively: with L = [[L11, 0], [L21, L22]],
+    L^-1 = [[L11^-1, 0], [-L22^-1 L21 L11^-1, L22^-1]].  All the O(n^3) work is in
+    float64 GEMMs (tensor cores) instead of cuSOLVER's triangular kernels."""
+    t = torch()
+    n = L.shape[0]
+    if n <= _BLOCK_INV_LEAF:
+        out.copy_(t.linalg.solve_triangular(
+            L, t.eye(n, dtype=L.dtype, device=L.device), upper=False))
+        return
+    h = ((n // 2 + 127) // 128) * 128
+    _tri_inv_lower(L[:h, :h], out[:h, :h])
+    _tri_inv_lower(L[h:, h:], out[h:, h:])
+    t.matmul(out[h:, h:], L[h:, :h] @ out[:h, :h], out=out[h:, :h])
+    out[h:, :h].neg_()
+    out[:h, h:].zero_()
+
+
+def _gram_of_lower(Li, out):
+    """out = Li^T Li for lower-triangular Li, recursively on the same 2 x 2 split
+    (only half-size GEMMs; the zero block of Li is never multiplied)."""
+    t = torch()
+    n = Li.shape[0]
+    if n <= _BLOCK_INV_LEAF:
+        t.matmul(Li.T, Li, out=out)
+        return
+    h = ((n // 2 + 127) // 128) * 128
+    A, X, B = Li[:h, :h], Li[h:, :h], Li[h:, h:]
+    _gram_of_lower(A, out[:h, :h])
+    out[:h, :h].addmm_(X.T, X)
+    t.matmul(B.T, X, out=out[h:, :h])
+    out[:h, h:].copy_(out[h:, :h].T)
+    _gram_of_lower(B, out[h:, h:])
+
+
+def blocked_spd_inverse(L):
+    """(L L^T)^-1 = L^-T L^-1 from the lower Cholesky factor, GEMM-rich."""
+    t = torch()
+    n = L.shape[0]
+    Li = t.empty_like(L)
+    _tri_inv_lower(L, Li)
+    C = t.empty_like(L)
+    _gram_of_lower(Li, C)
+    return C
+
+
 def _inverse_from_factor(L):
     """C = (L L^T)^-1.  One process: potri.  Row-sharded job (every rank holds
     the same L after the allreduce): rank r solves L L^T X = I[:, block_r] for
@@ -411,6 +461,8 @@ def _inverse_from_factor(L):
     rank, ws = world()
     D = L.shape[0]
     if ws == 1 or D < 2 * ws:
+        if D >= _BLOCK_INV_MIN and L.is_cuda:
+            return blocked_spd_inverse(L)
         return t.cholesky_inverse(L)
     per = (D + ws - 1) // ws            # equal blocks (all_gather_into_tensor)
     lo = min(rank * per, D)

@@ -259,3 +259,24 @@ def test_shard_rows_partition():
         assert all(a[1] == b[0] for a, b in zip(spans[:-1], spans[1:]))
         sizes = [hi - lo for lo, hi in spans]
         assert max(sizes) - min(sizes) <= 1
+
+
+def test_blocked_spd_inverse_matches_numpy():
+    """The GEMM-rich blocked inverse used on the GPU for D >= 1024
+    (_engine.blocked_spd_inverse) against numpy, on CPU tensors, with a leaf
+    size small enough to exercise three levels of recursion."""
+    import torch
+    rs = np.random.RandomState(3)
+    n = 700
+    A = rs.randn(n, 2 * n)
+    S = A.dot(A.T) / n + 0.5 * np.eye(n)
+    old = _engine._BLOCK_INV_LEAF
+    _engine._BLOCK_INV_LEAF = 128
+    try:
+        L = torch.linalg.cholesky(torch.from_numpy(S))
+        C = _engine.blocked_spd_inverse(L).numpy()
+    finally:
+        _engine._BLOCK_INV_LEAF = old
+    ref = np.linalg.inv(S)
+    assert np.max(np.abs(C - ref)) < 1e-10 * np.max(np.abs(ref))
+    assert np.max(np.abs(C - C.T)) < 1e-12
