@@ -509,8 +509,12 @@ def solve_posterior(G, p, var, lam, need_C=True):
         trgc = var * (D - (diagC / lam).sum())
         return Posterior(m, diagC, logdet, trgc, C=Cm)
     if ok:
-        eye = t.eye(D, dtype=G.dtype, device=G.device)
-        Linv = t.linalg.solve_triangular(L, eye, upper=False)
+        if D >= _BLOCK_INV_MIN and L.is_cuda:
+            Linv = t.empty_like(L)
+            _tri_inv_lower(L, Linv)
+        else:
+            eye = t.eye(D, dtype=G.dtype, device=G.device)
+            Linv = t.linalg.solve_triangular(L, eye, upper=False)
         diagC = (Linv * Linv).sum(dim=0)
         m = (Linv.T @ (Linv @ p)) / var
         logdet = 2.0 * t.log(dg).sum()

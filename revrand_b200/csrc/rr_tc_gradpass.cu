@@ -25,6 +25,8 @@
 //      work of the next.
 //
 // Replaces: revrand/slm.py:161-162, 193-197 + basis_functions.py:109-152, 888-901.
+#include <stdlib.h>
+
 #include "rr_common.cuh"
 #include "rr_tc.cuh"
 
@@ -513,7 +515,7 @@ static int gp_chunk_blocks(const rr_plan* pl, int64_t N) {
 
 size_t tc_gradpass_workspace(const rr_plan* pl, int64_t N) {
   const int64_t Dp = gp_dp(pl);
-  return align_up((size_t)gp_chunk_blocks(pl, N) * G2_TM * Dp * 2, 1024) +
+  return 2 * (align_up((size_t)gp_chunk_blocks(pl, N) * G2_TM * Dp * 2, 1024) + 1024) +
          align_up((size_t)Dp * Dp * 2, 1024) + align_up((size_t)N * 4, 256) + 8192;
 }
 
@@ -564,6 +566,33 @@ int phi_residual(const rr_plan* pl, const float* X, const float* y, int64_t N,
   return RR_OK;
 }
 
+// Helper stream + events (per device, created on first use): the Phi chunk of
+// row chunk c+1 is generated on the helper stream while the GEMM of chunk c runs
+// on the caller's stream (two scratch chunks, ping-pong).  A phi_fit block needs
+// 9 K registers and 1.6 KB of shared memory, so one fits on every SM next to the
+// resident GEMM CTA; and with nothing queued between them, consecutive GEMM
+// launches overlap the epilogue tail of one with the pipeline fill of the next.
+struct GpAux {
+  cudaStream_t stream = nullptr;
+  cudaEvent_t fork = nullptr, phi[2] = {nullptr, nullptr}, gemm[2] = {nullptr, nullptr};
+};
+static GpAux* gp_aux() {
+  static GpAux aux[64];
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
+  GpAux& a = aux[dev];
+  if (!a.stream) {
+    if (cudaStreamCreateWithFlags(&a.stream, cudaStreamNonBlocking) != cudaSuccess) return nullptr;
+    bool ok = cudaEventCreateWithFlags(&a.fork, cudaEventDisableTiming) == cudaSuccess;
+    for (int i = 0; i < 2; ++i) {
+      ok = ok && cudaEventCreateWithFlags(&a.phi[i], cudaEventDisableTiming) == cudaSuccess;
+      ok = ok && cudaEventCreateWithFlags(&a.gemm[i], cudaEventDisableTiming) == cudaSuccess;
+    }
+    if (!ok) return nullptr;
+  }
+  return &a;
+}
+
 int tc_gradpass(const rr_plan* pl, const float* X, const float* y, int64_t N,
                 const float* m, const float* C, double* R, double* sqerr, void* ws,
                 size_t wsb, cudaStream_t st) {
@@ -571,20 +600,32 @@ int tc_gradpass(const rr_plan* pl, const float* X, const float* y, int64_t N,
   const int RBc = gp_chunk_blocks(pl, N);
   const int64_t RC = (int64_t)RBc * G2_TM;
   Workspace W(ws, wsb);
-  uint8_t* PhT = W.take<uint8_t>(align_up((size_t)RC * Dp * 2, 1024) + 1024);
+  uint8_t* PhTb[2];
+  PhTb[0] = W.take<uint8_t>(align_up((size_t)RC * Dp * 2, 1024) + 1024);
+  PhTb[1] = W.take<uint8_t>(align_up((size_t)RC * Dp * 2, 1024) + 1024);
   uint8_t* BtT = W.take<uint8_t>(align_up((size_t)Dp * Dp * 2, 1024) + 1024);
   float* err = W.take<float>((size_t)N);      // fitted values, then residuals
   unsigned int* cmax = W.take<unsigned int>(1);
-  if (!PhT || !BtT || !err || !cmax) {
+  GpAux* aux = gp_aux();
+  static const bool no_overlap = getenv("RR_GP_NO_OVERLAP") != nullptr;   // A/B switch
+  cudaStream_t sp = (aux && !no_overlap) ? aux->stream : st;             // Phi stream
+  if (!PhTb[0] || !PhTb[1] || !BtT || !err || !cmax) {
     set_error("tcgen05 gradpass workspace too small (need %zu bytes)",
               tc_gradpass_workspace(pl, N));
     return RR_ERR_WORKSPACE;
   }
+  if (!aux) {
+    set_error("could not create the helper stream of the gradient pass");
+    return RR_ERR_CUDA;
+  }
   // the bulk copies need 16-byte aligned images
-  PhT = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(PhT) + 1023) & ~(uintptr_t)1023);
+  for (int i = 0; i < 2; ++i)
+    PhTb[i] = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(PhTb[i]) + 1023) & ~(uintptr_t)1023);
   BtT = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(BtT) + 1023) & ~(uintptr_t)1023);
   RR_CUDA_CHECK(cudaMemsetAsync(cmax, 0, sizeof(unsigned int), st));
   RR_CUDA_CHECK(cudaMemsetAsync(err, 0, (size_t)N * sizeof(float), st));
+  RR_CUDA_CHECK(cudaEventRecord(aux->fork, st));          // inputs (m, y, X) are ready
+  RR_CUDA_CHECK(cudaStreamWaitEvent(aux->stream, aux->fork, 0));
   absmax_kernel<<<sm_count() * 4, 256, 0, st>>>(C, (int64_t)pl->D * pl->D, cmax);
   RR_LAUNCH_CHECK("absmax_kernel");
   {
@@ -593,15 +634,24 @@ int tc_gradpass(const rr_plan* pl, const float* X, const float* y, int64_t N,
     RR_LAUNCH_CHECK("prep_c_kernel");
   }
   const int d = pl->d;
-  for (int64_t s = 0; s < N; s += RC) {
+  int c = 0;
+  for (int64_t s = 0; s < N; s += RC, ++c) {
     const int rows = (int)((N - s) < RC ? (N - s) : RC);
     const int RB = (rows + G2_TM - 1) / G2_TM;
     const int rows_pad = RB * G2_TM;
-    int rc = launch_phi_fit(pl, X + s * d, rows, rows_pad, Dp, m, PhT, err + s, st);
+    const int buf = c & 1;
+    uint8_t* PhT = PhTb[buf];
+    // helper stream: Phi chunk c (after the GEMM of chunk c-2 released the buffer)
+    if (c >= 2) RR_CUDA_CHECK(cudaStreamWaitEvent(aux->stream, aux->gemm[buf], 0));
+    int rc = launch_phi_fit(pl, X + s * d, rows, rows_pad, Dp, m, PhT, err + s, sp);
     if (rc) return rc;
     // fitted values -> residuals (in place) + their sum of squares
-    resid_finish_kernel<<<(rows + 1023) / 1024, 256, 0, st>>>(y + s, err + s, rows, err + s, sqerr);
+    resid_finish_kernel<<<(rows + 1023) / 1024, 256, 0, sp>>>(y + s, err + s, rows, err + s,
+                                                             sqerr);
     RR_LAUNCH_CHECK("resid_finish_kernel");
+    RR_CUDA_CHECK(cudaEventRecord(aux->phi[buf], sp));
+    // caller's stream: GEMM + epilogue of chunk c
+    RR_CUDA_CHECK(cudaStreamWaitEvent(st, aux->phi[buf], 0));
     const float* Xc = X + s * d;
     const float* ec = err + s;
     if (d <= 4) rc = launch_gp2<1>(pl, Xc, ec, rows, RB, FB, PhT, BtT, m, cmax, R, st);
@@ -610,6 +660,7 @@ int tc_gradpass(const rr_plan* pl, const float* X, const float* y, int64_t N,
     else if (d <= 24) rc = launch_gp2<6>(pl, Xc, ec, rows, RB, FB, PhT, BtT, m, cmax, R, st);
     else rc = launch_gp2<8>(pl, Xc, ec, rows, RB, FB, PhT, BtT, m, cmax, R, st);
     if (rc) return rc;
+    RR_CUDA_CHECK(cudaEventRecord(aux->gemm[buf], st));
   }
   return RR_OK;
 }
