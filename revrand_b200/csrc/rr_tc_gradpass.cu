@@ -43,7 +43,12 @@ constexpr int G2_STAGES = 5;
 constexpr int G2_STAGE_BYTES = 2 * G2_HALF;   // A half + B half
 constexpr int G2_THREADS = 6 * 32;      // producer, MMA / relay, 4 epilogue warps
 constexpr int G2_RED = 4 * 32 * 32;     // floats of one cross-warp reduction buffer
-constexpr int64_t G2_SCRATCH_BYTES = 40ll << 20;  // Phi chunk budget (L2 resident)
+// Phi chunk budget.  The chunk does not have to fit in L2: tiles are visited with
+// the output-feature block fastest, so the CTA pairs running at any time share a
+// handful of 2 MB row-block panels of Phi plus the 32 MB image of C; each panel is
+// fetched from HBM once and then hit in L2 by the other 15 feature blocks.  Large
+// chunks amortise the per-launch pipeline fill and the exposed last epilogue.
+constexpr int64_t G2_SCRATCH_BYTES = 160ll << 20;
 
 // internal feature f -> (frequency, is_sin): blocks of [64 cos | 64 sin]
 __device__ __forceinline__ int feat_theta(int f) { return 64 * (f >> 7) + (f & 63); }
