@@ -403,6 +403,18 @@ class Posterior(object):
 
 _BLOCK_INV_MIN = 1024   # below this potri is as fast
 _BLOCK_INV_LEAF = 512
+_BLOCK_INV_CUDA_ONLY = True   # tests flip this to exercise the blocked paths on CPU
+
+
+def _use_blocked(L):
+    return L.shape[0] >= _BLOCK_INV_MIN and (L.is_cuda or not _BLOCK_INV_CUDA_ONLY)
+
+
+def _split(n):
+    """Split point of the 2 x 2 recursion: half, rounded to a multiple of 128
+    when the matrix is large enough for that to leave two non-empty blocks."""
+    h = ((n // 2 + 127) // 128) * 128
+    return h if 0 < h < n else n // 2
 
 
 def _tri_inv_lower(L, out):
@@ -415,7 +427,7 @@ def _tri_inv_lower(L, out):
         out.copy_(t.linalg.solve_triangular(
             L, t.eye(n, dtype=L.dtype, device=L.device), upper=False))
         return
-    h = ((n // 2 + 127) // 128) * 128
+    h = _split(n)
     _tri_inv_lower(L[:h, :h], out[:h, :h])
     _tri_inv_lower(L[h:, h:], out[h:, h:])
     t.matmul(out[h:, h:], L[h:, :h] @ out[:h, :h], out=out[h:, :h])
@@ -431,7 +443,7 @@ def _gram_of_lower(Li, out):
     if n <= _BLOCK_INV_LEAF:
         t.matmul(Li.T, Li, out=out)
         return
-    h = ((n // 2 + 127) // 128) * 128
+    h = _split(n)
     A, X, B = Li[:h, :h], Li[h:, :h], Li[h:, h:]
     _gram_of_lower(A, out[:h, :h])
     out[:h, :h].addmm_(X.T, X)
@@ -461,17 +473,26 @@ def _inverse_from_factor(L):
     rank, ws = world()
     D = L.shape[0]
     if ws == 1 or D < 2 * ws:
-        if D >= _BLOCK_INV_MIN and L.is_cuda:
+        if _use_blocked(L):
             return blocked_spd_inverse(L)
         return t.cholesky_inverse(L)
     per = (D + ws - 1) // ws            # equal blocks (all_gather_into_tensor)
     lo = min(rank * per, D)
     hi = min(lo + per, D)
-    E = t.zeros((D, per), dtype=L.dtype, device=L.device)
-    if hi > lo:
-        E[lo:hi, :hi - lo] = t.eye(hi - lo, dtype=L.dtype, device=L.device)
-    Xb = t.cholesky_solve(E, L)          # D x per: columns lo..hi of C (rest: zeros)
-    rows = Xb.T.contiguous()             # per x D: rows lo..hi of C
+    if _use_blocked(L):
+        # L^-1 replicated (GEMM-rich, D^3/3), then this rank's rows of
+        # C = L^-T L^-1 with one (per x D x D) GEMM
+        Li = t.empty_like(L)
+        _tri_inv_lower(L, Li)
+        rows = t.zeros((per, D), dtype=L.dtype, device=L.device)
+        if hi > lo:
+            t.matmul(Li[:, lo:hi].T, Li, out=rows[:hi - lo])
+    else:
+        E = t.zeros((D, per), dtype=L.dtype, device=L.device)
+        if hi > lo:
+            E[lo:hi, :hi - lo] = t.eye(hi - lo, dtype=L.dtype, device=L.device)
+        Xb = t.cholesky_solve(E, L)      # D x per: columns lo..hi of C (rest: zeros)
+        rows = Xb.T.contiguous()         # per x D: rows lo..hi of C
     full = t.empty((ws * per, D), dtype=L.dtype, device=L.device)
     t.distributed.all_gather_into_tensor(full, rows)
     return full[:D]
@@ -509,7 +530,7 @@ def solve_posterior(G, p, var, lam, need_C=True):
         trgc = var * (D - (diagC / lam).sum())
         return Posterior(m, diagC, logdet, trgc, C=Cm)
     if ok:
-        if D >= _BLOCK_INV_MIN and L.is_cuda:
+        if _use_blocked(L):
             Linv = t.empty_like(L)
             _tri_inv_lower(L, Linv)
         else:

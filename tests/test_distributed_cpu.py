@@ -50,6 +50,12 @@ def _worker(rank, world, port, ret):
         ok = ok and np.allclose(post.C.numpy(), Cref, rtol=1e-9, atol=1e-12)
         ok = ok and np.allclose(post.m.numpy(), Cref.dot(Pf.T.dot(y)) / 0.3)
         ok = ok and np.isclose(post.trgc.item(), np.sum(A * Cref))
+        # same through the GEMM-rich blocked path used on the GPU for D >= 1024
+        _engine._BLOCK_INV_MIN, _engine._BLOCK_INV_LEAF = 8, 4
+        _engine._BLOCK_INV_CUDA_ONLY = False
+        post2 = _engine.solve_posterior(torch.from_numpy(A), torch.from_numpy(Pf.T.dot(y)),
+                                        0.3, torch.from_numpy(lam))
+        ok = ok and np.allclose(post2.C.numpy(), Cref, rtol=1e-9, atol=1e-12)
         ret[rank] = bool(ok)
     finally:
         dist.destroy_process_group()
