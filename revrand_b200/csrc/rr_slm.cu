@@ -11,8 +11,11 @@ namespace rr {
 constexpr int64_t SIMT_CHUNK = 8192;  // rows of Phi held in the workspace
 // RR_ENGINE_AUTO runs the fused tcgen05 engine from this many rows on; below it
 // the job is launch-latency sized and the chunked SIMT engine (fp32 features,
-// float64 Gram accumulation) is both fast enough and the most accurate.
-constexpr int64_t TC_AUTO_MIN_ROWS = 8192;
+// float64 Gram accumulation) is both fast enough and the most accurate.  The
+// tcgen05 value pass carries a zero-mean 2^-17 perturbation per trig value whose
+// effect on the posterior shrinks as 1/sqrt(N); small ill-conditioned problems
+// (tests: 256 frequencies on 1000 1-D points) need the SIMT engine for 1e-4.
+constexpr int64_t TC_AUTO_MIN_ROWS = 16384;
 
 // 1 = tcgen05, 0 = SIMT, -1 = tcgen05 demanded but unsupported.
 static int pick_engine(int engine, const rr_plan* plan, int64_t N) {

@@ -248,6 +248,9 @@ __device__ __forceinline__ bool mbar_try_wait_cl(uint64_t* bar, uint32_t parity)
 }
 __device__ __forceinline__ void mbar_wait_cl(uint64_t* bar, uint32_t parity) {
   while (!mbar_try_wait_cl(bar, parity)) {
+#ifdef RR_MBAR_BACKOFF
+    __nanosleep(RR_MBAR_BACKOFF);   // experiment: fewer polls, less issue power
+#endif
   }
 }
 

@@ -3,11 +3,8 @@ macro (results are garbage; only the timing matters)."""
 import glob, os, subprocess, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 CSRC = os.path.join(ROOT, "revrand_b200", "csrc")
-VARIANTS = {"base": [], "halfgen": ["-DRR_T2_EXP_HALFGEN"],
-            "nomma2": ["-DRR_T2_EXP_NOMMA2"],
-            "halfgen_nomma2": ["-DRR_T2_EXP_HALFGEN", "-DRR_T2_EXP_NOMMA2"],
-            "all_off": ["-DRR_T2_EXP_HALFGEN", "-DRR_T2_EXP_NOMMA2", "-DRR_T2_EXP_NOPROJ",
-                        "-DRR_T2_EXP_NODRAIN", "-DRR_T2_EXP_NOSTS", "-DRR_T2_EXP_NOMUFU"]}
+VARIANTS = {"base": [], "backoff20": ["-DRR_MBAR_BACKOFF=20"], "backoff100": ["-DRR_MBAR_BACKOFF=100"],
+            "hint": ["-DRR_MBAR_SUSPEND_HINT"], "base2": []}
 def lib(v):
     return os.path.join(ROOT, "revrand_b200", "lib", "librevrand_b200_exp_%s.so" % v)
 if "--build" in sys.argv:
@@ -25,11 +22,11 @@ if len(sys.argv) > 1 and sys.argv[1] in VARIANTS:
     from revrand_b200.basis_functions import RandomMatern32
     from revrand_b200.slm import _SLMProblem
     from bench import synthetic
-    X, y = synthetic(500000, 21)
+    X, y = synthetic(1000000, 21)
     prob = _SLMProblem(RandomMatern32(nbases=2048, Xdim=21, random_state=1), X, y)
     prob.plan.set_lenscales([4.0])
     ts = []
-    for _ in range(4):
+    for _ in range(8):
         prob.stats.zero_()
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a.record()
@@ -37,7 +34,7 @@ if len(sys.argv) > 1 and sys.argv[1] in VARIANTS:
         b.record()
         torch.cuda.synchronize()
         ts.append(a.elapsed_time(b))
-    print("%-14s N=5e5 suffstats ms: %s" % (sys.argv[1], " ".join("%.2f" % t for t in ts)), flush=True)
+    print("%-14s N=1e6 suffstats ms: %s" % (sys.argv[1], " ".join("%.2f" % t for t in ts)), flush=True)
 else:
     for v in VARIANTS:
         subprocess.call([sys.executable, os.path.abspath(__file__), v])
