@@ -14,7 +14,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "lib", "librevrand_b200.so")
 
-RR_ENGINE_AUTO, RR_ENGINE_SIMT, RR_ENGINE_TCGEN05 = 0, 1, 2
+RR_ENGINE_AUTO, RR_ENGINE_SIMT, RR_ENGINE_TCGEN05, RR_ENGINE_TCGEN05_FINE = 0, 1, 2, 3
 RR_OP_SUFFSTATS, RR_OP_GRADPASS, RR_OP_PREDICT = 1, 2, 3
 RR_OP_GLM_STEP, RR_OP_GLM_PREDICT, RR_OP_RESIDUAL = 4, 5, 6
 (RR_LIK_GAUSSIAN, RR_LIK_BERNOULLI, RR_LIK_BINOMIAL, RR_LIK_POISSON_EXP,

@@ -386,9 +386,11 @@ class Posterior(object):
     an evaluation only needs diag(C), m, logdet and -- for the gradient pass --
     a float32 image of C."""
 
-    def __init__(self, m, diagC, logdet, trgc, Linv=None, C=None):
+    def __init__(self, m, diagC, logdet, trgc, Linv=None, C=None, dg=None):
         self.m, self.diagC, self.logdet, self.trgc = m, diagC, logdet, trgc
         self._Linv, self._C = Linv, C
+        # (max / min of the Cholesky diagonal)^2: a cheap lower bound on cond(iC)
+        self.cond_est = None if dg is None else (dg.max() / dg.min()) ** 2
 
     @property
     def C(self):
@@ -528,7 +530,7 @@ def solve_posterior(G, p, var, lam, need_C=True):
         m = (Cm @ p) / var
         logdet = 2.0 * t.log(dg).sum()
         trgc = var * (D - (diagC / lam).sum())
-        return Posterior(m, diagC, logdet, trgc, C=Cm)
+        return Posterior(m, diagC, logdet, trgc, C=Cm, dg=dg)
     if ok:
         if _use_blocked(L):
             Linv = t.empty_like(L)
@@ -540,7 +542,7 @@ def solve_posterior(G, p, var, lam, need_C=True):
         m = (Linv.T @ (Linv @ p)) / var
         logdet = 2.0 * t.log(dg).sum()
         trgc = var * (D - (diagC / lam).sum())
-        return Posterior(m, diagC, logdet, trgc, Linv=Linv)
+        return Posterior(m, diagC, logdet, trgc, Linv=Linv, dg=dg)
     U, s, Vh = t.linalg.svd(iC)
     sc = t.clamp(s, min=SVD_FLOOR)
     Cm = (U / sc) @ Vh

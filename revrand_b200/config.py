@@ -17,9 +17,18 @@ ENGINE = os.environ.get("REVRAND_B200_ENGINE", "auto")
 def engine_code():
     from . import _cabi
     return {"auto": _cabi.RR_ENGINE_AUTO, "simt": _cabi.RR_ENGINE_SIMT,
-            "tcgen05": _cabi.RR_ENGINE_TCGEN05}[ENGINE]
+            "tcgen05": _cabi.RR_ENGINE_TCGEN05,
+            "tcgen05_fine": _cabi.RR_ENGINE_TCGEN05_FINE}[ENGINE]
 
 # Draw the GLM reparameterisation noise on the host from the model's
 # RandomState in the reference's order (slow: K_mix*L*D normals per step)
 # instead of on the device.
 GLM_HOST_RNG = os.environ.get("REVRAND_B200_HOST_RNG", "0") == "1"
+
+# The fused tcgen05 value pass perturbs every trig value by ~2e-6 (zero mean);
+# log-ML and its gradients stay within 1e-4, but the posterior moments of an
+# ill-conditioned evaluation inherit cond * noise / sqrt(N).  When the cheap
+# conditioning estimate of the BEST evaluation exceeds this threshold, the
+# reported posterior (weights_, covariance_) is recomputed once with the SIMT
+# engine (fp32 features, float64 accumulation).  0 disables the polish.
+POLISH_COND = float(os.environ.get("REVRAND_B200_POLISH_COND", "1e3"))

@@ -96,7 +96,7 @@ int launch_features(const rr_plan* plan, const float* X, int64_t N, float* Phi,
 int tc_suffstats_supported(const rr_plan* plan);
 size_t tc_suffstats_workspace(const rr_plan* plan, int64_t N);
 int tc_suffstats(const rr_plan* plan, const float* X, const float* y, int64_t N,
-                 double* G, double* p, void* ws, size_t ws_bytes,
+                 double* G, double* p, void* ws, size_t ws_bytes, int grid_bits,
                  cudaStream_t st);
 size_t tc_gradpass_workspace(const rr_plan* plan, int64_t N);
 int tc_gradpass(const rr_plan* plan, const float* X, const float* y, int64_t N,

@@ -20,7 +20,7 @@ constexpr int64_t TC_AUTO_MIN_ROWS = 16384;
 // 1 = tcgen05, 0 = SIMT, -1 = tcgen05 demanded but unsupported.
 static int pick_engine(int engine, const rr_plan* plan, int64_t N) {
   const bool tc_ok = tc_suffstats_supported(plan) != 0;
-  if (engine == RR_ENGINE_TCGEN05) return tc_ok ? 1 : -1;
+  if (engine == RR_ENGINE_TCGEN05 || engine == RR_ENGINE_TCGEN05_FINE) return tc_ok ? 1 : -1;
   if (engine == RR_ENGINE_SIMT) return 0;
   return (tc_ok && N >= TC_AUTO_MIN_ROWS) ? 1 : 0;
 }
@@ -185,7 +185,8 @@ extern "C" int rr_slm_suffstats(const rr_plan* plan, const float* X,
     return RR_ERR_UNSUPPORTED;
   }
   if (use_tc)
-    return tc_suffstats(plan, X, y, N, G, p, workspace, workspace_bytes, st);
+    return tc_suffstats(plan, X, y, N, G, p, workspace, workspace_bytes,
+                        engine == RR_ENGINE_TCGEN05_FINE ? 7 : 5, st);
   return simt_suffstats(plan, X, y, N, G, y ? p : nullptr, workspace,
                         workspace_bytes, st);
 }

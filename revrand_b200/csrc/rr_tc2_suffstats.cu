@@ -50,9 +50,11 @@ constexpr int T2_NCOL = 4 * T2_NB;   // 224 accumulator columns
 constexpr int T2_TILE_GROUP = 74;    // tiles whose scratch images are hot together
 constexpr int T2_XSTAGES = 3;
 constexpr int T2_PSTAGES = 2;
-constexpr int T2_CHAIN = 16384;      // rows per exact accumulation chain
-constexpr int T2_SUPER = 32768;      // rows per work item (2 chains)
-constexpr float T2_GRID_MAGIC = 393216.0f;  // 1.5 * 2^18: (c + M) - M rounds to 2^-5
+// The fixed-point grid of h1 is a run-time choice: grid 2^-g, magic 1.5 * 2^(23-g)
+// ((c + M) - M rounds c to the grid), exact chains of 2^(24-2g) rows.  g = 5 is the
+// default (16384-row chains); g = 7 quarters the rounding error of the remainder r
+// (|r| <= 2^-8) at the price of a drain every 1024 rows.
+constexpr int T2_SUPER = 32768;      // rows per work item
 constexpr float T2_RINT_MAGIC = 12582912.0f;  // 1.5 * 2^23
 constexpr float T2_TWO_PI = 6.283185307179586f;
 
@@ -185,6 +187,7 @@ struct T2GenCtx {
   uint32_t base;                     // shared address of the current Phi stage
   uint64_t* empty_bar;               // stage-free barrier, waited before the first store
   uint32_t empty_parity;
+  float grid_magic;
 #ifdef RR_T2_TRACE
   bool trw;
   int trs, trb;
@@ -246,7 +249,7 @@ __device__ __forceinline__ void t2_gen_slab(const T2GenCtx& cx, const float* u,
                                             const float* yrow, uint64_t& pc2,
                                             uint64_t& ps2) {
   const uint64_t RM2 = f2_pack(T2_RINT_MAGIC, T2_RINT_MAGIC);
-  const uint64_t GM2 = f2_pack(T2_GRID_MAGIC, T2_GRID_MAGIC);
+  const uint64_t GM2 = f2_pack(cx.grid_magic, cx.grid_magic);
   const uint64_t TP2 = f2_pack(T2_TWO_PI, T2_TWO_PI);
   uint64_t c2[T2_GPAIRS], s2[T2_GPAIRS];
   uint4 hc, rc, hs, rs, cf, sf;
@@ -340,7 +343,7 @@ __global__ void __launch_bounds__(T2_THREADS, 1)
 tc2_suffstats_kernel(rr_plan plan, const float* __restrict__ X,
                      const float* __restrict__ y, int64_t N, double* __restrict__ T,
                      double* __restrict__ p, int NIB, int NJB, int ntiles,
-                     int nitems, int64_t rpi) {
+                     int nitems, int64_t rpi, float grid_magic, int chain_rows) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>(
       (reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -423,7 +426,7 @@ tc2_suffstats_kernel(rr_plan plan, const float* __restrict__ X,
       for (int item = pair; item < nitems; item += npairs, ++itc) {
         const T2Item it = t2_decode(item, ntiles, NIB, NJB, N, rpi);
         const int nsl = (int)((it.r1 - it.r0 + T2_SLAB - 1) / T2_SLAB);
-        constexpr int SPC = T2_CHAIN / T2_SLAB;
+        const int SPC = chain_rows / T2_SLAB;
         mbar_wait_cl(&sb.w_full, itc & 1);
         // Tensor-pipe order  P(0) P(1) | P(2) G(0) | P(3) G(1) | ...  (P = projection,
         // G = Gram update).  U is single-buffered, so P(t+2) can only be issued once
@@ -622,6 +625,7 @@ tc2_suffstats_kernel(rr_plan plan, const float* __restrict__ X,
     // byte offsets of this thread's 16-byte chunks inside one operand image
     // (fixed for the whole kernel: row and chunk index never change)
     T2GenCtx cx;
+    cx.grid_magic = grid_magic;
     {
       const uint32_t row_cos = is_a ? (uint32_t)fl : (uint32_t)(fl - T2_NA);
       const uint32_t row_sin = row_cos + (is_a ? (uint32_t)T2_NA : (uint32_t)T2_NB);
@@ -725,7 +729,7 @@ tc2_suffstats_kernel(rr_plan plan, const float* __restrict__ X,
     for (int item = pair; item < nitems; item += npairs) {
       const T2Item it = t2_decode(item, ntiles, NIB, NJB, N, rpi);
       const int64_t rows = it.r1 - it.r0;
-      const int nch = (int)((rows + T2_CHAIN - 1) / T2_CHAIN);
+      const int nch = (int)((rows + chain_rows - 1) / chain_rows);
       // column tables (safe to rewrite: every epilogue warp has finished the
       // previous item before any of them passes the barrier below)
       asm volatile("bar.sync 2, 128;" ::: "memory");
@@ -844,7 +848,14 @@ size_t tc_suffstats_workspace(const rr_plan* pl, int64_t) {
 }
 
 int tc_suffstats(const rr_plan* pl, const float* X, const float* y, int64_t N,
-                 double* G, double* p, void* ws, size_t ws_bytes, cudaStream_t st) {
+                 double* G, double* p, void* ws, size_t ws_bytes, int grid_bits,
+                 cudaStream_t st) {
+  if (grid_bits < 5 || grid_bits > 8) {
+    set_error("tcgen05 suffstats: grid_bits must be 5..8");
+    return RR_ERR_INVALID;
+  }
+  const float grid_magic = 1.5f * (float)(1 << (23 - grid_bits));
+  const int chain_rows = 1 << (24 - 2 * grid_bits);
   const int D = pl->D;
   Workspace W(ws, ws_bytes);
   double* T = W.take<double>((size_t)D * D);
@@ -883,7 +894,7 @@ int tc_suffstats(const rr_plan* pl, const float* X, const float* y, int64_t N,
   cfg.attrs = attr;
   cfg.numAttrs = 1;
   RR_CUDA_CHECK(cudaLaunchKernelEx(&cfg, tc2_suffstats_kernel, *pl, X, y, N, T, p, NIB,
-                                   NJB, ntiles, (int)nitems, rpi));
+                                   NJB, ntiles, (int)nitems, rpi, grid_magic, chain_rows));
   RR_LAUNCH_CHECK("tc2_suffstats_kernel");
   dim3 fg((D + 31) / 32, (D + 31) / 32);
   t2_finalize_kernel<<<fg, 256, 0, st>>>(T, camp, G, D);

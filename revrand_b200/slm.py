@@ -61,6 +61,30 @@ class _SLMProblem(object):
         self.yy = None
         self.engine = config.engine_code()
 
+    def uses_tcgen05(self):
+        """True when RR_ENGINE_AUTO / tcgen05 routes this problem's value pass
+        to the fused tensor-core kernel (mirrors pick_engine in rr_slm.cu)."""
+        from . import _cabi
+        if self.engine == _cabi.RR_ENGINE_SIMT or not self.plan.tcgen05_ok():
+            return False
+        return self.engine != _cabi.RR_ENGINE_AUTO or self.Xd.shape[0] >= 16384
+
+    def polish(self, var, regs, hypers):
+        """Posterior at the given hyper-parameters from the SIMT engine's
+        statistics (fp32 features, float64 accumulation)."""
+        from . import _cabi
+        t = eng.torch()
+        plan, st = self.plan, self.stats
+        if plan.trig:
+            plan.set_lenscales([h for h in hypers])
+        st.zero_()
+        eng.slm_suffstats(plan, self.Xd, self.yd, st, engine=_cabi.RR_ENGINE_SIMT,
+                          want_yy=False)
+        eng.allreduce_sum_(st.flat)
+        lam_np, _ = self.basis.regularizer_diagonal(self.Xhost_probe, *regs)
+        lam = eng.to_device(lam_np, t.float64)
+        return eng.solve_posterior(st.G, st.p, float(var), lam, need_C=True)
+
     def evaluate(self, var, regs, hypers, want_grad=True):
         """Return dict of host scalars + device posterior for one eval."""
         t = eng.torch()
@@ -91,7 +115,8 @@ class _SLMProblem(object):
         else:
             eng.slm_residual(plan, self.Xd, self.yd, m32, sqerr=self.sqerr)
         eng.allreduce_sum_(self.rflat)
-        parts = [logdet.reshape(1), trgc.reshape(1), self.sqerr, q]
+        cond = post.cond_est if post.cond_est is not None else logdet.new_zeros(())
+        parts = [logdet.reshape(1), trgc.reshape(1), self.sqerr, cond.reshape(1), q]
         if want_grad and plan.ktot:
             WR = plan._Wfull_dev * self.R[:, :plan.ktot]
             g = t.stack([WR[:, ko:ko + b.K].sum(dim=1)
@@ -99,9 +124,10 @@ class _SLMProblem(object):
             parts.append(g.reshape(-1))
         host = t.cat(parts).cpu().numpy()
         out["logdet"], out["trgc"], out["sqerr"] = host[0], host[1], host[2]
-        out["q"] = host[3:3 + len(slices)]
+        out["cond_est"] = host[3]
+        out["q"] = host[4:4 + len(slices)]
         if g is not None:
-            out["g"] = host[3 + len(slices):].reshape(len(plan.trig), plan.d)
+            out["g"] = host[4 + len(slices):].reshape(len(plan.trig), plan.d)
         return out
 
 
@@ -157,7 +183,7 @@ class StandardLinearModel(BaseEstimator, RegressorMixin):
                    options={'maxiter': self.maxiter, 'maxcor': 100},
                    random_state=self.random_, nstarts=self.nstarts)
         self.var_, self.regularizer_, self.hypers_ = res.x
-        self._sync_posterior()
+        self._sync_posterior(self._problem)
         log.info("Done! ELBO = {}, var = {}, reg = {}, hypers = {}, "
                  "message = {}.".format(-res['fun'], self.var_,
                                         self.regularizer_, self.hypers_,
@@ -216,9 +242,10 @@ class StandardLinearModel(BaseEstimator, RegressorMixin):
                        + np.log(lam).sum() - D)
         if ELBO > self.obj_:
             self._m_dev, self._post = r["m"], r["post"]
+            self._best_point = (var, regs, hyps, float(r["cond_est"]))
             self.obj_ = ELBO
             if getattr(self, "_problem", None) is None:
-                self._sync_posterior()
+                self._sync_posterior(prob)
         if log.isEnabledFor(logging.INFO):
             log.info("ELBO = {}, var = {}, reg = {}, hypers = {}."
                      .format(ELBO, var, reg, hypers))
@@ -243,8 +270,18 @@ class StandardLinearModel(BaseEstimator, RegressorMixin):
         dhypers = dh if len(dh) != 1 else dh[0]
         return -ELBO, [-dvar, dL, dhypers]
 
-    def _sync_posterior(self):
-        """Materialise the cached best posterior as numpy attributes."""
+    def _sync_posterior(self, prob=None):
+        """Materialise the cached best posterior as numpy attributes.  If it came
+        from the fused tcgen05 value pass at an ill-conditioned point
+        (config.POLISH_COND), recompute it once with the SIMT engine: the fast
+        engine's log-ML and gradients hold 1e-4 everywhere, its posterior
+        moments only where the conditioning is moderate."""
+        best = getattr(self, "_best_point", None)
+        if (prob is not None and best is not None and config.POLISH_COND > 0
+                and best[3] > config.POLISH_COND and prob.uses_tcgen05()):
+            post = prob.polish(best[0], best[1], best[2])
+            self._m_dev, self._post = post.m, post
+            self._best_point = best[:3] + (0.0,)
         if getattr(self, "_m_dev", None) is not None:
             self.weights_ = self._m_dev.cpu().numpy()
             self.covariance_ = self._post.C.cpu().numpy()
@@ -274,7 +311,7 @@ class StandardLinearModel(BaseEstimator, RegressorMixin):
     def __getstate__(self):
         state = dict(self.__dict__)
         for k in ("_problem", "_cached_problem", "_problem_key", "_m_dev",
-                  "_post"):
+                  "_post", "_best_point"):
             state.pop(k, None)
         return state
 
