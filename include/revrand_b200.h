@@ -63,6 +63,15 @@ typedef struct rr_plan {
   const int32_t* ext_src; /* (next)                                          */
   const float* ext_val;   /* (next)                                          */
   const int32_t* ext_col; /* (next)                                          */
+  /* Optional (NULL = all trigonometric): per-frequency slot kind for the fused
+   * tcgen05 value pass, which can carry affine columns as pseudo-frequencies:
+   *   0: cos/sin pair of 2*pi*u (as above)
+   *   1: linear slot -- the single feature amp[k] * u, written to col_cos[k]
+   *      (u = sum_i X[n,i] Wt[i,k]: Wt selects and scales one input column so
+   *      that |u| <= 1; amp undoes the scale); col_sin[k] must be -1
+   *   2: constant slot -- the single feature amp[k] in col_cos[k]; col_sin[k] = -1
+   * A plan with kind != NULL must have next == 0 (the affine columns ARE slots). */
+  const uint8_t* kind;  /* (ktot) or NULL                                    */
 } rr_plan;
 
 /* Likelihood ids for rr_glm_step; revrand/likelihoods.py:18-545. */

@@ -30,6 +30,7 @@ class RRPlan(C.Structure):
         ("col_cos", C.c_void_p), ("col_sin", C.c_void_p),
         ("ext_src", C.c_void_p), ("ext_val", C.c_void_p),
         ("ext_col", C.c_void_p),
+        ("kind", C.c_void_p),
     ]
 
 

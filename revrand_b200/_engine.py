@@ -144,6 +144,52 @@ class FeaturePlan(object):
         self._Wt = t.zeros((self.d, max(self.ktot, 1)), dtype=f32,
                            device=device())
         self.struct = RRPlan()
+        self.struct_tc = None      # extended plan (affine columns as slots), see below
+        self._ext_host = (cat(ext_src, np.int32), cat(ext_val, np.float32),
+                          cat(ext_col, np.int32))
+        self.refresh()
+
+    def enable_tc_extras(self, col_absmax):
+        """Let the fused tcgen05 value pass carry the affine (Linear / Bias)
+        columns as pseudo-frequency slots (rr_plan.kind): slot j projects
+        u = X[:, src] / max|X[:, src]| (|u| <= 1, as the fixed-point split of
+        the kernel requires) and its amplitude undoes the scale; constant
+        columns are slots of kind 2.  ``col_absmax``: (d,) max |X[:, i]| over
+        ALL rows of the job (all ranks)."""
+        t = torch()
+        if not (self.next and self.ktot):
+            return
+        src, val, col = self._ext_host
+        ktx = self.ktot + self.next
+        scale = np.maximum(np.asarray(col_absmax, dtype=np.float64), 1e-30)
+        Wx = np.zeros((self.d, self.next), dtype=np.float32)
+        amp = np.zeros(self.next, dtype=np.float32)
+        kind = np.zeros(ktx, dtype=np.uint8)
+        for j in range(self.next):
+            if src[j] >= 0:
+                Wx[src[j], j] = 1.0 / scale[src[j]]
+                amp[j] = scale[src[j]]
+                kind[self.ktot + j] = 1
+            else:
+                amp[j] = val[j]
+                kind[self.ktot + j] = 2
+        i32, f32 = t.int32, t.float32
+        self._Wt_x = t.zeros((self.d, ktx), dtype=f32, device=device())
+        self._Wt_x[:, self.ktot:] = to_device(Wx, f32)
+        self._amp_x = t.cat([self._amp, to_device(amp, f32)])
+        self._col_cos_x = t.cat([self._col_cos, to_device(col, i32)])
+        self._col_sin_x = t.cat([self._col_sin,
+                                 t.full((self.next,), -1, dtype=i32, device=device())])
+        self._kind_x = to_device(kind, t.uint8)
+        s = RRPlan()
+        s.d, s.ktot, s.next, s.D = self.d, ktx, 0, self.D
+        s.Wt = self._Wt_x.data_ptr()
+        s.amp = self._amp_x.data_ptr()
+        s.col_cos = self._col_cos_x.data_ptr()
+        s.col_sin = self._col_sin_x.data_ptr()
+        s.ext_src = s.ext_val = s.ext_col = None
+        s.kind = self._kind_x.data_ptr()
+        self.struct_tc = s
         self.refresh()
 
     def set_lenscales(self, lenscales):
@@ -179,8 +225,13 @@ class FeaturePlan(object):
         s.ext_src = self._ext_src.data_ptr()
         s.ext_val = self._ext_val.data_ptr()
         s.ext_col = self._ext_col.data_ptr()
+        s.kind = None
+        if self.struct_tc is not None:
+            self._Wt_x[:, :self.ktot].copy_(self._Wt)
 
     def tcgen05_ok(self):
+        if self.next:
+            return self.struct_tc is not None and self.d <= 32
         return bool(_cabi.load().rr_tcgen05_supported(self.d, self.ktot,
                                                      self.next, self.D))
 
@@ -280,8 +331,13 @@ def slm_suffstats(plan, Xd, yd, stats, engine=_cabi.RR_ENGINE_AUTO,
     lib = _cabi.load()
     N = Xd.shape[0]
     nb = _ws_bytes(_cabi.RR_OP_SUFFSTATS, N, plan, engine=engine)
+    struct = plan.struct
+    if plan.struct_tc is not None and engine != _cabi.RR_ENGINE_SIMT:
+        # affine columns ride along as pseudo-frequency slots of the fused kernel
+        struct = plan.struct_tc
+        nb = max(nb, plan.D * plan.D * 8 + plan.D * 4 + 8192)
     ws = workspace(nb)
-    check(lib.rr_slm_suffstats(C.byref(plan.struct), _ptr(Xd), _ptr(yd), N,
+    check(lib.rr_slm_suffstats(C.byref(struct), _ptr(Xd), _ptr(yd), N,
                                _ptr(stats.G), _ptr(stats.p),
                                _ptr(stats.yy) if want_yy else C.c_void_p(0),
                                _ptr(ws), ws.numel(), engine, _stream_ptr()),

@@ -247,7 +247,7 @@ template <bool MASKED, bool DO_P>
 __device__ __forceinline__ void t2_gen_slab(const T2GenCtx& cx, const float* u,
                                             uint32_t live, bool is_b, bool store,
                                             const float* yrow, uint64_t& pc2,
-                                            uint64_t& ps2) {
+                                            uint64_t& ps2, int kind = 0) {
   const uint64_t RM2 = f2_pack(T2_RINT_MAGIC, T2_RINT_MAGIC);
   const uint64_t GM2 = f2_pack(cx.grid_magic, cx.grid_magic);
   const uint64_t TP2 = f2_pack(T2_TWO_PI, T2_TWO_PI);
@@ -268,6 +268,15 @@ __device__ __forceinline__ void t2_gen_slab(const T2GenCtx& cx, const float* u,
     f2_unpack(ang, a0, a1);
     float c0 = __cosf(a0), s0 = __sinf(a0), c1 = __cosf(a1), s1 = __sinf(a1);
     if (MASKED) {
+      // pseudo-frequency slots (affine columns): "cos" = u or 1, "sin" = 0
+      if (kind == 1) {
+        c0 = u[2 * i];
+        c1 = u[2 * i + 1];
+        s0 = s1 = 0.0f;
+      } else if (kind == 2) {
+        c0 = c1 = 1.0f;
+        s0 = s1 = 0.0f;
+      }
       const bool on0 = (live >> (2 * i)) & 1u, on1 = (live >> (2 * i + 1)) & 1u;
       c0 = on0 ? c0 : 0.0f;
       s0 = on0 ? s0 : 0.0f;
@@ -643,8 +652,10 @@ tc2_suffstats_kernel(rr_plan plan, const float* __restrict__ X,
       const int theta = is_a ? T2_IB * it.ib + T2_NA * (int)crank + fl
                              : T2_JB * it.jb + T2_NB * (int)crank + (fl - T2_NA);
       const bool valid = has_row && theta < ktot;
-      // lanes without a feature row store nothing: they may run the unmasked code
-      const bool all_valid = __all_sync(0xffffffffu, valid || !has_row);
+      const int kind = (valid && plan.kind != nullptr) ? (int)plan.kind[theta] : 0;
+      // lanes without a feature row store nothing: they may run the unmasked code;
+      // warps that hold pseudo-frequency slots take the masked (general) variant
+      const bool all_valid = __all_sync(0xffffffffu, (valid && kind == 0) || !has_row);
       // ---- W tile of this item (previous item's projections have all completed:
       //      this thread has consumed their U) -------------------------------------
       if (h == 0) {   // one warp per lane quadrant writes the W tile
@@ -697,7 +708,7 @@ tc2_suffstats_kernel(rr_plan plan, const float* __restrict__ X,
         if (want_p) {   // warp-uniform, designated A tiles only
           uint64_t pc2 = 0ull, ps2 = 0ull;   // (+0.0f, +0.0f)
           const float* yrow = y + row0 + T2_GROWS * h;
-          if (masked) t2_gen_slab<true, true>(cx, u, live, false, true, yrow, pc2, ps2);
+          if (masked) t2_gen_slab<true, true>(cx, u, live, false, true, yrow, pc2, ps2, kind);
           else t2_gen_slab<false, true>(cx, u, live, false, true, yrow, pc2, ps2);
           float a0, a1, b0, b1;
           f2_unpack(pc2, a0, a1);
@@ -706,7 +717,7 @@ tc2_suffstats_kernel(rr_plan plan, const float* __restrict__ X,
           ps_d += (double)b0 + (double)b1;
         } else {
           uint64_t dummy0 = 0ull, dummy1 = 0ull;
-          if (masked) t2_gen_slab<true, false>(cx, u, has_row ? live : 0u, !is_a, has_row, nullptr, dummy0, dummy1);
+          if (masked) t2_gen_slab<true, false>(cx, u, has_row ? live : 0u, !is_a, has_row, nullptr, dummy0, dummy1, kind);
           else t2_gen_slab<false, false>(cx, u, live, !is_a, has_row, nullptr, dummy0, dummy1);
         }
         T2_TRACE(trw, gs, trb + 3);
@@ -716,8 +727,9 @@ tc2_suffstats_kernel(rr_plan plan, const float* __restrict__ X,
       }
       if (want_p && valid) {
         const double a = (double)plan.amp[theta];
-        atomicAdd(p + plan.col_cos[theta], a * pc_d);
-        atomicAdd(p + plan.col_sin[theta], a * ps_d);
+        const int cc = plan.col_cos[theta], cs = plan.col_sin[theta];
+        if (cc >= 0) atomicAdd(p + cc, a * pc_d);
+        if (cs >= 0) atomicAdd(p + cs, a * ps_d);
       }
     }
   } else {
@@ -740,14 +752,15 @@ tc2_suffstats_kernel(rr_plan plan, const float* __restrict__ X,
         const bool ok = th < ktot;
         const int col = ok ? (ty ? plan.col_sin[th] : plan.col_cos[th]) : -1;
         // invalid columns get a key below every row key, so one compare decides
-        sb.etab[j] = make_int2(ok ? col * D : 0, ok ? 2 * th + ty : -1);
+        sb.etab[j] = make_int2(col >= 0 ? col * D : 0, col >= 0 ? 2 * th + ty : -1);
       }
       asm volatile("bar.sync 2, 128;" ::: "memory");
       const int theta_a = T2_IB * it.ib + T2_NA * (int)crank + (L & 63);
       const bool valid_a = theta_a < ktot;
-      const int ca = valid_a ? (type_a ? plan.col_sin[theta_a] : plan.col_cos[theta_a]) : 0;
+      const int ca_raw = valid_a ? (type_a ? plan.col_sin[theta_a] : plan.col_cos[theta_a]) : -1;
+      const int ca = ca_raw >= 0 ? ca_raw : 0;
       // rows that own no feature never pass the key test
-      const int key_a = valid_a ? 2 * theta_a + type_a : 0x7fffffff;
+      const int key_a = ca_raw >= 0 ? 2 * theta_a + type_a : 0x7fffffff;
       double* Tca = T + ca;
       for (int ch = 0; ch < nch; ++ch, ++gc) {
         mbar_wait_cl(&sb.acc_full, gc & 1);
@@ -804,8 +817,8 @@ __global__ void t2_colamp_kernel(rr_plan plan, float* __restrict__ camp) {
   const int th = blockIdx.x * blockDim.x + threadIdx.x;
   if (th < plan.ktot) {
     const float a = plan.amp[th];
-    camp[plan.col_cos[th]] = a;
-    camp[plan.col_sin[th]] = a;
+    if (plan.col_cos[th] >= 0) camp[plan.col_cos[th]] = a;
+    if (plan.col_sin[th] >= 0) camp[plan.col_sin[th]] = a;
   }
 }
 
@@ -838,8 +851,10 @@ t2_finalize_kernel(const double* __restrict__ T, const float* __restrict__ camp,
 // Host side
 // ---------------------------------------------------------------------------
 int tc_suffstats_supported(const rr_plan* pl) {
-  return (pl->d >= 1 && pl->d <= 32 && pl->ktot >= 1 && pl->next == 0 &&
-          pl->D == 2 * pl->ktot) ? 1 : 0;
+  // pure trigonometric plans, or plans whose affine columns ride along as
+  // pseudo-frequency slots (kind != NULL; then D <= 2 * ktot)
+  if (pl->d < 1 || pl->d > 32 || pl->ktot < 1 || pl->next != 0) return 0;
+  return (pl->kind != nullptr ? pl->D <= 2 * pl->ktot : pl->D == 2 * pl->ktot) ? 1 : 0;
 }
 
 size_t tc_suffstats_workspace(const rr_plan* pl, int64_t) {

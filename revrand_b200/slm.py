@@ -51,6 +51,14 @@ class _SLMProblem(object):
         self.Xhost_probe = np.asarray(X[:1], dtype=float)
         hyp0 = basis.params_values()
         self.plan = basis._plan(self.d, hyp0)
+        if self.plan.next and self.plan.ktot and self.d <= 32:
+            # concatenated bases: the fused value pass carries the Linear / Bias
+            # columns as pseudo-frequency slots scaled by max |X[:, i]| of the job
+            amax = (self.Xd.abs().amax(dim=0) if self.Xd.shape[0]
+                    else t.zeros(self.d, device=self.Xd.device)).double()
+            if self.world > 1:
+                t.distributed.all_reduce(amax, op=t.distributed.ReduceOp.MAX)
+            self.plan.enable_tc_extras(amax.cpu().numpy())
         self.D = self.plan.D
         self.stats = eng.SuffStats(self.D)
         self.first = True

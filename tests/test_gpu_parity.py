@@ -288,6 +288,38 @@ def test_fused_suffstats_vs_oracle(K, d, N):
             y.astype(np.float32).astype(float))) < 1e-6 * y.dot(y)
 
 
+def test_fused_suffstats_with_affine_columns():
+    """BasisCat(RandomRBF + LinearBasis(onescol) + BiasBasis): the fused tcgen05
+    value pass carries the 1 + d + 1 affine columns as pseudo-frequency slots
+    (rr_plan.kind); G and Phi^T y of the whole concatenation against float64."""
+    N, d, K = 20011, 5, 100
+    X, y = _synthetic(N, d, seed=5)
+    X[:, 2] *= 3.7            # unequal column scales
+    ls = 1.7
+    cat = (bf.RandomRBF(nbases=K, Xdim=d, random_state=3) + bf.LinearBasis(onescol=True)
+           + bf.BiasBasis(offset=2.5))
+    plan = cat._plan(d, [ls])
+    assert plan.next == d + 2 and not plan.tcgen05_ok()
+    plan.enable_tc_extras(np.abs(X).max(axis=0))
+    assert plan.tcgen05_ok()
+    Xd, yd = _engine.to_device(X), _engine.to_device(y)
+    blocks = [dict(kind="trig", W=cat.bases[0].W, lenscale=ls, cols=None),
+              dict(kind="linear", onescol=True, cols=None),
+              dict(kind="bias", offset=2.5, cols=None)]
+    Phi = orc.concat_features(X.astype(np.float32).astype(float), blocks)
+    Gref, pref = Phi.T.dot(Phi), Phi.T.dot(y.astype(np.float32).astype(float))
+    for engine in (_cabi.RR_ENGINE_TCGEN05, _cabi.RR_ENGINE_SIMT):
+        st = _engine.SuffStats(plan.D)
+        _engine.slm_suffstats(plan, Xd, yd, st, engine=engine)
+        G = st.G.cpu().numpy()
+        assert np.max(np.abs(G - G.T)) <= 1e-12 * np.max(np.abs(G)) + 1e-12
+        assert relerr(G, Gref) < 2e-6, engine
+        # the affine x affine block on its own (it is tiny next to the trig block)
+        assert relerr(G[2 * K:, 2 * K:], Gref[2 * K:, 2 * K:]) < 2e-6, engine
+        assert relerr(G[:2 * K, 2 * K:], Gref[:2 * K, 2 * K:]) < 5e-6, engine
+        assert relerr(st.p.cpu().numpy(), pref) < 5e-6, engine
+
+
 def test_full_size_properties_config2():
     """BASELINE config 2 shape (N=1e6, d=21, K=2048): size-independent
     properties of the fused value pass.
