@@ -16,6 +16,7 @@ from . import _cabi
 from ._cabi import RRPlan, RevrandB200Error, check
 
 CHOLTHRESH = 1e-5   # revrand/mathfun/linalg.py:31
+TC_AUTO_MIN_ROWS = 16384   # RR_ENGINE_AUTO: fused tcgen05 engine from here on (rr_slm.cu)
 SVD_FLOOR = 1e-15   # revrand/mathfun/linalg.py:128 (s_tol)
 TWO_PI = 2.0 * math.pi
 
@@ -332,7 +333,9 @@ def slm_suffstats(plan, Xd, yd, stats, engine=_cabi.RR_ENGINE_AUTO,
     N = Xd.shape[0]
     nb = _ws_bytes(_cabi.RR_OP_SUFFSTATS, N, plan, engine=engine)
     struct = plan.struct
-    if plan.struct_tc is not None and engine != _cabi.RR_ENGINE_SIMT:
+    use_tc = (engine in (_cabi.RR_ENGINE_TCGEN05, _cabi.RR_ENGINE_TCGEN05_FINE)
+              or (engine == _cabi.RR_ENGINE_AUTO and N >= TC_AUTO_MIN_ROWS))
+    if plan.struct_tc is not None and use_tc:
         # affine columns ride along as pseudo-frequency slots of the fused kernel
         struct = plan.struct_tc
         nb = max(nb, plan.D * plan.D * 8 + plan.D * 4 + 8192)

@@ -99,6 +99,7 @@ int tc_suffstats(const rr_plan* plan, const float* X, const float* y, int64_t N,
                  double* G, double* p, void* ws, size_t ws_bytes, int grid_bits,
                  cudaStream_t st);
 size_t tc_gradpass_workspace(const rr_plan* plan, int64_t N);
+int tc_gradpass_supported(const rr_plan* plan);
 int tc_gradpass(const rr_plan* plan, const float* X, const float* y, int64_t N,
                 const float* m, const float* C, double* R, double* sqerr, void* ws,
                 size_t ws_bytes, cudaStream_t st);

@@ -18,8 +18,8 @@ constexpr int64_t SIMT_CHUNK = 8192;  // rows of Phi held in the workspace
 constexpr int64_t TC_AUTO_MIN_ROWS = 16384;
 
 // 1 = tcgen05, 0 = SIMT, -1 = tcgen05 demanded but unsupported.
-static int pick_engine(int engine, const rr_plan* plan, int64_t N) {
-  const bool tc_ok = tc_suffstats_supported(plan) != 0;
+static int pick_engine(int engine, const rr_plan* plan, int64_t N, bool grad = false) {
+  const bool tc_ok = (grad ? tc_gradpass_supported(plan) : tc_suffstats_supported(plan)) != 0;
   if (engine == RR_ENGINE_TCGEN05 || engine == RR_ENGINE_TCGEN05_FINE) return tc_ok ? 1 : -1;
   if (engine == RR_ENGINE_SIMT) return 0;
   return (tc_ok && N >= TC_AUTO_MIN_ROWS) ? 1 : 0;
@@ -187,6 +187,11 @@ extern "C" int rr_slm_suffstats(const rr_plan* plan, const float* X,
   if (use_tc)
     return tc_suffstats(plan, X, y, N, G, p, workspace, workspace_bytes,
                         engine == RR_ENGINE_TCGEN05_FINE ? 7 : 5, st);
+  if (plan->kind != nullptr) {
+    set_error("a plan with pseudo-frequency slots (kind != NULL) is only understood by "
+              "the tcgen05 engine; pass the plain plan to the SIMT engine");
+    return RR_ERR_UNSUPPORTED;
+  }
   return simt_suffstats(plan, X, y, N, G, y ? p : nullptr, workspace,
                         workspace_bytes, st);
 }
@@ -217,7 +222,7 @@ extern "C" int rr_slm_gradpass(const rr_plan* plan, const float* X,
     if (!fbuf) { set_error("gradpass workspace too small"); return RR_ERR_WORKSPACE; }
     return phi_residual(plan, X, y, N, m, nullptr, sqerr, fbuf, st);
   }
-  const int use_tc = pick_engine(engine, plan, N);
+  const int use_tc = pick_engine(engine, plan, N, true);
   if (use_tc < 0) {
     set_error("tcgen05 engine does not support this plan");
     return RR_ERR_UNSUPPORTED;
@@ -260,7 +265,8 @@ extern "C" int rr_slm_predict(const rr_plan* plan, const float* X, int64_t N,
 namespace rr {
 size_t slm_workspace_bytes(int op, int64_t N, const rr_plan* pl, int engine) {
   size_t s = simt_ws(op, N, pl);
-  if (op != RR_OP_PREDICT && op != RR_OP_RESIDUAL && pick_engine(engine, pl, N) == 1) {
+  if (op != RR_OP_PREDICT && op != RR_OP_RESIDUAL &&
+      pick_engine(engine, pl, N, op == RR_OP_GRADPASS) == 1) {
     size_t t = op == RR_OP_SUFFSTATS ? tc_suffstats_workspace(pl, N)
                                      : tc_gradpass_workspace(pl, N);
     return t > 256 ? t : 256;

@@ -74,22 +74,32 @@ __global__ void absmax_kernel(const float* __restrict__ C, int64_t n,
 }
 
 // Bt[fo][fj] = s * amp_fj * C[col fo][col fj] as fp16, tile-major, s = 1/max|C|.
+// Rows fo: the Dp (padded) trigonometric output features; columns fj: all Dk
+// reduction features = the trigonometric ones followed by the affine columns
+// (Linear / Bias bases, amplitude 1) padded to a multiple of 64.
 __global__ void __launch_bounds__(256)
-prep_c_kernel(rr_plan plan, const float* __restrict__ C, int Dp,
+prep_c_kernel(rr_plan plan, const float* __restrict__ C, int Dp, int Dk,
               const unsigned int* __restrict__ cmax_bits, uint8_t* __restrict__ BtT) {
   const int fj = blockIdx.x * blockDim.x + threadIdx.x;
   const int fo = blockIdx.y;
-  if (fj >= Dp) return;
+  if (fj >= Dk) return;
   const float cmax = __uint_as_float(*cmax_bits);
   const float s = cmax > 0.0f ? 1.0f / cmax : 0.0f;
-  const int tj = feat_theta(fj), to = feat_theta(fo);
+  const int to = feat_theta(fo);
   float v = 0.0f;
-  if (tj < plan.ktot && to < plan.ktot) {
-    const int cj = feat_is_sin(fj) ? plan.col_sin[tj] : plan.col_cos[tj];
+  if (to < plan.ktot) {
     const int co = feat_is_sin(fo) ? plan.col_sin[to] : plan.col_cos[to];
-    v = s * plan.amp[tj] * C[(int64_t)co * plan.D + cj];
+    if (fj < Dp) {
+      const int tj = feat_theta(fj);
+      if (tj < plan.ktot) {
+        const int cj = feat_is_sin(fj) ? plan.col_sin[tj] : plan.col_cos[tj];
+        v = s * plan.amp[tj] * C[(int64_t)co * plan.D + cj];
+      }
+    } else if (fj - Dp < plan.next) {
+      v = s * C[(int64_t)co * plan.D + plan.ext_col[fj - Dp]];
+    }
   }
-  *reinterpret_cast<__half*>(BtT + tile_off(fo, fj, Dp / G2_KT)) = __float2half_rn(v);
+  *reinterpret_cast<__half*>(BtT + tile_off(fo, fj, Dk / G2_KT)) = __float2half_rn(v);
 }
 
 // ---- Phi chunk + fitted values --------------------------------------------------
@@ -104,8 +114,8 @@ constexpr int PE_ROWS = 16;
 constexpr int PE_PAIRS = 128;
 template <bool STORE>
 __global__ void __launch_bounds__(PE_PAIRS)
-phi_fit_kernel(rr_plan plan, const float* __restrict__ X, int rows, int Dp,
-               const float* __restrict__ m, uint8_t* __restrict__ PhT,
+phi_fit_kernel(rr_plan plan, const float* __restrict__ X, int rows, int Dp, int Dk,
+               int gy_trig, const float* __restrict__ m, uint8_t* __restrict__ PhT,
                float* __restrict__ fbuf) {
   extern __shared__ float xs[];            // PE_ROWS x d
   __shared__ float part[PE_PAIRS / 32][PE_ROWS];
@@ -117,6 +127,31 @@ phi_fit_kernel(rr_plan plan, const float* __restrict__ X, int rows, int Dp,
     xs[t] = (n0 + r < rows) ? X[(int64_t)n0 * d + t] : 0.0f;
   }
   __syncthreads();
+  if (STORE && (int)blockIdx.y >= gy_trig) {
+    // affine columns (Linear / Bias bases) of the chunk: internal features
+    // Dp + 2e, Dp + 2e + 1 as one half2 per row; zero padding up to Dk
+    const int e0 = 2 * (((int)blockIdx.y - gy_trig) * PE_PAIRS + tid);
+    if (Dp + e0 < Dk) {
+      const int fc = Dp + e0;
+      const int nkb = Dk / G2_KT;
+      uint8_t* img = PhT + ((int64_t)(n0 >> 8) * nkb + (fc >> 6)) * G2_IMG + (int64_t)(n0 & 255) * 128;
+      const uint32_t c4 = (uint32_t)((fc & 63) >> 3) << 4, inner = (uint32_t)(fc & 7) * 2;
+      const bool in0 = e0 < plan.next, in1 = e0 + 1 < plan.next;
+      const int s0 = in0 ? plan.ext_src[e0] : -1;           // < 0: constant column
+      const int s1 = in1 ? plan.ext_src[e0 + 1] : -1;
+      const float c0 = (in0 && s0 < 0) ? plan.ext_val[e0] : 0.0f;
+      const float c1 = (in1 && s1 < 0) ? plan.ext_val[e0 + 1] : 0.0f;
+#pragma unroll
+      for (int r = 0; r < PE_ROWS; ++r) {
+        const bool live = n0 + r < rows;
+        const float v0 = !live ? 0.0f : (s0 >= 0 ? xs[r * d + s0] : c0);
+        const float v1 = !live ? 0.0f : (s1 >= 0 ? xs[r * d + s1] : c1);
+        *reinterpret_cast<__half2*>(img + r * 128 + (c4 ^ ((uint32_t)(r & 7) << 4)) + inner) =
+            __floats2half2_rn(v0, v1);
+      }
+    }
+    return;
+  }
   const int th0 = 2 * (blockIdx.y * PE_PAIRS + tid);   // even frequency of this pair
   const bool v0 = th0 < ktot, v1 = th0 + 1 < ktot;
   float u0[PE_ROWS], u1[PE_ROWS];
@@ -148,9 +183,12 @@ phi_fit_kernel(rr_plan plan, const float* __restrict__ X, int rows, int Dp,
   // (the next k block); the 16-byte chunk index is XORed with (row & 7).
   uint8_t* img = nullptr;
   uint32_t inner = 0, c4 = 0;
-  if (STORE) {
+  // a block covers 2 * PE_PAIRS frequencies; when the padded frequency count is
+  // only half of that (ktot <= 64 mod 128) the upper threads own no column
+  const bool st_ok = STORE && th0 < Dp / 2;
+  if (st_ok) {
     const int fc = 128 * (th0 >> 6) + (th0 & 63);     // internal cos column of th0
-    const int nkb = Dp / G2_KT;
+    const int nkb = Dk / G2_KT;
     img = PhT + ((int64_t)(n0 >> 8) * nkb + (fc >> 6)) * G2_IMG + (int64_t)(n0 & 255) * 128;
     c4 = (uint32_t)((fc & 63) >> 3) << 4;
     inner = (uint32_t)(fc & 7) * 2;
@@ -171,7 +209,7 @@ phi_fit_kernel(rr_plan plan, const float* __restrict__ X, int rows, int Dp,
       c1 = __cosf(fr);
     }
     f[r] = fmaf(c0, mc0, fmaf(s0, ms0, fmaf(c1, mc1, s1 * ms1)));
-    if (STORE) {
+    if (st_ok) {
       // (n0 + r) & 7 == r & 7 because n0 is a multiple of 16
       uint8_t* p = img + r * 128 + (c4 ^ ((uint32_t)(r & 7) << 4)) + inner;
       *reinterpret_cast<__half2*>(p) = __floats2half2_rn(c0, c1);
@@ -220,14 +258,15 @@ resid_finish_kernel(const float* __restrict__ y, const float* __restrict__ fbuf,
 }
 
 static int launch_phi_fit(const rr_plan* pl, const float* X, int rows, int rows_pad, int Dp,
-                          const float* m, uint8_t* PhT, float* fbuf, cudaStream_t st) {
+                          int Dk, const float* m, uint8_t* PhT, float* fbuf, cudaStream_t st) {
   const int nth = PhT ? Dp / 2 : pl->ktot;             // padded frequency count when storing
   int gy = (nth + 2 * PE_PAIRS - 1) / (2 * PE_PAIRS);
   if (gy < 1) gy = 1;                                  // plans with no trig block: extras only
-  dim3 grid((PhT ? rows_pad : rows + PE_ROWS - 1) / PE_ROWS, gy);
+  const int gy_ext = PhT ? ((Dk - Dp) / 2 + PE_PAIRS - 1) / PE_PAIRS : 0;   // affine column blocks
+  dim3 grid((PhT ? rows_pad : rows + PE_ROWS - 1) / PE_ROWS, gy + gy_ext);
   const size_t smem = PE_ROWS * pl->d * sizeof(float);
-  if (PhT) phi_fit_kernel<true><<<grid, PE_PAIRS, smem, st>>>(*pl, X, rows, Dp, m, PhT, fbuf);
-  else phi_fit_kernel<false><<<grid, PE_PAIRS, smem, st>>>(*pl, X, rows, Dp, m, nullptr, fbuf);
+  if (PhT) phi_fit_kernel<true><<<grid, PE_PAIRS, smem, st>>>(*pl, X, rows, Dp, Dk, gy, m, PhT, fbuf);
+  else phi_fit_kernel<false><<<grid, PE_PAIRS, smem, st>>>(*pl, X, rows, Dp, Dk, gy, m, nullptr, fbuf);
   RR_LAUNCH_CHECK("phi_fit_kernel");
   return RR_OK;
 }
@@ -259,7 +298,7 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t
 template <int IG>   // input dimensions per reducing warp: d <= 4 * IG
 __global__ void __launch_bounds__(G2_THREADS, 1)
 gp2_kernel(rr_plan plan, const float* __restrict__ X, const float* __restrict__ err,
-           int rows, int RB, int FB, const uint8_t* __restrict__ PhT,
+           int rows, int RB, int FB, int nkb, const uint8_t* __restrict__ PhT,
            const uint8_t* __restrict__ BtT, const float* __restrict__ m,
            const unsigned int* __restrict__ cmax_bits, double* __restrict__ R) {
   constexpr int DPAD = 4 * IG;
@@ -276,7 +315,7 @@ gp2_kernel(rr_plan plan, const float* __restrict__ X, const float* __restrict__ 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const uint32_t crank = cluster_ctarank();
   const int pair = blockIdx.x >> 1, npairs = gridDim.x >> 1;
-  const int nkb = FB * (G2_TN / G2_KT);     // k blocks over all Dp features
+  // nkb: k blocks over all reduction features (trigonometric + affine columns)
   const int ntiles = RB * FB;
   const int d = plan.d, ktot = plan.ktot;
 
@@ -495,12 +534,19 @@ gp2_kernel(rr_plan plan, const float* __restrict__ X, const float* __restrict__ 
 // ---- host ---------------------------------------------------------------------
 // padded feature count: whole 256-feature output tiles (= 128 frequencies)
 static int gp_dp(const rr_plan* pl) { return ((pl->ktot + 127) / 128) * 256; }
+// reduction extent: trigonometric features + affine columns padded to a k block
+static int gp_dk(const rr_plan* pl) { return gp_dp(pl) + ((pl->next + G2_KT - 1) / G2_KT) * G2_KT; }
+
+int tc_gradpass_supported(const rr_plan* pl) {
+  return (pl->d >= 1 && pl->d <= 32 && pl->ktot >= 1 && pl->next >= 0 &&
+          pl->D == 2 * pl->ktot + pl->next) ? 1 : 0;
+}
 
 // Row blocks (of 256 rows) per chunk: as many as the scratch budget allows, then
 // trimmed so that the tile count fills whole rounds of the persistent CTA pairs.
 static int gp_chunk_blocks(const rr_plan* pl, int64_t N) {
   const int Dp = gp_dp(pl), FB = Dp / G2_TN;
-  int rbmax = (int)(G2_SCRATCH_BYTES / ((int64_t)G2_TM * Dp * 2));
+  int rbmax = (int)(G2_SCRATCH_BYTES / ((int64_t)G2_TM * gp_dk(pl) * 2));
   if (rbmax < 1) rbmax = 1;
   const int64_t need = (N + G2_TM - 1) / G2_TM;
   if (need <= rbmax) return (int)need;
@@ -519,14 +565,14 @@ static int gp_chunk_blocks(const rr_plan* pl, int64_t N) {
 }
 
 size_t tc_gradpass_workspace(const rr_plan* pl, int64_t N) {
-  const int64_t Dp = gp_dp(pl);
-  return 2 * (align_up((size_t)gp_chunk_blocks(pl, N) * G2_TM * Dp * 2, 1024) + 1024) +
-         align_up((size_t)Dp * Dp * 2, 1024) + align_up((size_t)N * 4, 256) + 8192;
+  const int64_t Dp = gp_dp(pl), Dk = gp_dk(pl);
+  return 2 * (align_up((size_t)gp_chunk_blocks(pl, N) * G2_TM * Dk * 2, 1024) + 1024) +
+         align_up((size_t)Dp * Dk * 2, 1024) + align_up((size_t)N * 4, 256) + 8192;
 }
 
 template <int IG>
 static int launch_gp2(const rr_plan* pl, const float* X, const float* err, int rows,
-                      int RB, int FB, const uint8_t* PhT, const uint8_t* BtT,
+                      int RB, int FB, int nkb, const uint8_t* PhT, const uint8_t* BtT,
                       const float* m, const unsigned int* cmax, double* R,
                       cudaStream_t st) {
   const size_t smem = (size_t)G2_STAGES * G2_STAGE_BYTES + 2 * G2_RED * 4 +
@@ -547,7 +593,7 @@ static int launch_gp2(const rr_plan* pl, const float* X, const float* err, int r
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  RR_CUDA_CHECK(cudaLaunchKernelEx(&cfg, gp2_kernel<IG>, *pl, X, err, rows, RB, FB, PhT, BtT,
+  RR_CUDA_CHECK(cudaLaunchKernelEx(&cfg, gp2_kernel<IG>, *pl, X, err, rows, RB, FB, nkb, PhT, BtT,
                                    m, cmax, R));
   RR_LAUNCH_CHECK("gp2_kernel");
   return RR_OK;
@@ -563,7 +609,7 @@ int phi_residual(const rr_plan* pl, const float* X, const float* y, int64_t N,
   const int64_t CH = 1 << 20;
   for (int64_t s = 0; s < N; s += CH) {
     const int rows = (int)((N - s) < CH ? (N - s) : CH);
-    int rc = launch_phi_fit(pl, X + s * pl->d, rows, rows, 0, m, nullptr, fbuf + s, st);
+    int rc = launch_phi_fit(pl, X + s * pl->d, rows, rows, 0, 0, m, nullptr, fbuf + s, st);
     if (rc) return rc;
   }
   resid_finish_kernel<<<sm_count() * 4, 256, 0, st>>>(y, fbuf, N, err, sqerr);
@@ -601,14 +647,14 @@ static GpAux* gp_aux() {
 int tc_gradpass(const rr_plan* pl, const float* X, const float* y, int64_t N,
                 const float* m, const float* C, double* R, double* sqerr, void* ws,
                 size_t wsb, cudaStream_t st) {
-  const int Dp = gp_dp(pl), FB = Dp / G2_TN;
+  const int Dp = gp_dp(pl), Dk = gp_dk(pl), FB = Dp / G2_TN, nkb = Dk / G2_KT;
   const int RBc = gp_chunk_blocks(pl, N);
   const int64_t RC = (int64_t)RBc * G2_TM;
   Workspace W(ws, wsb);
   uint8_t* PhTb[2];
-  PhTb[0] = W.take<uint8_t>(align_up((size_t)RC * Dp * 2, 1024) + 1024);
-  PhTb[1] = W.take<uint8_t>(align_up((size_t)RC * Dp * 2, 1024) + 1024);
-  uint8_t* BtT = W.take<uint8_t>(align_up((size_t)Dp * Dp * 2, 1024) + 1024);
+  PhTb[0] = W.take<uint8_t>(align_up((size_t)RC * Dk * 2, 1024) + 1024);
+  PhTb[1] = W.take<uint8_t>(align_up((size_t)RC * Dk * 2, 1024) + 1024);
+  uint8_t* BtT = W.take<uint8_t>(align_up((size_t)Dp * Dk * 2, 1024) + 1024);
   float* err = W.take<float>((size_t)N);      // fitted values, then residuals
   unsigned int* cmax = W.take<unsigned int>(1);
   GpAux* aux = gp_aux();
@@ -634,8 +680,8 @@ int tc_gradpass(const rr_plan* pl, const float* X, const float* y, int64_t N,
   absmax_kernel<<<sm_count() * 4, 256, 0, st>>>(C, (int64_t)pl->D * pl->D, cmax);
   RR_LAUNCH_CHECK("absmax_kernel");
   {
-    dim3 grid((Dp + 255) / 256, Dp);
-    prep_c_kernel<<<grid, 256, 0, st>>>(*pl, C, Dp, cmax, BtT);
+    dim3 grid((Dk + 255) / 256, Dp);
+    prep_c_kernel<<<grid, 256, 0, st>>>(*pl, C, Dp, Dk, cmax, BtT);
     RR_LAUNCH_CHECK("prep_c_kernel");
   }
   const int d = pl->d;
@@ -648,7 +694,7 @@ int tc_gradpass(const rr_plan* pl, const float* X, const float* y, int64_t N,
     uint8_t* PhT = PhTb[buf];
     // helper stream: Phi chunk c (after the GEMM of chunk c-2 released the buffer)
     if (c >= 2) RR_CUDA_CHECK(cudaStreamWaitEvent(aux->stream, aux->gemm[buf], 0));
-    int rc = launch_phi_fit(pl, X + s * d, rows, rows_pad, Dp, m, PhT, err + s, sp);
+    int rc = launch_phi_fit(pl, X + s * d, rows, rows_pad, Dp, Dk, m, PhT, err + s, sp);
     if (rc) return rc;
     // fitted values -> residuals (in place) + their sum of squares
     resid_finish_kernel<<<(rows + 1023) / 1024, 256, 0, sp>>>(y + s, err + s, rows, err + s,
@@ -659,11 +705,11 @@ int tc_gradpass(const rr_plan* pl, const float* X, const float* y, int64_t N,
     RR_CUDA_CHECK(cudaStreamWaitEvent(st, aux->phi[buf], 0));
     const float* Xc = X + s * d;
     const float* ec = err + s;
-    if (d <= 4) rc = launch_gp2<1>(pl, Xc, ec, rows, RB, FB, PhT, BtT, m, cmax, R, st);
-    else if (d <= 8) rc = launch_gp2<2>(pl, Xc, ec, rows, RB, FB, PhT, BtT, m, cmax, R, st);
-    else if (d <= 16) rc = launch_gp2<4>(pl, Xc, ec, rows, RB, FB, PhT, BtT, m, cmax, R, st);
-    else if (d <= 24) rc = launch_gp2<6>(pl, Xc, ec, rows, RB, FB, PhT, BtT, m, cmax, R, st);
-    else rc = launch_gp2<8>(pl, Xc, ec, rows, RB, FB, PhT, BtT, m, cmax, R, st);
+    if (d <= 4) rc = launch_gp2<1>(pl, Xc, ec, rows, RB, FB, nkb, PhT, BtT, m, cmax, R, st);
+    else if (d <= 8) rc = launch_gp2<2>(pl, Xc, ec, rows, RB, FB, nkb, PhT, BtT, m, cmax, R, st);
+    else if (d <= 16) rc = launch_gp2<4>(pl, Xc, ec, rows, RB, FB, nkb, PhT, BtT, m, cmax, R, st);
+    else if (d <= 24) rc = launch_gp2<6>(pl, Xc, ec, rows, RB, FB, nkb, PhT, BtT, m, cmax, R, st);
+    else rc = launch_gp2<8>(pl, Xc, ec, rows, RB, FB, nkb, PhT, BtT, m, cmax, R, st);
     if (rc) return rc;
     RR_CUDA_CHECK(cudaEventRecord(aux->gemm[buf], st));
   }

@@ -75,7 +75,8 @@ class _SLMProblem(object):
         from . import _cabi
         if self.engine == _cabi.RR_ENGINE_SIMT or not self.plan.tcgen05_ok():
             return False
-        return self.engine != _cabi.RR_ENGINE_AUTO or self.Xd.shape[0] >= 16384
+        return (self.engine != _cabi.RR_ENGINE_AUTO
+                or self.Xd.shape[0] >= eng.TC_AUTO_MIN_ROWS)
 
     def polish(self, var, regs, hypers):
         """Posterior at the given hyper-parameters from the SIMT engine's

@@ -129,7 +129,9 @@ def test_slm_elbo_auto_engine(golden, name):
 
 
 TCGEN05_CASES = ["rbf_iso_d1", "rbf_iso_d3", "matern32_ard_d5", "cauchy_ard_d21",
-                 "config1_sine"]   # single random-trigonometric block
+                 "config1_sine",           # single random-trigonometric block
+                 "rbf_plus_linear",        # + LinearBasis: affine columns ride along
+                 "two_trig_plus_bias"]     # two trig blocks (one on a column subset) + bias
 
 
 @pytest.mark.parametrize("name", TCGEN05_CASES)
@@ -204,12 +206,45 @@ def test_posterior_polish_on_ill_conditioned_problem():
     assert 1e-4 < relerr(slm2.weights_, ref["m"]) < 1e-2
 
 
+def test_tcgen05_concatenated_basis_vs_oracle_mid_size():
+    """Config-5 shaped basis, BasisCat(RandomRBF + LinearBasis(onescol)), through
+    both tcgen05 kernels (affine columns as pseudo-frequency slots in the value
+    pass and as extra reduction columns in the gradient pass) against the float64
+    oracle at N=20011, d=21, K=160."""
+    N, d, K = 20011, 21, 160
+    X, y = _synthetic(N, d, seed=13)
+    ls = 3.0 * (1.0 + 0.05 * np.arange(d))
+    rbf = bf.RandomRBF(nbases=K, Xdim=d, random_state=6, lenscale=Parameter(ls, Positive()),
+                       regularizer=Parameter(1.3, Positive()))
+    lin = bf.LinearBasis(onescol=True, regularizer=Parameter(2.0, Positive()))
+    old = config.ENGINE
+    config.ENGINE = "tcgen05"
+    try:
+        slm = rr.StandardLinearModel(basis=rbf + lin)
+        slm.obj_ = -np.inf
+        nelbo, (dv, dr, dl) = slm._elbo(X, y, 0.05, [1.3, 2.0], ls)
+        assert slm._cached_problem.uses_tcgen05()
+    finally:
+        config.ENGINE = old
+    blocks = [dict(kind="trig", W=rbf.W, lenscale=ls, cols=None),
+              dict(kind="linear", onescol=True, cols=None)]
+    ref = orc.slm_elbo(X, y, 0.05, [1.3, 2.0], blocks)
+    assert abs(nelbo - ref["neg_elbo"]) <= 1e-4 * abs(ref["neg_elbo"])
+    assert relerr(slm.weights_, ref["m"]) < 1e-4
+    np.testing.assert_allclose(slm.covariance_.diagonal(), ref["C"].diagonal(), rtol=1e-4)
+    assert abs(dv - ref["dvar"]) <= 1e-4 * abs(ref["dvar"])
+    np.testing.assert_allclose(np.ravel(dr), np.ravel(ref["dreg"]), rtol=1e-4)
+    assert relerr(dl, ref["dhyp"][0]) < 5e-3
+
+
 def test_tcgen05_engine_is_selected_for_rff():
     b = bf.RandomMatern32(nbases=2048, Xdim=21, random_state=1)
     plan = b._plan(21, [1.0])
     assert plan.tcgen05_ok()
     plan2 = (b + bf.LinearBasis())._plan(21, [1.0])
-    assert not plan2.tcgen05_ok()
+    assert not plan2.tcgen05_ok()      # until the column scales of a data set are known
+    plan2.enable_tc_extras(np.ones(21))
+    assert plan2.tcgen05_ok()
 
 
 LIK = dict(gaussian=lk.Gaussian, bernoulli=lk.Bernoulli, binomial=lk.Binomial,
