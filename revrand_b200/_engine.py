@@ -214,7 +214,9 @@ class FeaturePlan(object):
         """Recompute Wt = W / lenscale / 2pi (float64 on host) and upload."""
         t = torch()
         if self.ktot:
-            Wt = self.Wfull * self.inv_lenscale_full() / TWO_PI
+            # (a random start may draw a lengthscale so small that W / l leaves the
+            # fp32 range: keep it finite, the phase is meaningless there anyway)
+            Wt = np.clip(self.Wfull * self.inv_lenscale_full() / TWO_PI, -3e38, 3e38)
             self._Wt.copy_(t.from_numpy(np.ascontiguousarray(
                 Wt.astype(np.float32))), non_blocking=False)
         s = self.struct

@@ -11,6 +11,7 @@ Tolerances (north_star: rtol 1e-4 in fp32 on identical seeded bases):
 
 import numpy as np
 import pytest
+from scipy.stats import gamma
 
 import revrand_b200 as rr
 from revrand_b200 import Parameter, Positive, _cabi, _engine, config
@@ -433,6 +434,36 @@ def test_slm_fit_config1_end_to_end():
     oEy, oVy = orc.slm_predict_moments(Xs, blocks, o["m"], o["C"], slm.var_)
     assert relerr(Ey, oEy) < 2e-3
     assert abs(-o["neg_elbo"] - slm.obj_) < 1e-3 * abs(slm.obj_) + 1e-2
+
+
+def test_slm_fit_mid_size_through_tcgen05_engines():
+    """fit() at a size RR_ENGINE_AUTO routes to the tcgen05 engines: value-only
+    random starts, L-BFGS-B on the fused value + gradient passes, posterior polish
+    at the end.  The reported posterior must be the float64 oracle's posterior at
+    the learned hyper-parameters."""
+    N, d, K = 40000, 8, 128
+    X, y = _synthetic(N, d, seed=21)
+    basis = bf.RandomRBF(nbases=K, Xdim=d, random_state=5,
+                         lenscale=Parameter(gamma(2.0, scale=1.5), Positive()))
+    slm = rr.StandardLinearModel(basis=basis, nstarts=6, maxiter=40, random_state=7)
+    slm.fit(X, y)
+    Xs, _ = _synthetic(2000, d, seed=22)
+    # weights_ / covariance_ / obj_ belong to the best evaluation seen (slm.py:173-177),
+    # which L-BFGS-B normally also returns as res.x
+    bvar, bregs, bhyps = slm._best_point[:3]
+    blocks = [dict(kind="trig", W=basis.W, lenscale=bhyps[0], cols=None)]
+    o = orc.slm_elbo(X, y, bvar, list(bregs), blocks)
+    assert abs(-o["neg_elbo"] - slm.obj_) <= 1e-4 * abs(slm.obj_)
+    assert relerr(slm.weights_, o["m"]) < 1e-4
+    np.testing.assert_allclose(slm.covariance_.diagonal(), o["C"].diagonal(), rtol=1e-4)
+    np.testing.assert_allclose(slm.var_, bvar, rtol=1e-6)
+    Ey, Vy = slm.predict_moments(Xs)
+    assert np.all(Vy > 0)
+    oEy, oVy = orc.slm_predict_moments(Xs, blocks, o["m"], o["C"], slm.var_)
+    assert relerr(Ey, oEy) < 1e-4
+    # sanity: 128 frequencies explain most of the 8-D training signal (var(y) ~ 0.5)
+    f = orc.slm_predict_moments(X[:5000], blocks, o["m"], o["C"], slm.var_)[0]
+    assert np.mean((f - y[:5000]) ** 2) < 0.25
 
 
 def test_glm_fit_poisson_small():
