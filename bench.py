@@ -267,6 +267,26 @@ def run_ours(args):
         except Exception:
             pass
 
+    # ---- value-only evaluations (random-start phase of fit: no gradient pass,
+    #      no explicit inverse) ---------------------------------------------------
+    for i in range(2):
+        prob.evaluate(EVAL_POINTS[i][1], [REG], [EVAL_POINTS[i][0]], want_grad=False)
+    barrier()
+    nvo = max(3, min(args.steps, 6))
+    evv = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+           for _ in range(nvo)]
+    for i in range(nvo):
+        flush.zero_()
+        ls, var = EVAL_POINTS[i % len(EVAL_POINTS)]
+        evv[i][0].record()
+        prob.evaluate(var, [REG], [ls], want_grad=False)
+        evv[i][1].record()
+    barrier()
+    tv = torch.tensor([sum(a.elapsed_time(b) for a, b in evv)], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(tv, op=dist.ReduceOp.MAX)
+    value_only = 1e3 / (float(tv.item()) / nvo)
+
     # ---- end to end through the public API with HOST buffers ----------------
     Xh = torch.from_numpy(X[lo:hi]).pin_memory()
     yh = torch.from_numpy(y[lo:hi]).pin_memory()
@@ -315,6 +335,8 @@ def run_ours(args):
         "e2e": {"value": e2e_val, "unit": "evals/s", "h2d_bytes_per_step": h2d,
                 "d2h_bytes_per_step": d2h},
         "gpu_launches": int(launches),
+        "value_only": {"value": value_only, "unit": "evals/s",
+                       "note": "log-ML value without gradients (random-start phase of fit)"},
         "roofline": roofline,
     }
     if rank == 0 and world == 1 and not args.no_cpu:
