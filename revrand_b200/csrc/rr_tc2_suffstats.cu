@@ -645,10 +645,14 @@ tc2_suffstats_kernel(rr_plan plan, const float* __restrict__ X,
         cx.off_sin[cg] = tile + sw128_off(row_sin, (uint32_t)(T2_GCHUNKS * h + cg));
       }
     }
+    // shared::cluster address of the leader CTA's u_empty barrier (mapa reads a
+    // special register; keep it out of the per-slab path)
+    const uint32_t u_empty_leader = mapa_u32(smem_u32(&sb.u_empty), 0);
     uint32_t gs = 0;
     for (int item = pair; item < nitems; item += npairs) {
       const T2Item it = t2_decode(item, ntiles, NIB, NJB, N, rpi);
       const int nsl = (int)((it.r1 - it.r0 + T2_SLAB - 1) / T2_SLAB);
+      const int tail_rows = (int)(it.r1 - it.r0) - (nsl - 1) * T2_SLAB;   // rows of the last slab
       const int theta = is_a ? T2_IB * it.ib + T2_NA * (int)crank + fl
                              : T2_JB * it.jb + T2_NB * (int)crank + (fl - T2_NA);
       const bool valid = has_row && theta < ktot;
@@ -675,8 +679,7 @@ tc2_suffstats_kernel(rr_plan plan, const float* __restrict__ X,
       double pc_d = 0.0, ps_d = 0.0;
 
       for (int t = 0; t < nsl; ++t, ++gs) {
-        const int64_t row0 = it.r0 + (int64_t)t * T2_SLAB;
-        const int vrows = (int)((it.r1 - row0) < T2_SLAB ? (it.r1 - row0) : T2_SLAB);
+        const int vrows = (t == nsl - 1) ? tail_rows : T2_SLAB;
         float u[T2_GROWS];
         const bool trw = lane == 0 && (gw == 0 || gw == T2_GEN_WARPS - 1);
         const int trb = gw == 0 ? 0 : 16;
@@ -688,7 +691,7 @@ tc2_suffstats_kernel(rr_plan plan, const float* __restrict__ X,
         tmem_ld_wait();
         tc_fence_before_sync();
         __syncwarp();
-        if (lane == 0) t2_arrive_leader(&sb.u_empty, crank);
+        if (lane == 0) mbar_arrive_cluster(u_empty_leader);
         T2_TRACE(trw, gs, trb + 2);
 
         const uint32_t ps = gs % T2_PSTAGES;
@@ -707,7 +710,7 @@ tc2_suffstats_kernel(rr_plan plan, const float* __restrict__ X,
         const bool masked = !(all_valid && vrows == T2_SLAB);   // warp-uniform
         if (want_p) {   // warp-uniform, designated A tiles only
           uint64_t pc2 = 0ull, ps2 = 0ull;   // (+0.0f, +0.0f)
-          const float* yrow = y + row0 + T2_GROWS * h;
+          const float* yrow = y + it.r0 + (int64_t)t * T2_SLAB + T2_GROWS * h;
           if (masked) t2_gen_slab<true, true>(cx, u, live, false, true, yrow, pc2, ps2, kind);
           else t2_gen_slab<false, true>(cx, u, live, false, true, yrow, pc2, ps2);
           float a0, a1, b0, b1;
