@@ -43,6 +43,36 @@ def test_library_exports_every_declared_symbol():
                                   0, 0, _cabi.RR_ENGINE_AUTO) > 0
 
 
+def test_binding_signatures_match_the_header():
+    """Argument COUNT and pointer/integer/float kind of every ctypes signature
+    against the prototype in include/revrand_b200.h (a changed prototype with a
+    stale binding would otherwise only show up as garbage on the GPU box)."""
+    hdr = open(os.path.join(ROOT, "include", "revrand_b200.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    protos = dict(re.findall(r"\b(rr_[a-z0-9_]+)\s*\(([^;{]*?)\)\s*;", hdr, flags=re.S))
+    assert set(protos) == set(_cabi.SIGNATURES)
+
+    def kind_of_c(arg):
+        arg = " ".join(arg.split())
+        if "*" in arg:
+            return "ptr"
+        if arg.startswith(("float", "double")):
+            return "float"
+        return "int"
+
+    def kind_of_ctypes(t):
+        if t in (ctypes.c_float, ctypes.c_double):
+            return "float"
+        if t in (ctypes.c_void_p, ctypes.c_char_p) or hasattr(t, "contents"):
+            return "ptr"
+        return "int"
+
+    for name, (res, args) in _cabi.SIGNATURES.items():
+        cargs = [a for a in protos[name].split(",") if a.strip() and a.strip() != "void"]
+        assert len(cargs) == len(args), (name, cargs, args)
+        assert [kind_of_c(a) for a in cargs] == [kind_of_ctypes(t) for t in args], name
+
+
 def test_no_cpu_fallback():
     import torch
     if torch.cuda.is_available():
