@@ -323,11 +323,12 @@ def run_ours(args):
         "metric": METRIC, "value": value, "unit": "evals/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
-        "dtype": "f16 (tcgen05 kind::f16 fixed-point-split products, tf32 projection, "
-                 "fp32 accumulate in TMEM, f64 statistics and solve)",
+        "dtype": "f16",
         "data": "synthetic",
         "config": {"workload": "config2: SLM + RandomMatern32(nbases=%d), N=%d, d=%d, "
                                "value+grad eval, isotropic lengthscale" % (K, N, d),
+                   "arithmetic": "tcgen05 kind::f16 fixed-point-split products, tf32 "
+                                 "projection, fp32 accumulate in TMEM, f64 statistics and solve",
                    "rows_per_gpu": n_local, "l2": "flushed between timed steps "
                    "(256 MiB write)", "engine": os.environ.get("REVRAND_B200_ENGINE", "auto"),
                    "parallelism": "rows sharded x%d, 2 allreduces/eval" % world},
