@@ -363,7 +363,7 @@ def main():
     ap.add_argument("--N", type=int, default=1000000)
     ap.add_argument("--d", type=int, default=21)
     ap.add_argument("--K", type=int, default=2048)
-    ap.add_argument("--cpu-sample", type=int, default=20000)
+    ap.add_argument("--cpu-sample", type=int, default=40000)
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
