@@ -48,7 +48,7 @@ constexpr int G2_RED = 4 * 32 * 32;     // floats of one cross-warp reduction bu
 // handful of 2 MB row-block panels of Phi plus the 32 MB image of C; each panel is
 // fetched from HBM once and then hit in L2 by the other 15 feature blocks.  Large
 // chunks amortise the per-launch pipeline fill and the exposed last epilogue.
-constexpr int64_t G2_SCRATCH_BYTES = 160ll << 20;
+constexpr int64_t G2_SCRATCH_BYTES = 320ll << 20;
 
 // internal feature f -> (frequency, is_sin): blocks of [64 cos | 64 sin]
 __device__ __forceinline__ int feat_theta(int f) { return 64 * (f >> 7) + (f & 63); }
