@@ -11,9 +11,16 @@
  *
  * Conventions
  *  - All data pointers are DEVICE pointers owned by the caller; the library
- *    allocates nothing persistent.  Matrices are row-major.
+ *    allocates nothing persistent and keeps no global state besides a
+ *    thread-local error string and a launch counter.  Matrices are row-major.
  *  - `stream` is a cudaStream_t passed as void* (NULL = default stream).
  *    Calls are asynchronous with respect to the host.
+ *  - Two passes can overlap their feature generation with their tensor-core
+ *    work on a helper stream.  That stream and its events belong to an
+ *    `rr_context` the CALLER creates and destroys (one per host thread and
+ *    device); passing ctx == NULL runs everything on `stream`.  Every call
+ *    joins the helper stream back into `stream` before it returns, on error
+ *    paths too, so a context is capturable in a CUDA graph with the call.
  *  - Return value: 0 on success, negative rr_status otherwise;
  *    rr_last_error() returns a thread-local message.  No C++ exceptions
  *    cross this boundary.
@@ -84,11 +91,24 @@ typedef enum rr_likelihood {
 } rr_likelihood;
 
 /* Engine selection flags for the SLM passes. */
-#define RR_ENGINE_AUTO 0   /* fused tcgen05 path when the plan allows it */
+#define RR_ENGINE_AUTO 0   /* tensor-core path when the plan allows it and the
+                              job has at least rr_engine_auto_min_rows() rows */
 #define RR_ENGINE_SIMT 1   /* chunked CUDA-core path (any plan)          */
-#define RR_ENGINE_TCGEN05 2 /* fused tcgen05 path, error if unsupported  */
-#define RR_ENGINE_TCGEN05_FINE 3 /* same, value pass on a 4x finer fixed-point grid:
-                                    a quarter of the rounding noise, ~1.4x the time */
+#define RR_ENGINE_TCGEN05 2 /* tensor-core path, error if unsupported: value pass in
+                               exact 24-bit fixed point on tcgen05 kind::i8, gradient
+                               pass on kind::f16 */
+#define RR_ENGINE_TCGEN05_FINE 3    /* round-1 fused kind::f16 value pass, 2^-7 grid */
+#define RR_ENGINE_TCGEN05_FUSED16 4 /* round-1 fused kind::f16 value pass, 2^-5 grid
+                                       (kept for A/B measurements) */
+
+/* Helper stream + events for the passes that overlap generation with tensor-core
+ * work (see Conventions).  Created on the current device. */
+typedef struct rr_context rr_context;
+int rr_context_create(rr_context** out);
+int rr_context_destroy(rr_context* ctx);
+
+/* Row count from which RR_ENGINE_AUTO uses the tensor-core engine. */
+int64_t rr_engine_auto_min_rows(void);
 
 int rr_version(void);
 const char* rr_last_error(void);
@@ -136,12 +156,14 @@ int rr_fastfood_features(const float* Xs, int64_t N, int32_t d, int32_t d2,
  * Value pass of StandardLinearModel._elbo: G += Phi^T Phi, p += Phi^T y,
  * yy += y^T y over this rank's rows; replaces slm.py:145-146 and the
  * Phi.T.dot(y) of :157.  G is (D,D) float64, p (D) float64, yy (1) float64.
- * Phi is never written to HBM by the tcgen05 engine.
+ * The tensor-core engine rounds every feature value once to 24-bit fixed point
+ * and forms G and p from those integers EXACTLY (int8 digits, int32
+ * accumulators): the result is independent of tiling and row partitioning.
  */
 int rr_slm_suffstats(const rr_plan* plan, const float* X, const float* y,
                      int64_t N, double* G, double* p, double* yy,
                      void* workspace, size_t workspace_bytes, int32_t engine,
-                     void* stream);
+                     rr_context* ctx, void* stream);
 
 /*
  * Residual pass: sqerr += sum_n (y_n - phi_n^T m)^2 (slm.py:161-162);
@@ -165,7 +187,7 @@ int rr_slm_residual(const rr_plan* plan, const float* X, const float* y,
 int rr_slm_gradpass(const rr_plan* plan, const float* X, const float* y,
                     int64_t N, const float* m, const float* C, double* R,
                     double* sqerr, void* workspace, size_t workspace_bytes,
-                    int32_t engine, void* stream);
+                    int32_t engine, rr_context* ctx, void* stream);
 
 /*
  * Predictive moments (slm.py:239-242): Ey = Phi m, Vf = rowsum((Phi C) * Phi).
@@ -225,6 +247,15 @@ int rr_tcgen05_supported(int32_t d, int32_t ktot, int32_t next, int32_t D);
  * max_abs_err (host pointer) receives the largest deviation.
  */
 int rr_tcgen05_selftest(double* max_abs_err);
+
+/*
+ * Self-test of the kind::i8 path: one CTA pair (cta_group::2, M = 256,
+ * N = 160), `kblocks` K blocks of 64 through the 64-byte-swizzled layout and
+ * the six digit products of the value pass, compared BIT-EXACTLY with a host
+ * integer reference.  mismatches (host pointer) receives the number of wrong
+ * accumulator entries; returns 0 when it is zero.
+ */
+int rr_tcgen05_i8_selftest(int32_t kblocks, int64_t* mismatches);
 
 /*
  * Diagnostic: repeat D += A B^T over one 128 x 256 x 64 fp16 tile `reps`

@@ -15,6 +15,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "lib", "librevrand_b200.so")
 
 RR_ENGINE_AUTO, RR_ENGINE_SIMT, RR_ENGINE_TCGEN05, RR_ENGINE_TCGEN05_FINE = 0, 1, 2, 3
+RR_ENGINE_TCGEN05_FUSED16 = 4
 RR_OP_SUFFSTATS, RR_OP_GRADPASS, RR_OP_PREDICT = 1, 2, 3
 RR_OP_GLM_STEP, RR_OP_GLM_PREDICT, RR_OP_RESIDUAL = 4, 5, 6
 (RR_LIK_GAUSSIAN, RR_LIK_BERNOULLI, RR_LIK_BINOMIAL, RR_LIK_POISSON_EXP,
@@ -48,11 +49,14 @@ SIGNATURES = {
     "rr_trig_grad": (C.c_int, [_P, _I64, _I32, _P, _I32, _P, _I32, _I32, _P, _P]),
     "rr_fastfood_features": (C.c_int, [_P, _I64, _I32, _I32, _I32, _P, _P, _P,
                                        _P, _P, _P, _P]),
+    "rr_context_create": (C.c_int, [C.POINTER(_P)]),
+    "rr_context_destroy": (C.c_int, [_P]),
+    "rr_engine_auto_min_rows": (_I64, []),
     "rr_slm_suffstats": (C.c_int, [_PLAN, _P, _P, _I64, _P, _P, _P, _P, _SZ,
-                                   _I32, _P]),
+                                   _I32, _P, _P]),
     "rr_slm_residual": (C.c_int, [_PLAN, _P, _P, _I64, _P, _P, _P, _P, _SZ, _P]),
     "rr_slm_gradpass": (C.c_int, [_PLAN, _P, _P, _I64, _P, _P, _P, _P, _P, _SZ,
-                                  _I32, _P]),
+                                  _I32, _P, _P]),
     "rr_slm_predict": (C.c_int, [_PLAN, _P, _I64, _P, _P, _P, _P, _P, _SZ, _P]),
     "rr_glm_step": (C.c_int, [_PLAN, _P, _P, _P, _I64, _P, _P, _I32, _P, _I32,
                               _I32, _F32, _P, _P, _P, _P, _P, _P, _SZ, _P]),
@@ -61,6 +65,7 @@ SIGNATURES = {
     "rr_workspace_bytes": (_SZ, [_I32, _I64, _I32, _I32, _I32, _I32, _I32, _I32]),
     "rr_tcgen05_supported": (C.c_int, [_I32, _I32, _I32, _I32]),
     "rr_tcgen05_selftest": (C.c_int, [C.POINTER(C.c_double)]),
+    "rr_tcgen05_i8_selftest": (C.c_int, [_I32, C.POINTER(_I64)]),
     "rr_tcgen05_accum_probe": (C.c_int, [_P, _P, _P, _P, _I32, _I32, _P, _P]),
 }
 

@@ -16,7 +16,6 @@ from . import _cabi
 from ._cabi import RRPlan, RevrandB200Error, check
 
 CHOLTHRESH = 1e-5   # revrand/mathfun/linalg.py:31
-TC_AUTO_MIN_ROWS = 16384   # RR_ENGINE_AUTO: fused tcgen05 engine from here on (rr_slm.cu)
 SVD_FLOOR = 1e-15   # revrand/mathfun/linalg.py:128 (s_tol)
 TWO_PI = 2.0 * math.pi
 
@@ -47,6 +46,48 @@ def device():
 
 def _stream_ptr():
     return C.c_void_p(torch().cuda.current_stream().cuda_stream)
+
+
+def auto_min_rows():
+    """Row count from which RR_ENGINE_AUTO uses the tensor-core engine (asked
+    of the library: one source for the constant)."""
+    return int(_cabi.load().rr_engine_auto_min_rows())
+
+
+_FUSED16 = (_cabi.RR_ENGINE_TCGEN05_FINE, _cabi.RR_ENGINE_TCGEN05_FUSED16)
+
+# rr_context per (thread, device): the caller-owned helper stream + events that
+# let a pass overlap its feature generation with its tensor-core work.
+import threading as _threading
+
+_ctx_local = _threading.local()
+
+
+class _Context(object):
+    def __init__(self):
+        h = C.c_void_p()
+        check(_cabi.load().rr_context_create(C.byref(h)), "rr_context_create")
+        self.handle = h
+
+    def __del__(self):
+        try:
+            if self.handle:
+                _cabi.load().rr_context_destroy(self.handle)
+        except Exception:
+            pass
+
+
+def context():
+    """The rr_context of this thread for the current device (None while a CUDA
+    graph is being captured elsewhere is the caller's business)."""
+    t = require_cuda()
+    dev = t.cuda.current_device()
+    tab = getattr(_ctx_local, "tab", None)
+    if tab is None:
+        tab = _ctx_local.tab = {}
+    if dev not in tab:
+        tab[dev] = _Context()
+    return tab[dev].handle
 
 
 def _ptr(tensor):
@@ -233,8 +274,6 @@ class FeaturePlan(object):
             self._Wt_x[:, :self.ktot].copy_(self._Wt)
 
     def tcgen05_ok(self):
-        if self.next:
-            return self.struct_tc is not None and self.d <= 32
         return bool(_cabi.load().rr_tcgen05_supported(self.d, self.ktot,
                                                      self.next, self.D))
 
@@ -335,17 +374,16 @@ def slm_suffstats(plan, Xd, yd, stats, engine=_cabi.RR_ENGINE_AUTO,
     N = Xd.shape[0]
     nb = _ws_bytes(_cabi.RR_OP_SUFFSTATS, N, plan, engine=engine)
     struct = plan.struct
-    use_tc = (engine in (_cabi.RR_ENGINE_TCGEN05, _cabi.RR_ENGINE_TCGEN05_FINE)
-              or (engine == _cabi.RR_ENGINE_AUTO and N >= TC_AUTO_MIN_ROWS))
-    if plan.struct_tc is not None and use_tc:
-        # affine columns ride along as pseudo-frequency slots of the fused kernel
+    if plan.struct_tc is not None and engine in _FUSED16:
+        # round-1 fused kind::f16 kernel: affine columns as pseudo-frequency slots
         struct = plan.struct_tc
         nb = max(nb, plan.D * plan.D * 8 + plan.D * 4 + 8192)
     ws = workspace(nb)
     check(lib.rr_slm_suffstats(C.byref(struct), _ptr(Xd), _ptr(yd), N,
                                _ptr(stats.G), _ptr(stats.p),
                                _ptr(stats.yy) if want_yy else C.c_void_p(0),
-                               _ptr(ws), ws.numel(), engine, _stream_ptr()),
+                               _ptr(ws), ws.numel(), engine, context(),
+                               _stream_ptr()),
           "rr_slm_suffstats")
 
 
@@ -371,7 +409,8 @@ def slm_gradpass(plan, Xd, yd, m32, C32, R, sqerr,
     ws = workspace(nb)
     check(lib.rr_slm_gradpass(C.byref(plan.struct), _ptr(Xd), _ptr(yd), N,
                               _ptr(m32), _ptr(C32), _ptr(R), _ptr(sqerr),
-                              _ptr(ws), ws.numel(), engine, _stream_ptr()),
+                              _ptr(ws), ws.numel(), engine, context(),
+                              _stream_ptr()),
           "rr_slm_gradpass")
 
 
@@ -436,6 +475,15 @@ def tcgen05_selftest():
     rc = _cabi.load().rr_tcgen05_selftest(C.byref(err))
     check(rc, "rr_tcgen05_selftest")
     return err.value
+
+
+def tcgen05_i8_selftest(kblocks=9):
+    """Bit-exact check of the kind::i8 GEMM kernel; returns the mismatch count."""
+    require_cuda()
+    bad = C.c_int64(-1)
+    rc = _cabi.load().rr_tcgen05_i8_selftest(int(kblocks), C.byref(bad))
+    check(rc, "rr_tcgen05_i8_selftest")
+    return bad.value
 
 
 # ---------------------------------------------------------------------------

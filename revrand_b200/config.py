@@ -9,8 +9,10 @@ import os
 # are unaffected either way.
 REFERENCE_COMPAT = os.environ.get("REVRAND_B200_REFERENCE_COMPAT", "1") != "0"
 
-# Engine for the SLM passes: "auto" (fused tcgen05 when the basis allows it),
-# "simt" (chunked CUDA-core path) or "tcgen05" (error if unsupported).
+# Engine for the SLM passes: "auto" (tensor-core engine when the basis allows it
+# and the job is large enough), "simt" (chunked CUDA-core path), "tcgen05" (error
+# if unsupported); "tcgen05_fused16" / "tcgen05_fine" select the round-1 fused
+# kind::f16 value pass for A/B measurements.
 ENGINE = os.environ.get("REVRAND_B200_ENGINE", "auto")
 
 
@@ -18,17 +20,18 @@ def engine_code():
     from . import _cabi
     return {"auto": _cabi.RR_ENGINE_AUTO, "simt": _cabi.RR_ENGINE_SIMT,
             "tcgen05": _cabi.RR_ENGINE_TCGEN05,
-            "tcgen05_fine": _cabi.RR_ENGINE_TCGEN05_FINE}[ENGINE]
+            "tcgen05_fine": _cabi.RR_ENGINE_TCGEN05_FINE,
+            "tcgen05_fused16": _cabi.RR_ENGINE_TCGEN05_FUSED16}[ENGINE]
 
 # Draw the GLM reparameterisation noise on the host from the model's
 # RandomState in the reference's order (slow: K_mix*L*D normals per step)
 # instead of on the device.
 GLM_HOST_RNG = os.environ.get("REVRAND_B200_HOST_RNG", "0") == "1"
 
-# The fused tcgen05 value pass perturbs every trig value by ~2e-6 (zero mean);
-# log-ML and its gradients stay within 1e-4, but the posterior moments of an
-# ill-conditioned evaluation inherit cond * noise / sqrt(N).  When the cheap
-# conditioning estimate of the BEST evaluation exceeds this threshold, the
-# reported posterior (weights_, covariance_) is recomputed once with the SIMT
-# engine (fp32 features, float64 accumulation).  0 disables the polish.
+# Only the round-1 fused kind::f16 value pass ("tcgen05_fused16" / "tcgen05_fine")
+# needs this: it perturbs every trig value by ~2e-6 (zero mean), and the posterior
+# moments of an ill-conditioned evaluation inherit cond * noise / sqrt(N).  When
+# the conditioning estimate of the BEST evaluation exceeds this threshold, the
+# reported posterior is recomputed once with the SIMT engine.  The default engine
+# (24-bit fixed point on kind::i8) meets 1e-4 everywhere and never polishes.
 POLISH_COND = float(os.environ.get("REVRAND_B200_POLISH_COND", "1e3"))

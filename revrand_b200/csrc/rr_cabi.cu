@@ -1,6 +1,7 @@
 // Library-level C-ABI pieces: error string, version, device info, workspace
 // queries.
 #include <stdarg.h>
+#include <new>
 #include <string.h>
 
 #include "rr_common.cuh"
@@ -33,12 +34,70 @@ int sm_count() {
   return cached[dev];
 }
 
+// RR_ENGINE_AUTO runs the tensor-core engine from this many rows on; below it the
+// job is launch-latency sized and the chunked SIMT engine is as fast.
+int64_t tc_auto_min_rows() { return 16384; }
+
 size_t slm_workspace_bytes(int op, int64_t N, const rr_plan* pl, int engine);
 size_t glm_workspace_bytes(int op, int64_t M, const rr_plan* pl, int S);
 
 }  // namespace rr
 
-extern "C" int rr_version(void) { return 100; }
+// Caller-owned helper stream + events (header: Conventions).
+struct rr_context {
+  cudaStream_t aux;
+  cudaEvent_t fork, a[2], b[2];
+};
+
+namespace rr {
+int ctx_aux(rr_context* ctx, cudaStream_t* stream, cudaEvent_t* fork, cudaEvent_t a[2],
+            cudaEvent_t b[2]) {
+  if (ctx == nullptr) return RR_OK;
+  *stream = ctx->aux;
+  *fork = ctx->fork;
+  for (int i = 0; i < 2; ++i) {
+    a[i] = ctx->a[i];
+    b[i] = ctx->b[i];
+  }
+  return RR_OK;
+}
+}  // namespace rr
+
+extern "C" int rr_context_create(rr_context** out) {
+  RR_REQUIRE(out != nullptr, "null pointer");
+  rr_context* c = new (std::nothrow) rr_context();
+  RR_REQUIRE(c != nullptr, "out of host memory");
+  memset(c, 0, sizeof(*c));
+  bool ok = cudaStreamCreateWithFlags(&c->aux, cudaStreamNonBlocking) == cudaSuccess;
+  ok = ok && cudaEventCreateWithFlags(&c->fork, cudaEventDisableTiming) == cudaSuccess;
+  for (int i = 0; i < 2; ++i) {
+    ok = ok && cudaEventCreateWithFlags(&c->a[i], cudaEventDisableTiming) == cudaSuccess;
+    ok = ok && cudaEventCreateWithFlags(&c->b[i], cudaEventDisableTiming) == cudaSuccess;
+  }
+  if (!ok) {
+    rr::set_error("rr_context_create: %s", cudaGetErrorString(cudaGetLastError()));
+    rr_context_destroy(c);
+    return RR_ERR_CUDA;
+  }
+  *out = c;
+  return RR_OK;
+}
+
+extern "C" int rr_context_destroy(rr_context* c) {
+  if (c == nullptr) return RR_OK;
+  if (c->fork) cudaEventDestroy(c->fork);
+  for (int i = 0; i < 2; ++i) {
+    if (c->a[i]) cudaEventDestroy(c->a[i]);
+    if (c->b[i]) cudaEventDestroy(c->b[i]);
+  }
+  if (c->aux) cudaStreamDestroy(c->aux);
+  delete c;
+  return RR_OK;
+}
+
+extern "C" int64_t rr_engine_auto_min_rows(void) { return rr::tc_auto_min_rows(); }
+
+extern "C" int rr_version(void) { return 200; }
 
 extern "C" uint64_t rr_launch_count(void) { return (uint64_t)rr::launches(); }
 
@@ -89,5 +148,5 @@ extern "C" int rr_tcgen05_supported(int32_t d, int32_t ktot, int32_t next,
   pl.ktot = ktot;
   pl.next = next;
   pl.D = D;
-  return rr::tc_suffstats_supported(&pl);
+  return rr::tc3_suffstats_supported(&pl);
 }

@@ -59,6 +59,11 @@ struct Workspace {
 };
 
 int sm_count();
+int64_t tc_auto_min_rows();
+
+// Helper stream + events of an rr_context (NULL ctx: *stream is left alone).
+int ctx_aux(rr_context* ctx, cudaStream_t* stream, cudaEvent_t* fork, cudaEvent_t a[2],
+            cudaEvent_t b[2]);
 
 // ---- device helpers --------------------------------------------------------
 
@@ -98,11 +103,16 @@ size_t tc_suffstats_workspace(const rr_plan* plan, int64_t N);
 int tc_suffstats(const rr_plan* plan, const float* X, const float* y, int64_t N,
                  double* G, double* p, void* ws, size_t ws_bytes, int grid_bits,
                  cudaStream_t st);
+int tc3_suffstats_supported(const rr_plan* plan);
+size_t tc3_suffstats_workspace(const rr_plan* plan, int64_t N);
+int tc3_suffstats(const rr_plan* plan, const float* X, const float* y, int64_t N,
+                  double* G, double* p, void* ws, size_t ws_bytes, rr_context* ctx,
+                  cudaStream_t st);
 size_t tc_gradpass_workspace(const rr_plan* plan, int64_t N);
 int tc_gradpass_supported(const rr_plan* plan);
 int tc_gradpass(const rr_plan* plan, const float* X, const float* y, int64_t N,
                 const float* m, const float* C, double* R, double* sqerr, void* ws,
-                size_t ws_bytes, cudaStream_t st);
+                size_t ws_bytes, rr_context* ctx, cudaStream_t st);
 int phi_residual(const rr_plan* plan, const float* X, const float* y, int64_t N,
                  const float* m, float* err, double* sqerr, float* fbuf,
                  cudaStream_t st);

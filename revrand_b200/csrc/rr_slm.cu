@@ -1,7 +1,7 @@
 // Standard linear model passes: C-ABI entry points, engine dispatch and the
 // chunked SIMT engine (works for any feature plan; Phi is materialised one
 // row chunk at a time in the caller's workspace).  The fused tcgen05 engine
-// lives in rr_tc_suffstats.cu / rr_tc_gradpass.cu.
+// lives in rr_tc3_syrk.cu (value pass) / rr_tc_gradpass.cu.
 //
 // Reference: revrand/slm.py:142-199 (_elbo), :219-244 (predict_moments).
 #include "rr_common.cuh"
@@ -9,20 +9,23 @@
 namespace rr {
 
 constexpr int64_t SIMT_CHUNK = 8192;  // rows of Phi held in the workspace
-// RR_ENGINE_AUTO runs the fused tcgen05 engine from this many rows on; below it
-// the job is launch-latency sized and the chunked SIMT engine (fp32 features,
-// float64 Gram accumulation) is both fast enough and the most accurate.  The
-// tcgen05 value pass carries a zero-mean 2^-17 perturbation per trig value whose
-// effect on the posterior shrinks as 1/sqrt(N); small ill-conditioned problems
-// (tests: 256 frequencies on 1000 1-D points) need the SIMT engine for 1e-4.
-constexpr int64_t TC_AUTO_MIN_ROWS = 16384;
 
-// 1 = tcgen05, 0 = SIMT, -1 = tcgen05 demanded but unsupported.
+// Value pass: 1 = int8 fixed-point tensor-core engine (rr_tc3_syrk.cu), 2 = the
+// round-1 fused kind::f16 kernel (rr_tc2_suffstats.cu, kept for A/B runs),
+// 0 = SIMT, -1 = a tensor-core engine was demanded but cannot run this plan.
+// Gradient pass: 1 = tcgen05 (rr_tc_gradpass.cu), 0 = SIMT, -1 as above.
 static int pick_engine(int engine, const rr_plan* plan, int64_t N, bool grad = false) {
-  const bool tc_ok = (grad ? tc_gradpass_supported(plan) : tc_suffstats_supported(plan)) != 0;
-  if (engine == RR_ENGINE_TCGEN05 || engine == RR_ENGINE_TCGEN05_FINE) return tc_ok ? 1 : -1;
   if (engine == RR_ENGINE_SIMT) return 0;
-  return (tc_ok && N >= TC_AUTO_MIN_ROWS) ? 1 : 0;
+  if (grad) {
+    const bool ok = tc_gradpass_supported(plan) != 0;
+    if (engine != RR_ENGINE_AUTO) return ok ? 1 : -1;
+    return (ok && N >= tc_auto_min_rows()) ? 1 : 0;
+  }
+  if (engine == RR_ENGINE_TCGEN05_FINE || engine == RR_ENGINE_TCGEN05_FUSED16)
+    return tc_suffstats_supported(plan) ? 2 : -1;
+  const bool ok = tc3_suffstats_supported(plan) != 0;
+  if (engine == RR_ENGINE_TCGEN05) return ok ? 1 : -1;
+  return (ok && N >= tc_auto_min_rows()) ? 1 : 0;
 }
 
 // p[j] += sum_r Phi[r,j] * y[r].  Thread per column, grid.y splits rows;
@@ -170,7 +173,7 @@ extern "C" int rr_slm_suffstats(const rr_plan* plan, const float* X,
                                 const float* y, int64_t N, double* G, double* p,
                                 double* yy, void* workspace,
                                 size_t workspace_bytes, int32_t engine,
-                                void* stream) {
+                                rr_context* ctx, void* stream) {
   RR_REQUIRE(plan && X && G, "null pointer");
   RR_REQUIRE(N >= 0, "negative N");
   cudaStream_t st = (cudaStream_t)stream;
@@ -184,12 +187,14 @@ extern "C" int rr_slm_suffstats(const rr_plan* plan, const float* X,
     set_error("tcgen05 engine does not support this plan");
     return RR_ERR_UNSUPPORTED;
   }
-  if (use_tc)
+  if (use_tc == 1)
+    return tc3_suffstats(plan, X, y, N, G, y ? p : nullptr, workspace, workspace_bytes, ctx, st);
+  if (use_tc == 2)
     return tc_suffstats(plan, X, y, N, G, p, workspace, workspace_bytes,
                         engine == RR_ENGINE_TCGEN05_FINE ? 7 : 5, st);
   if (plan->kind != nullptr) {
     set_error("a plan with pseudo-frequency slots (kind != NULL) is only understood by "
-              "the tcgen05 engine; pass the plain plan to the SIMT engine");
+              "the fused kind::f16 engine; pass the plain plan to the other engines");
     return RR_ERR_UNSUPPORTED;
   }
   return simt_suffstats(plan, X, y, N, G, y ? p : nullptr, workspace,
@@ -212,7 +217,7 @@ extern "C" int rr_slm_gradpass(const rr_plan* plan, const float* X,
                                const float* y, int64_t N, const float* m,
                                const float* C, double* R, double* sqerr,
                                void* workspace, size_t workspace_bytes,
-                               int32_t engine, void* stream) {
+                               int32_t engine, rr_context* ctx, void* stream) {
   RR_REQUIRE(plan && X && y && m && C && R && sqerr, "null pointer");
   if (N == 0) return RR_OK;
   cudaStream_t st = (cudaStream_t)stream;
@@ -228,7 +233,7 @@ extern "C" int rr_slm_gradpass(const rr_plan* plan, const float* X,
     return RR_ERR_UNSUPPORTED;
   }
   if (use_tc)
-    return tc_gradpass(plan, X, y, N, m, C, R, sqerr, workspace, workspace_bytes, st);
+    return tc_gradpass(plan, X, y, N, m, C, R, sqerr, workspace, workspace_bytes, ctx, st);
   return simt_gradpass(plan, X, y, N, m, C, R, sqerr, workspace, workspace_bytes, st);
 }
 
@@ -265,11 +270,13 @@ extern "C" int rr_slm_predict(const rr_plan* plan, const float* X, int64_t N,
 namespace rr {
 size_t slm_workspace_bytes(int op, int64_t N, const rr_plan* pl, int engine) {
   size_t s = simt_ws(op, N, pl);
-  if (op != RR_OP_PREDICT && op != RR_OP_RESIDUAL &&
-      pick_engine(engine, pl, N, op == RR_OP_GRADPASS) == 1) {
-    size_t t = op == RR_OP_SUFFSTATS ? tc_suffstats_workspace(pl, N)
-                                     : tc_gradpass_workspace(pl, N);
-    return t > 256 ? t : 256;
+  if (op != RR_OP_PREDICT && op != RR_OP_RESIDUAL) {
+    const int e = pick_engine(engine, pl, N, op == RR_OP_GRADPASS);
+    if (e > 0) {
+      size_t t = op == RR_OP_GRADPASS ? tc_gradpass_workspace(pl, N)
+                 : (e == 1 ? tc3_suffstats_workspace(pl, N) : tc_suffstats_workspace(pl, N));
+      return t > 256 ? t : 256;
+    }
   }
   return s;
 }

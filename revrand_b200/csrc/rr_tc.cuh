@@ -350,5 +350,81 @@ __device__ __forceinline__ void tmem_ld8_nowait(uint32_t taddr, float* v) {
       : "memory");
 }
 
+
+// ============================================================================
+// kind::i8 (signed 8-bit operands, int32 accumulators) and the 64-byte swizzle.
+//
+// An i8 operand tile is K-major with 64-byte rows (K = 64 elements) in the
+// SWIZZLE_64B layout: byte k of row r lives at
+//     r*64 + (((k>>4) ^ ((r>>1)&3)) << 4) + (k&15)
+// (cute Swizzle<2,4,3>: address bits [7,9) are XORed into bits [4,6)); 8-row
+// groups are 512 bytes apart (stride byte offset) and tiles are 512-byte
+// aligned.  One tcgen05.mma.kind::i8 consumes K = 32 bytes of every row; the
+// second K step of a 64-byte row advances the descriptor start by 32 bytes.
+// ============================================================================
+__device__ __forceinline__ uint64_t make_desc_sw64(uint32_t saddr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);
+  d |= (uint64_t)1 << 16;              // LBO: unused for swizzled K-major
+  d |= (uint64_t)(512u >> 4) << 32;    // SBO: 8 rows * 64 B
+  d |= (uint64_t)1 << 46;              // descriptor version (sm_100)
+  d |= (uint64_t)4 << 61;              // SWIZZLE_64B
+  return d;
+}
+__device__ __host__ __forceinline__ uint32_t sw64_off(uint32_t row, uint32_t chunk) {
+  return row * 64u + ((chunk ^ ((row >> 1) & 3u)) << 4);
+}
+// Instruction descriptor for kind::i8: signed 8-bit A and B (both K-major),
+// int32 accumulator (c_format = 2), no saturation.
+__device__ __forceinline__ uint32_t make_idesc_i8(uint32_t M, uint32_t N) {
+  return (2u << 4) | (1u << 7) | (1u << 10) | ((N >> 3) << 17) | ((M >> 4) << 24);
+}
+__device__ __forceinline__ void umma_i8_ss(uint32_t tmem_d, uint64_t desc_a,
+                                           uint64_t desc_b, uint32_t idesc,
+                                           uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma2_i8_ss(uint32_t tmem_d, uint64_t desc_a,
+                                            uint64_t desc_b, uint32_t idesc,
+                                            uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::i8 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+
+// ---- bulk (TMA, non-tensor) global -> shared copies ---------------------------
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)),
+               "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes,
+                                         uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::
+          "r"(dst),
+      "l"(src), "r"(bytes), "r"(smem_u32(bar))
+      : "memory");
+}
+// TMEM -> registers: 32 lanes x 16 consecutive int32 columns per warp, no wait.
+__device__ __forceinline__ void tmem_ld16i_nowait(uint32_t taddr, int* r) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]),
+        "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]),
+        "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+}
+
 }  // namespace tc
 }  // namespace rr

@@ -1,0 +1,734 @@
+// Value pass of the SLM log marginal likelihood in exact 24-bit fixed point on
+// the int8 tensor cores (tcgen05.mma.kind::i8):
+//     G += Phi^T Phi,   p += Phi^T y,   Phi = amp * [cos | sin](2 pi X Wt) (+ affine columns).
+//
+// Every feature value v in [-1, 1] (a cosine, a sine, x / max|x| of an affine
+// column, y / max|y|) is rounded ONCE to the integer I = rint(v * S),
+// S = 2^23 - 2^16 - 2^9, and written as three balanced base-256 digits
+//     I = d0 * 65536 + d1 * 256 + d2,    d0, d1, d2 in [-128, 127]
+// i.e. three int8 planes.  The Gram matrix of the integers is then
+//     sum_n I_a I_b = 2^32 S00 + 2^24 (S01 + S10) + 2^16 (S11 + S02 + S20) + [2^8 (S12 + S21) + S22]
+// with Sij = sum_n di_a dj_b: six int8 x int8 -> int32 tensor-core products
+// into three accumulators; the bracket (relative weight 2^-24) is dropped.
+// Integer accumulation is EXACT (|ACC| < 2^31 for 32768-row chains), so the
+// result does not depend on tile order, chunking or the number of ranks, and
+// there is no accumulation bias to engineer around (the fp16 path needed a
+// fixed-point head / remainder split for that).  Each chain is drained as
+//     int64 v = ACC0 * 65536 + ACC1 * 256 + ACC2     (exact)
+// and added (RED.F64, also exact: |sum| < 2^53) to a float64 image T of the
+// upper triangle; a finalize kernel applies 2^16 / S^2 and the amplitudes.
+//
+// Phi itself is produced once per (row, frequency) by t3_digits_kernel -- fp32
+// projection, exact range reduction in turns, sincospif -- as a tile-major
+// int8 image that the GEMM streams with bulk copies.  In the previous design
+// the trigonometric generators sat inside the tensor-core kernel and
+// re-evaluated every feature for each of the ~18 output tiles it takes part
+// in; at 2 x 10^9 (row, frequency) pairs per pass that made the generators,
+// not the tensor pipe, the bound.
+//
+// y rides along as feature column D of the B side, so Phi^T y comes out of
+// the same exact arithmetic.
+//
+// Replaces: revrand/slm.py:145-146, :157 and basis_functions.py:859-864,
+// 1622-1627 (BasisCat.transform), 468-485 (LinearBasis), 415-432 (BiasBasis).
+#include <stdlib.h>
+#include <string.h>
+
+#include "rr_common.cuh"
+#include "rr_tc.cuh"
+
+namespace rr {
+
+using namespace tc;
+
+constexpr int S3_TM = 256;                        // A-side features per tile (128 per CTA)
+constexpr int S3_TN = 160;                        // B-side features per tile (80 per CTA)
+constexpr int S3_KB = 64;                         // rows of X per K block (one 64-byte line)
+constexpr int S3_STAGES = 5;
+constexpr int S3_A_PLANE = (S3_TM / 2) * S3_KB;   // 8192: one digit plane of a CTA's A half
+constexpr int S3_B_PLANE = (S3_TN / 2) * S3_KB;   // 5120
+constexpr int S3_STAGE_BYTES = 3 * (S3_A_PLANE + S3_B_PLANE);   // 39936
+constexpr int S3_THREADS = 6 * 32;                // producer, MMA / relay, 4 epilogue warps
+constexpr int S3_CHAIN = 32768;                   // rows per exact int32 accumulation chain
+constexpr int S3_CHAIN_KB = S3_CHAIN / S3_KB;     // 512
+constexpr float S3_SCALE = 8322560.0f;            // S = 2^23 - 2^16 - 2^9: |d0| <= 127
+constexpr int S3_GROUP_CHAINS = 8;                // chains per generator / GEMM launch
+constexpr size_t S3_GROUP_BYTES_MAX = (size_t)4 << 30;   // digit image budget per buffer
+
+static_assert(S3_A_PLANE % 512 == 0 && S3_B_PLANE % 512 == 0, "64B-swizzle tiles are 512-byte aligned");
+static_assert(3 * S3_TN <= 512, "three int32 accumulators in TMEM");
+// worst case |ACC2| = 3 * 128 * 128 * S3_CHAIN
+static_assert(3ll * 128 * 128 * S3_CHAIN < (1ll << 31), "int32 accumulators must not overflow");
+
+// first column panel that reaches the upper triangle of row panel ib
+__host__ __device__ __forceinline__ int s3_jmin(int ib) { return (S3_TM * ib) / S3_TN; }
+
+// ---- scales ---------------------------------------------------------------------
+// scales[i] = max |X[:, i]| (i < d, only when need_x), scales[d] = max |y|, as
+// float bit patterns (non-negative floats order like unsigned integers).
+__global__ void __launch_bounds__(256)
+t3_scales_kernel(const float* __restrict__ X, const float* __restrict__ y, int64_t N, int d,
+                 int need_x, unsigned int* __restrict__ scales) {
+  extern __shared__ unsigned int smax[];   // d + 1
+  for (int i = threadIdx.x; i <= d; i += blockDim.x) smax[i] = 0u;
+  __syncthreads();
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  const int64_t t0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (y) {
+    float my = 0.0f;
+    for (int64_t i = t0; i < N; i += stride) my = fmaxf(my, fabsf(y[i]));
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) my = fmaxf(my, __shfl_xor_sync(0xffffffffu, my, o));
+    if ((threadIdx.x & 31) == 0) atomicMax(&smax[d], __float_as_uint(my));
+  }
+  if (need_x) {
+    // a thread walks one column: stride is a multiple of d away from its start
+    const int64_t total = N * d;
+    const int64_t step = stride * d;           // keeps (e % d) fixed per thread
+    for (int64_t c0 = t0; c0 < stride * d && c0 < total; c0 += stride) {
+      float mx = 0.0f;
+      for (int64_t e = c0; e < total; e += step) mx = fmaxf(mx, fabsf(X[e]));
+      atomicMax(&smax[(int)(c0 % d)], __float_as_uint(mx));
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i <= d; i += blockDim.x)
+    if (smax[i]) atomicMax(&scales[i], smax[i]);
+}
+
+// camp[f] = real amplitude of integer feature f (f <= D; f == D is the y column).
+__global__ void t3_colamp_kernel(rr_plan plan, const unsigned int* __restrict__ scales,
+                                 float* __restrict__ camp) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t < plan.ktot) {
+    const float a = plan.amp[t];
+    if (plan.col_cos[t] >= 0) camp[plan.col_cos[t]] = a;
+    if (plan.col_sin[t] >= 0) camp[plan.col_sin[t]] = a;
+  }
+  if (t < plan.next) {
+    const int src = plan.ext_src[t];
+    camp[plan.ext_col[t]] = src >= 0 ? __uint_as_float(scales[src]) : plan.ext_val[t];
+  }
+  if (t == 0) camp[plan.D] = __uint_as_float(scales[plan.d]);
+}
+
+// ---- digit image ------------------------------------------------------------------
+// img[kb][plane][f][64 bytes]: K block kb = 64 consecutive rows, plane 0..2 = d0,
+// d1, d2, feature f in Phi's own column order (f == D: y, f > D: zero padding up
+// to Fp).  Inside a 64-byte line the 16-byte chunk of rows 16c .. 16c+15 sits at
+// chunk position c ^ ((f >> 1) & 3): the SWIZZLE_64B image of a tile whose first
+// feature is a multiple of 8, so ANY run of features (8-aligned) of one plane and
+// K block is one contiguous, ready-to-use operand tile.
+__device__ __forceinline__ int t3_quant(float v) {
+  // (I + 0x8080) ^ 0x8080: byte 0 = d2, byte 1 = d1, byte 2 = d0 (two's complement)
+  return (__float2int_rn(v * S3_SCALE) + 0x8080) ^ 0x8080;
+}
+// gather byte `b` of four quantised values into one word per plane
+__device__ __forceinline__ void t3_pack4(int k0, int k1, int k2, int k3, uint32_t& p0,
+                                         uint32_t& p1, uint32_t& p2) {
+  const uint32_t t01 = __byte_perm((uint32_t)k0, (uint32_t)k1, 0x5140);
+  const uint32_t t23 = __byte_perm((uint32_t)k2, (uint32_t)k3, 0x5140);
+  const uint32_t u01 = __byte_perm((uint32_t)k0, (uint32_t)k1, 0x0062);
+  const uint32_t u23 = __byte_perm((uint32_t)k2, (uint32_t)k3, 0x0062);
+  p2 = __byte_perm(t01, t23, 0x5410);
+  p1 = __byte_perm(t01, t23, 0x7632);
+  p0 = __byte_perm(u01, u23, 0x5410);
+}
+__device__ __forceinline__ void t3_store_planes(uint8_t* __restrict__ img, int64_t kb, int Fp,
+                                                int f, int chunk, const uint4& d0,
+                                                const uint4& d1, const uint4& d2) {
+  uint8_t* base = img + (((int64_t)kb * 3) * Fp + f) * 64 + (((uint32_t)chunk ^ (((uint32_t)f >> 1) & 3u)) << 4);
+  const int64_t plane = (int64_t)Fp * 64;
+  *reinterpret_cast<uint4*>(base) = d0;
+  *reinterpret_cast<uint4*>(base + plane) = d1;
+  *reinterpret_cast<uint4*>(base + 2 * plane) = d2;
+}
+
+constexpr int T3_FREQS = 64;     // frequencies (or affine / padding features) per block
+
+// Block = one K block (64 rows) x 64 frequencies; thread = one frequency x 16 rows
+// (one 16-byte chunk of each of its six digit lines).  grid.y counts the
+// trigonometric blocks first, then the blocks of "other" features: affine
+// columns, the y column and the zero padding.
+__global__ void __launch_bounds__(256)
+t3_digits_kernel(rr_plan plan, const float* __restrict__ X, const float* __restrict__ y,
+                 int64_t rows, int Fp, int gy_trig, const unsigned int* __restrict__ scales,
+                 uint8_t* __restrict__ img) {
+  extern __shared__ float xs[];            // [d][64]: column i of the slab, rows fastest
+  const int d = plan.d, ktot = plan.ktot;
+  const int tid = threadIdx.x;
+  const int64_t kb = blockIdx.x;
+  const int64_t n0 = kb * S3_KB;
+  for (int e = tid; e < S3_KB * d; e += 256) {
+    const int r = e / d, i = e - r * d;
+    xs[i * S3_KB + r] = (n0 + r < rows) ? X[n0 * d + e] : 0.0f;
+  }
+  __syncthreads();
+  const int fl = tid >> 2, rg = tid & 3;
+  const int64_t nrow0 = n0 + 16 * rg;      // first row of this thread's chunk
+  if ((int)blockIdx.y >= gy_trig) {
+    // ---- affine columns, y, padding -------------------------------------------
+    const int e = ((int)blockIdx.y - gy_trig) * T3_FREQS + fl;
+    int f;
+    float vals[16];
+    if (e < plan.next) {
+      f = plan.ext_col[e];
+      const int src = plan.ext_src[e];
+      float inv = 0.0f;
+      if (src >= 0) {
+        const float sc = __uint_as_float(scales[src]);
+        inv = sc > 0.0f ? 1.0f / sc : 0.0f;
+      }
+#pragma unroll
+      for (int r = 0; r < 16; ++r) {
+        float v = src >= 0 ? xs[src * S3_KB + 16 * rg + r] * inv : 1.0f;
+        v = fminf(1.0f, fmaxf(-1.0f, v));
+        vals[r] = (nrow0 + r < rows) ? v : 0.0f;
+      }
+    } else if (e == plan.next) {
+      f = plan.D;
+      const float sc = __uint_as_float(scales[d]);
+      const float inv = (y != nullptr && sc > 0.0f) ? 1.0f / sc : 0.0f;
+#pragma unroll
+      for (int r = 0; r < 16; ++r) {
+        float v = (y != nullptr && nrow0 + r < rows) ? y[nrow0 + r] * inv : 0.0f;
+        vals[r] = fminf(1.0f, fmaxf(-1.0f, v));
+      }
+    } else {
+      f = plan.D + (e - plan.next);
+      if (f >= Fp) return;
+#pragma unroll
+      for (int r = 0; r < 16; ++r) vals[r] = 0.0f;
+    }
+    uint4 q0, q1, q2;
+    uint32_t* w0 = reinterpret_cast<uint32_t*>(&q0);
+    uint32_t* w1 = reinterpret_cast<uint32_t*>(&q1);
+    uint32_t* w2 = reinterpret_cast<uint32_t*>(&q2);
+#pragma unroll
+    for (int g = 0; g < 4; ++g)
+      t3_pack4(t3_quant(vals[4 * g]), t3_quant(vals[4 * g + 1]), t3_quant(vals[4 * g + 2]),
+               t3_quant(vals[4 * g + 3]), w0[g], w1[g], w2[g]);
+    t3_store_planes(img, kb, Fp, f, rg, q0, q1, q2);
+    return;
+  }
+  // ---- trigonometric features ------------------------------------------------------
+  const int k = (int)blockIdx.y * T3_FREQS + fl;
+  if (k >= ktot) return;
+  float u[16];
+#pragma unroll
+  for (int r = 0; r < 16; ++r) u[r] = 0.0f;
+  const float* xr = xs + 16 * rg;
+  for (int i = 0; i < d; ++i) {
+    const float w = __ldg(plan.Wt + (int64_t)i * ktot + k);
+    const float4* x4 = reinterpret_cast<const float4*>(xr + i * S3_KB);
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+      const float4 xv = x4[g];
+      u[4 * g + 0] = fmaf(xv.x, w, u[4 * g + 0]);
+      u[4 * g + 1] = fmaf(xv.y, w, u[4 * g + 1]);
+      u[4 * g + 2] = fmaf(xv.z, w, u[4 * g + 2]);
+      u[4 * g + 3] = fmaf(xv.w, w, u[4 * g + 3]);
+    }
+  }
+  const int fc = plan.col_cos[k], fs = plan.col_sin[k];
+  uint4 c0, c1, c2, s0, s1, s2;
+  uint32_t* cw0 = reinterpret_cast<uint32_t*>(&c0);
+  uint32_t* cw1 = reinterpret_cast<uint32_t*>(&c1);
+  uint32_t* cw2 = reinterpret_cast<uint32_t*>(&c2);
+  uint32_t* sw0 = reinterpret_cast<uint32_t*>(&s0);
+  uint32_t* sw1 = reinterpret_cast<uint32_t*>(&s1);
+  uint32_t* sw2 = reinterpret_cast<uint32_t*>(&s2);
+#pragma unroll
+  for (int g = 0; g < 4; ++g) {
+    int kc[4], ks[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int r = 4 * g + j;
+      float sv, cv;
+      sincos_turns(u[r], &sv, &cv);
+      const bool live = nrow0 + r < rows;
+      kc[j] = t3_quant(live ? cv : 0.0f);
+      ks[j] = t3_quant(live ? sv : 0.0f);
+    }
+    t3_pack4(kc[0], kc[1], kc[2], kc[3], cw0[g], cw1[g], cw2[g]);
+    t3_pack4(ks[0], ks[1], ks[2], ks[3], sw0[g], sw1[g], sw2[g]);
+  }
+  if (fc >= 0) t3_store_planes(img, kb, Fp, fc, rg, c0, c1, c2);
+  if (fs >= 0) t3_store_planes(img, kb, Fp, fs, rg, s0, s1, s2);
+}
+
+// ---- int8 SYRK ----------------------------------------------------------------------
+struct S3Bars {
+  uint64_t full[S3_STAGES];        // own bulk copies landed (complete_tx)
+  uint64_t peer_full[S3_STAGES];   // leader only: the peer CTA's copies landed
+  uint64_t empty[S3_STAGES];       // multicast commit: stage consumed by the MMAs
+  uint64_t acc_full;               // multicast commit: the chain's accumulators are complete
+  uint64_t acc_empty;              // leader waits; count 8 (epilogue warps of both CTAs)
+  uint32_t tmem_base;
+};
+
+struct S3Item {
+  int ib, jb;
+  int kb0, nkb;      // K blocks of this chain inside the launch's image
+};
+
+__device__ __forceinline__ S3Item s3_decode(int item, int ntiles, int NIB, int NJB,
+                                            int nkb_total) {
+  S3Item it;
+  const int chain = item / ntiles;
+  int t = item - chain * ntiles;
+  int ib = 0;
+  for (; ib < NIB; ++ib) {
+    const int cnt = NJB - s3_jmin(ib);
+    if (t < cnt) break;
+    t -= cnt;
+  }
+  it.ib = ib;
+  it.jb = s3_jmin(ib) + t;
+  it.kb0 = chain * S3_CHAIN_KB;
+  const int left = nkb_total - it.kb0;
+  it.nkb = left < S3_CHAIN_KB ? left : S3_CHAIN_KB;
+  return it;
+}
+
+// T is (D + 1) x ldT float64, T[fb][fa] for fb >= fa (fa fastest: a warp's 32
+// accumulator lanes are 32 consecutive fa).
+__global__ void __launch_bounds__(S3_THREADS, 1)
+t3_syrk_kernel(const uint8_t* __restrict__ img, int Fp, int nkb_total, int D, int NIB, int NJB,
+               int ntiles, int nitems, double* __restrict__ T, int64_t ldT) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>(
+      (reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  __shared__ S3Bars sb;
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const uint32_t crank = cluster_ctarank();
+  const int pair = blockIdx.x >> 1, npairs = gridDim.x >> 1;
+
+  if (tid == 0) {
+    for (int s = 0; s < S3_STAGES; ++s) {
+      mbar_init(&sb.full[s], 1);
+      mbar_init(&sb.peer_full[s], 1);
+      mbar_init(&sb.empty[s], 1);
+    }
+    mbar_init(&sb.acc_full, 1);
+    mbar_init(&sb.acc_empty, 8);
+    mbar_fence_init();
+  }
+  if (warp == 1) tmem_alloc_2cta(&sb.tmem_base, 512);
+  tc_fence_before_sync();
+  __syncthreads();
+  cluster_sync_all();
+  tc_fence_after_sync();
+  const uint32_t tmem = sb.tmem_base;
+  const int64_t plane = (int64_t)Fp * 64;          // bytes of one digit plane of one K block
+
+  if (warp == 0) {
+    // ============================ producer (both CTAs) ============================
+    if (elect_one()) {
+      uint32_t g = 0;
+      for (int item = pair; item < nitems; item += npairs) {
+        const S3Item it = s3_decode(item, ntiles, NIB, NJB, nkb_total);
+        const uint8_t* a_src = img + ((int64_t)it.kb0 * 3) * plane +
+                               (int64_t)(S3_TM * it.ib + (S3_TM / 2) * (int)crank) * 64;
+        const uint8_t* b_src = img + ((int64_t)it.kb0 * 3) * plane +
+                               (int64_t)(S3_TN * it.jb + (S3_TN / 2) * (int)crank) * 64;
+        for (int kb = 0; kb < it.nkb; ++kb, ++g) {
+          const uint32_t s = g % S3_STAGES;
+          mbar_wait_cl(&sb.empty[s], ((g / S3_STAGES) & 1) ^ 1);
+          const uint32_t dst = smem_u32(smem + s * S3_STAGE_BYTES);
+          mbar_expect_tx(&sb.full[s], S3_STAGE_BYTES);
+#pragma unroll
+          for (int j = 0; j < 3; ++j) {
+            bulk_g2s(dst + j * S3_A_PLANE, a_src + ((int64_t)kb * 3 + j) * plane, S3_A_PLANE,
+                     &sb.full[s]);
+            bulk_g2s(dst + 3 * S3_A_PLANE + j * S3_B_PLANE,
+                     b_src + ((int64_t)kb * 3 + j) * plane, S3_B_PLANE, &sb.full[s]);
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (crank == 0) {
+      // ========================== MMA issuer (leader CTA) ==========================
+      const uint32_t idesc = make_idesc_i8(S3_TM, S3_TN);
+      const uint32_t acc0 = tmem, acc1 = tmem + S3_TN, acc2 = tmem + 2 * S3_TN;
+      uint32_t g = 0, itc = 0;
+      for (int item = pair; item < nitems; item += npairs, ++itc) {
+        const S3Item it = s3_decode(item, ntiles, NIB, NJB, nkb_total);
+        mbar_wait_cl(&sb.acc_empty, (itc & 1) ^ 1);
+        tc_fence_after_sync();
+        for (int kb = 0; kb < it.nkb; ++kb, ++g) {
+          const uint32_t s = g % S3_STAGES;
+          const uint32_t ph = (g / S3_STAGES) & 1;
+          mbar_wait_cl(&sb.full[s], ph);
+          mbar_wait_cl(&sb.peer_full[s], ph);
+          tc_fence_after_sync();
+          if (elect_one()) {
+            const uint32_t a0 = smem_u32(smem + s * S3_STAGE_BYTES);
+            const uint32_t b0 = a0 + 3 * S3_A_PLANE;
+            const uint64_t da0 = make_desc_sw64(a0), da1 = make_desc_sw64(a0 + S3_A_PLANE),
+                           da2 = make_desc_sw64(a0 + 2 * S3_A_PLANE);
+            const uint64_t db0 = make_desc_sw64(b0), db1 = make_desc_sw64(b0 + S3_B_PLANE),
+                           db2 = make_desc_sw64(b0 + 2 * S3_B_PLANE);
+#pragma unroll
+            for (int k = 0; k < S3_KB / 32; ++k) {
+              const uint64_t adv = (uint64_t)(2 * k);
+              const uint32_t acc = (kb | k) != 0;
+              umma2_i8_ss(acc0, da0 + adv, db0 + adv, idesc, acc);
+              umma2_i8_ss(acc1, da0 + adv, db1 + adv, idesc, acc);
+              umma2_i8_ss(acc1, da1 + adv, db0 + adv, idesc, 1);
+              umma2_i8_ss(acc2, da1 + adv, db1 + adv, idesc, acc);
+              umma2_i8_ss(acc2, da0 + adv, db2 + adv, idesc, 1);
+              umma2_i8_ss(acc2, da2 + adv, db0 + adv, idesc, 1);
+            }
+            umma2_commit_mc(&sb.empty[s]);
+            if (kb == it.nkb - 1) umma2_commit_mc(&sb.acc_full);
+          }
+          __syncwarp();
+        }
+      }
+    } else {
+      // ===================== relay (peer CTA): my stage landed =====================
+      uint32_t g = 0;
+      for (int item = pair; item < nitems; item += npairs) {
+        const S3Item it = s3_decode(item, ntiles, NIB, NJB, nkb_total);
+        for (int kb = 0; kb < it.nkb; ++kb, ++g) {
+          const uint32_t s = g % S3_STAGES;
+          mbar_wait_cl(&sb.full[s], (g / S3_STAGES) & 1);
+          if (lane == 0) mbar_arrive_cluster(mapa_u32(smem_u32(&sb.peer_full[s]), 0));
+          __syncwarp();
+        }
+      }
+    }
+  } else {
+    // ============================ epilogue (warps 2..5) ============================
+    const int q = warp & 3;               // TMEM lane quadrant this warp may read
+    uint32_t itc = 0;
+    for (int item = pair; item < nitems; item += npairs, ++itc) {
+      const S3Item it = s3_decode(item, ntiles, NIB, NJB, nkb_total);
+      const int fa = S3_TM * it.ib + (S3_TM / 2) * (int)crank + 32 * q + lane;
+      const int fb0 = S3_TN * it.jb;
+      mbar_wait_cl(&sb.acc_full, itc & 1);
+      tc_fence_after_sync();
+      const uint32_t tacc = tmem + ((uint32_t)(32 * q) << 16);
+      double* Tcol = T + fa;
+#pragma unroll 1
+      for (int c0 = 0; c0 < S3_TN; c0 += 16) {
+        int a0[16], a1[16], a2[16];
+        tmem_ld16i_nowait(tacc + (uint32_t)c0, a0);
+        tmem_ld16i_nowait(tacc + (uint32_t)(S3_TN + c0), a1);
+        tmem_ld16i_nowait(tacc + (uint32_t)(2 * S3_TN + c0), a2);
+        tmem_ld_wait();
+        if (c0 + 16 >= S3_TN) {             // all TMEM reads of this chain are done
+          tc_fence_before_sync();
+          __syncwarp();
+          if (lane == 0) mbar_arrive_cluster(mapa_u32(smem_u32(&sb.acc_empty), 0));
+        }
+#pragma unroll
+        for (int r = 0; r < 16; ++r) {
+          const int fb = fb0 + c0 + r;
+          if (fa < D && fb <= D && fb >= fa) {
+            const long long v = (long long)a0[r] * 65536ll + (long long)a1[r] * 256ll +
+                                (long long)a2[r];
+            if (v != 0) atomicAdd(Tcol + (int64_t)fb * ldT, (double)v);
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  cluster_sync_all();
+  if (warp == 1) tmem_dealloc_2cta(tmem, 512);
+}
+
+// G[i][j] += kappa * camp_i * camp_j * T[max(i,j)][min(i,j)],  p[i] += kappa * camp_i * camp_D * T[D][i].
+__global__ void __launch_bounds__(256)
+t3_finalize_kernel(const double* __restrict__ T, int64_t ldT, const float* __restrict__ camp,
+                   double* __restrict__ G, double* __restrict__ p, int D, double kappa) {
+  __shared__ double tile[32][33];
+  const int bx = blockIdx.x, by = blockIdx.y;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;   // 32 x 8
+  if (by == gridDim.y - 1) {
+    // last grid row: the y column -> p
+    if (p != nullptr) {
+      const int i = bx * 32 + tx;
+      if (ty == 0 && i < D)
+        p[i] += kappa * (double)camp[i] * (double)camp[D] * T[(int64_t)D * ldT + i];
+    }
+    return;
+  }
+  if (by >= bx) {
+    // lower (or diagonal) block of G: rows by, columns bx -> T[i][j] directly
+    for (int r = ty; r < 32; r += 8) {
+      const int i = by * 32 + r, j = bx * 32 + tx;
+      tile[r][tx] = (i < D && j < D) ? T[(int64_t)i * ldT + j] : 0.0;
+    }
+    __syncthreads();
+    for (int r = ty; r < 32; r += 8) {
+      const int i = by * 32 + r, j = bx * 32 + tx;
+      if (i < D && j < D) {
+        const double v = (by > bx || r >= tx) ? tile[r][tx] : tile[tx][r];
+        G[(int64_t)i * D + j] += kappa * (double)camp[i] * (double)camp[j] * v;
+      }
+    }
+  } else {
+    // upper block: G[i][j] = T[j][i]; read T's block (rows bx, columns by) coalesced
+    for (int r = ty; r < 32; r += 8) {
+      const int jj = bx * 32 + r, ii = by * 32 + tx;
+      tile[r][tx] = (jj < D && ii < D) ? T[(int64_t)jj * ldT + ii] : 0.0;
+    }
+    __syncthreads();
+    for (int r = ty; r < 32; r += 8) {
+      const int i = by * 32 + r, j = bx * 32 + tx;
+      if (i < D && j < D)
+        G[(int64_t)i * D + j] += kappa * (double)camp[i] * (double)camp[j] * tile[tx][r];
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------
+// Host side
+// ---------------------------------------------------------------------------
+struct S3Shape {
+  int D, NIB, NJB, Fp, ntiles;
+  int64_t ldT, group_rows;
+  size_t group_bytes;
+};
+
+static S3Shape s3_shape(const rr_plan* pl, int64_t N) {
+  S3Shape s;
+  s.D = pl->D;
+  s.NIB = (s.D + S3_TM - 1) / S3_TM;
+  s.NJB = (s.D + 1 + S3_TN - 1) / S3_TN;
+  const int fa = S3_TM * s.NIB, fb = S3_TN * s.NJB;
+  s.Fp = fa > fb ? fa : fb;
+  s.ntiles = 0;
+  for (int ib = 0; ib < s.NIB; ++ib) s.ntiles += s.NJB - s3_jmin(ib);
+  s.ldT = ((int64_t)s.D + 3) / 4 * 4;
+  int64_t chains = S3_GROUP_CHAINS;
+  const int64_t per_chain = (int64_t)3 * S3_CHAIN * s.Fp;
+  while (chains > 1 && (size_t)(chains * per_chain) > S3_GROUP_BYTES_MAX) --chains;
+  const int64_t need = (N + S3_CHAIN - 1) / S3_CHAIN;
+  if (need < chains) chains = need < 1 ? 1 : need;
+  s.group_rows = chains * S3_CHAIN;
+  int64_t rows_buf = s.group_rows < N ? s.group_rows : ((N + S3_KB - 1) / S3_KB) * S3_KB;
+  if (rows_buf < S3_KB) rows_buf = S3_KB;
+  s.group_bytes = (size_t)3 * rows_buf * s.Fp;
+  return s;
+}
+
+int tc3_suffstats_supported(const rr_plan* pl) {
+  if (pl->d < 1 || pl->d > 128 || pl->D < 1 || pl->kind != nullptr) return 0;
+  return pl->D == 2 * pl->ktot + pl->next ? 1 : 0;
+}
+
+size_t tc3_suffstats_workspace(const rr_plan* pl, int64_t N) {
+  const S3Shape s = s3_shape(pl, N);
+  return align_up((size_t)(s.D + 1) * s.ldT * sizeof(double), 256) +
+         align_up((size_t)(s.D + 1) * sizeof(float), 256) +
+         align_up((size_t)(pl->d + 1) * sizeof(unsigned int), 256) +
+         2 * (align_up(s.group_bytes, 1024) + 1024) + 4096;
+}
+
+static int launch_syrk(const uint8_t* img, const S3Shape& s, int nkb, double* T, cudaStream_t st) {
+  const size_t smem = (size_t)S3_STAGES * S3_STAGE_BYTES + 1024;
+  RR_CUDA_CHECK(cudaFuncSetAttribute(t3_syrk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     (int)smem));
+  const int nchains = (nkb + S3_CHAIN_KB - 1) / S3_CHAIN_KB;
+  const int nitems = nchains * s.ntiles;
+  int npairs = sm_count() / 2;
+  if (nitems < npairs) npairs = nitems;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(2 * npairs);
+  cfg.blockDim = dim3(S3_THREADS);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  RR_CUDA_CHECK(cudaLaunchKernelEx(&cfg, t3_syrk_kernel, img, s.Fp, nkb, s.D, s.NIB, s.NJB,
+                                   s.ntiles, nitems, T, s.ldT));
+  RR_LAUNCH_CHECK("t3_syrk_kernel");
+  return RR_OK;
+}
+
+static int tc3_groups(const rr_plan* pl, const S3Shape& s, const float* X, const float* y,
+                      int64_t N, const unsigned int* scales, uint8_t* const imgs[2], double* T,
+                      bool overlap, cudaStream_t sg, cudaStream_t st, cudaEvent_t ev_gen[2],
+                      cudaEvent_t ev_mma[2]) {
+  const int d = pl->d, D = s.D;
+  const int gy_trig = (pl->ktot + T3_FREQS - 1) / T3_FREQS;
+  const int nother = pl->next + 1 + (s.Fp - (D + 1));
+  const int gy_other = (nother + T3_FREQS - 1) / T3_FREQS;
+  const size_t dsmem = (size_t)S3_KB * d * sizeof(float);
+  int g = 0;
+  for (int64_t r0 = 0; r0 < N; r0 += s.group_rows, ++g) {
+    const int64_t rows = (N - r0) < s.group_rows ? (N - r0) : s.group_rows;
+    const int nkb = (int)((rows + S3_KB - 1) / S3_KB);
+    const int buf = g & 1;
+    if (overlap && g >= 2) RR_CUDA_CHECK(cudaStreamWaitEvent(sg, ev_mma[buf], 0));
+    dim3 grid((unsigned)nkb, (unsigned)(gy_trig + gy_other));
+    t3_digits_kernel<<<grid, 256, dsmem, sg>>>(*pl, X + r0 * d, y ? y + r0 : nullptr, rows, s.Fp,
+                                               gy_trig, scales, imgs[buf]);
+    RR_LAUNCH_CHECK("t3_digits_kernel");
+    if (overlap) {
+      RR_CUDA_CHECK(cudaEventRecord(ev_gen[buf], sg));
+      RR_CUDA_CHECK(cudaStreamWaitEvent(st, ev_gen[buf], 0));
+    }
+    const int rc = launch_syrk(imgs[buf], s, nkb, T, st);
+    if (rc) return rc;
+    if (overlap) RR_CUDA_CHECK(cudaEventRecord(ev_mma[buf], st));
+  }
+  return RR_OK;
+}
+
+int tc3_suffstats(const rr_plan* pl, const float* X, const float* y, int64_t N, double* G,
+                  double* p, void* ws, size_t ws_bytes, rr_context* ctx, cudaStream_t st) {
+  const S3Shape s = s3_shape(pl, N);
+  const int D = s.D, d = pl->d;
+  Workspace W(ws, ws_bytes);
+  double* T = W.take<double>((size_t)(D + 1) * s.ldT);
+  float* camp = W.take<float>((size_t)D + 1);
+  unsigned int* scales = W.take<unsigned int>((size_t)d + 1);
+  uint8_t* imgs[2];
+  imgs[0] = W.take<uint8_t>(align_up(s.group_bytes, 1024) + 1024);
+  imgs[1] = W.take<uint8_t>(align_up(s.group_bytes, 1024) + 1024);
+  if (!T || !camp || !scales || !imgs[0] || !imgs[1]) {
+    set_error("int8 suffstats workspace too small (need %zu bytes)",
+              tc3_suffstats_workspace(pl, N));
+    return RR_ERR_WORKSPACE;
+  }
+  for (int i = 0; i < 2; ++i)
+    imgs[i] = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(imgs[i]) + 1023) & ~(uintptr_t)1023);
+
+  RR_CUDA_CHECK(cudaMemsetAsync(T, 0, (size_t)(D + 1) * s.ldT * sizeof(double), st));
+  RR_CUDA_CHECK(cudaMemsetAsync(scales, 0, (size_t)(d + 1) * sizeof(unsigned int), st));
+  RR_CUDA_CHECK(cudaMemsetAsync(camp, 0, (size_t)(D + 1) * sizeof(float), st));
+  bool need_x = false;   // any affine column that copies an input column?  (host plan is a
+                         // device image: decide from `next` alone)
+  need_x = pl->next > 0;
+  {
+    const int blocks = sm_count() * 4;
+    t3_scales_kernel<<<blocks, 256, (size_t)(d + 1) * sizeof(unsigned int), st>>>(
+        X, (p != nullptr) ? y : nullptr, N, d, need_x ? 1 : 0, scales);
+    RR_LAUNCH_CHECK("t3_scales_kernel");
+    const int nth = pl->ktot > pl->next ? pl->ktot : pl->next;
+    t3_colamp_kernel<<<(nth + 256) / 256, 256, 0, st>>>(*pl, scales, camp);
+    RR_LAUNCH_CHECK("t3_colamp_kernel");
+  }
+
+  cudaStream_t sg = st;                     // generator stream
+  cudaEvent_t ev_fork = nullptr, ev_gen[2] = {nullptr, nullptr}, ev_mma[2] = {nullptr, nullptr};
+  if (ctx != nullptr && ctx_aux(ctx, &sg, &ev_fork, ev_gen, ev_mma) != RR_OK) return RR_ERR_CUDA;
+  const bool overlap = sg != st;
+  if (overlap) {
+    RR_CUDA_CHECK(cudaEventRecord(ev_fork, st));
+    RR_CUDA_CHECK(cudaStreamWaitEvent(sg, ev_fork, 0));
+  }
+
+  {
+    const int rc = tc3_groups(pl, s, X, (p != nullptr) ? y : nullptr, N, scales, imgs, T, overlap, sg,
+                              st, ev_gen, ev_mma);
+    if (rc) {   // join whatever the helper stream still has queued, then report
+      if (overlap && cudaEventRecord(ev_fork, sg) == cudaSuccess) cudaStreamWaitEvent(st, ev_fork, 0);
+      return rc;
+    }
+  }
+  {
+    const double kappa = 65536.0 / ((double)S3_SCALE * (double)S3_SCALE);
+    dim3 fg((D + 31) / 32, (D + 31) / 32 + 1);
+    t3_finalize_kernel<<<fg, 256, 0, st>>>(T, s.ldT, camp, G, p, D, kappa);
+    RR_LAUNCH_CHECK("t3_finalize_kernel");
+  }
+  return RR_OK;
+}
+
+}  // namespace rr
+
+// ---------------------------------------------------------------------------
+// Self-test: the production GEMM kernel on a random digit image, bit-exact
+// against a host integer reference (descriptor encodings, 64-byte swizzle,
+// digit-product schedule, TMEM drain, triangular tile set).
+// ---------------------------------------------------------------------------
+extern "C" int rr_tcgen05_i8_selftest(int32_t kblocks, int64_t* mismatches) {
+  using namespace rr;
+  RR_REQUIRE(kblocks >= 1 && kblocks <= 4096, "kblocks out of range");
+  rr_plan pl;
+  memset(&pl, 0, sizeof(pl));
+  pl.d = 1;
+  pl.ktot = 150;
+  pl.D = 300;
+  const int64_t N = (int64_t)kblocks * S3_KB;
+  S3Shape s = s3_shape(&pl, N);
+  const int D = s.D, Fp = s.Fp;
+  const size_t img_bytes = (size_t)3 * kblocks * Fp * 64;
+  const size_t t_bytes = (size_t)(D + 1) * s.ldT * sizeof(double);
+  int8_t* hd = (int8_t*)malloc((size_t)3 * N * Fp);        // [plane][row n][feature f]
+  uint8_t* himg = (uint8_t*)calloc(img_bytes, 1);
+  double* hT = (double*)malloc(t_bytes);
+  uint8_t* dimg = nullptr;
+  double* dT = nullptr;
+  int rc = RR_OK;
+  cudaError_t e;
+  uint32_t seed = 777u;
+  auto rnd = [&]() {
+    seed = seed * 1664525u + 1013904223u;
+    return (int)((seed >> 13) & 0xFF) - 128;
+  };
+  for (int j = 0; j < 3; ++j)
+    for (int64_t n = 0; n < N; ++n)
+      for (int f = 0; f < Fp; ++f) {
+        const int8_t v = (int8_t)((f <= D) ? rnd() : 0);
+        hd[((size_t)j * N + n) * Fp + f] = v;
+        const int64_t kb = n / S3_KB;
+        const uint32_t r = (uint32_t)(n % S3_KB);
+        himg[(((size_t)kb * 3 + j) * Fp + f) * 64 + (((r >> 4) ^ (((uint32_t)f >> 1) & 3u)) << 4) + (r & 15u)] =
+            (uint8_t)v;
+      }
+#define ST_CHECK(x) do { e = (x); if (e != cudaSuccess) { set_error("i8 selftest: %s: %s", #x, cudaGetErrorString(e)); rc = RR_ERR_CUDA; goto done; } } while (0)
+  ST_CHECK(cudaMalloc(&dimg, img_bytes));
+  ST_CHECK(cudaMalloc(&dT, t_bytes));
+  ST_CHECK(cudaMemcpy(dimg, himg, img_bytes, cudaMemcpyHostToDevice));
+  ST_CHECK(cudaMemset(dT, 0, t_bytes));
+  rc = launch_syrk(dimg, s, kblocks, dT, 0);
+  if (rc) goto done;
+  ST_CHECK(cudaDeviceSynchronize());
+  ST_CHECK(cudaMemcpy(hT, dT, t_bytes, cudaMemcpyDeviceToHost));
+  {
+    int64_t bad = 0;
+    for (int fb = 0; fb <= D; ++fb)
+      for (int fa = 0; fa < D; ++fa) {
+        long long ref = 0;
+        if (fb >= fa) {
+          for (int64_t n = 0; n < N; ++n) {
+            const long long a0 = hd[((size_t)0 * N + n) * Fp + fa], a1 = hd[((size_t)1 * N + n) * Fp + fa],
+                            a2 = hd[((size_t)2 * N + n) * Fp + fa];
+            const long long b0 = hd[((size_t)0 * N + n) * Fp + fb], b1 = hd[((size_t)1 * N + n) * Fp + fb],
+                            b2 = hd[((size_t)2 * N + n) * Fp + fb];
+            ref += a0 * b0 * 65536ll + (a0 * b1 + a1 * b0) * 256ll + (a1 * b1 + a0 * b2 + a2 * b0);
+          }
+        }
+        if (hT[(size_t)fb * s.ldT + fa] != (double)ref) ++bad;
+      }
+    if (mismatches) *mismatches = bad;
+    if (bad) {
+      set_error("tcgen05 kind::i8 selftest: %lld accumulator entries differ from the host reference",
+                (long long)bad);
+      rc = RR_ERR_CUDA;
+    }
+  }
+done:
+#undef ST_CHECK
+  cudaFree(dimg);
+  cudaFree(dT);
+  free(hd);
+  free(himg);
+  free(hT);
+  return rc;
+}

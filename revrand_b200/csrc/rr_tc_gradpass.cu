@@ -6,10 +6,10 @@
 //   R += X^T Q                                                  (d x ktot, float64)
 //
 // dPhi (N x 2K x d in the reference, basis_functions.py:888-901) is never
-// formed, and Phi only ever exists as an fp16 row chunk in a scratch buffer
-// sized to stay L2-resident together with the fp16 image of C.  Per row chunk:
+// formed, and Phi only ever exists as an fp16 row chunk (up to 320 MB, two
+// ping-pong buffers) in the caller's workspace.  Per row chunk:
 //
-//   1. phi_err_kernel: one pass over the chunk's (row, frequency) pairs on the
+//   1. phi_fit_kernel: one pass over the chunk's (row, frequency) pairs on the
 //      CUDA cores: fp32 projection, exact range reduction, MUFU sin/cos.  It
 //      accumulates f = Phi m in fp32 from the very same trig values (so the
 //      residuals cost no extra transcendental work) and writes the fp16 Phi
@@ -280,20 +280,6 @@ struct G2Bars {
   uint64_t acc_empty[2];           // leader waits; count 8 (epilogue warps of both CTAs)
   uint32_t tmem_base;
 };
-
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)),
-               "r"(bytes)
-               : "memory");
-}
-__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes,
-                                         uint64_t* bar) {
-  asm volatile(
-      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::
-          "r"(dst),
-      "l"(src), "r"(bytes), "r"(smem_u32(bar))
-      : "memory");
-}
 
 template <int IG>   // input dimensions per reducing warp: d <= 4 * IG
 __global__ void __launch_bounds__(G2_THREADS, 1)
@@ -617,36 +603,22 @@ int phi_residual(const rr_plan* pl, const float* X, const float* y, int64_t N,
   return RR_OK;
 }
 
-// Helper stream + events (per device, created on first use): the Phi chunk of
-// row chunk c+1 is generated on the helper stream while the GEMM of chunk c runs
-// on the caller's stream (two scratch chunks, ping-pong).  A phi_fit block needs
-// 9 K registers and 1.6 KB of shared memory, so one fits on every SM next to the
-// resident GEMM CTA; and with nothing queued between them, consecutive GEMM
-// launches overlap the epilogue tail of one with the pipeline fill of the next.
-struct GpAux {
-  cudaStream_t stream = nullptr;
-  cudaEvent_t fork = nullptr, phi[2] = {nullptr, nullptr}, gemm[2] = {nullptr, nullptr};
-};
-static GpAux* gp_aux() {
-  static GpAux aux[64];
-  int dev = 0;
-  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
-  GpAux& a = aux[dev];
-  if (!a.stream) {
-    if (cudaStreamCreateWithFlags(&a.stream, cudaStreamNonBlocking) != cudaSuccess) return nullptr;
-    bool ok = cudaEventCreateWithFlags(&a.fork, cudaEventDisableTiming) == cudaSuccess;
-    for (int i = 0; i < 2; ++i) {
-      ok = ok && cudaEventCreateWithFlags(&a.phi[i], cudaEventDisableTiming) == cudaSuccess;
-      ok = ok && cudaEventCreateWithFlags(&a.gemm[i], cudaEventDisableTiming) == cudaSuccess;
-    }
-    if (!ok) return nullptr;
-  }
-  return &a;
+// The Phi chunk of row chunk c+1 is generated on the context's helper stream while
+// the GEMM of chunk c runs on the caller's stream (two scratch chunks, ping-pong).
+// A phi_fit block needs 9 K registers and 1.6 KB of shared memory, so one fits on
+// every SM next to the resident GEMM CTA; and with nothing queued between them,
+// consecutive GEMM launches overlap the epilogue tail of one with the pipeline
+// fill of the next.  Without a context everything runs on the caller's stream.
+// error path: whatever the helper stream still has queued is joined back into the
+// caller's stream before the status is returned
+static int join_helper(int rc, bool overlap, cudaStream_t sp, cudaStream_t st, cudaEvent_t ev) {
+  if (overlap && cudaEventRecord(ev, sp) == cudaSuccess) cudaStreamWaitEvent(st, ev, 0);
+  return rc;
 }
 
 int tc_gradpass(const rr_plan* pl, const float* X, const float* y, int64_t N,
                 const float* m, const float* C, double* R, double* sqerr, void* ws,
-                size_t wsb, cudaStream_t st) {
+                size_t wsb, rr_context* ctx, cudaStream_t st) {
   const int Dp = gp_dp(pl), Dk = gp_dk(pl), FB = Dp / G2_TN, nkb = Dk / G2_KT;
   const int RBc = gp_chunk_blocks(pl, N);
   const int64_t RC = (int64_t)RBc * G2_TM;
@@ -657,17 +629,14 @@ int tc_gradpass(const rr_plan* pl, const float* X, const float* y, int64_t N,
   uint8_t* BtT = W.take<uint8_t>(align_up((size_t)Dp * Dk * 2, 1024) + 1024);
   float* err = W.take<float>((size_t)N);      // fitted values, then residuals
   unsigned int* cmax = W.take<unsigned int>(1);
-  GpAux* aux = gp_aux();
-  static const bool no_overlap = getenv("RR_GP_NO_OVERLAP") != nullptr;   // A/B switch
-  cudaStream_t sp = (aux && !no_overlap) ? aux->stream : st;             // Phi stream
+  cudaStream_t sp = st;                                                   // Phi stream
+  cudaEvent_t ev_fork = nullptr, ev_phi[2] = {nullptr, nullptr}, ev_gemm[2] = {nullptr, nullptr};
+  if (ctx_aux(ctx, &sp, &ev_fork, ev_phi, ev_gemm) != RR_OK) return RR_ERR_CUDA;
+  const bool overlap = sp != st;
   if (!PhTb[0] || !PhTb[1] || !BtT || !err || !cmax) {
     set_error("tcgen05 gradpass workspace too small (need %zu bytes)",
               tc_gradpass_workspace(pl, N));
     return RR_ERR_WORKSPACE;
-  }
-  if (!aux) {
-    set_error("could not create the helper stream of the gradient pass");
-    return RR_ERR_CUDA;
   }
   // the bulk copies need 16-byte aligned images
   for (int i = 0; i < 2; ++i)
@@ -675,8 +644,10 @@ int tc_gradpass(const rr_plan* pl, const float* X, const float* y, int64_t N,
   BtT = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(BtT) + 1023) & ~(uintptr_t)1023);
   RR_CUDA_CHECK(cudaMemsetAsync(cmax, 0, sizeof(unsigned int), st));
   RR_CUDA_CHECK(cudaMemsetAsync(err, 0, (size_t)N * sizeof(float), st));
-  RR_CUDA_CHECK(cudaEventRecord(aux->fork, st));          // inputs (m, y, X) are ready
-  RR_CUDA_CHECK(cudaStreamWaitEvent(aux->stream, aux->fork, 0));
+  if (overlap) {
+    RR_CUDA_CHECK(cudaEventRecord(ev_fork, st));          // inputs (m, y, X) are ready
+    RR_CUDA_CHECK(cudaStreamWaitEvent(sp, ev_fork, 0));
+  }
   absmax_kernel<<<sm_count() * 4, 256, 0, st>>>(C, (int64_t)pl->D * pl->D, cmax);
   RR_LAUNCH_CHECK("absmax_kernel");
   {
@@ -693,16 +664,18 @@ int tc_gradpass(const rr_plan* pl, const float* X, const float* y, int64_t N,
     const int buf = c & 1;
     uint8_t* PhT = PhTb[buf];
     // helper stream: Phi chunk c (after the GEMM of chunk c-2 released the buffer)
-    if (c >= 2) RR_CUDA_CHECK(cudaStreamWaitEvent(aux->stream, aux->gemm[buf], 0));
+    if (overlap && c >= 2) RR_CUDA_CHECK(cudaStreamWaitEvent(sp, ev_gemm[buf], 0));
     int rc = launch_phi_fit(pl, X + s * d, rows, rows_pad, Dp, Dk, m, PhT, err + s, sp);
-    if (rc) return rc;
+    if (rc) return join_helper(rc, overlap, sp, st, ev_fork);
     // fitted values -> residuals (in place) + their sum of squares
     resid_finish_kernel<<<(rows + 1023) / 1024, 256, 0, sp>>>(y + s, err + s, rows, err + s,
                                                              sqerr);
     RR_LAUNCH_CHECK("resid_finish_kernel");
-    RR_CUDA_CHECK(cudaEventRecord(aux->phi[buf], sp));
-    // caller's stream: GEMM + epilogue of chunk c
-    RR_CUDA_CHECK(cudaStreamWaitEvent(st, aux->phi[buf], 0));
+    if (overlap) {
+      RR_CUDA_CHECK(cudaEventRecord(ev_phi[buf], sp));
+      // caller's stream: GEMM + epilogue of chunk c
+      RR_CUDA_CHECK(cudaStreamWaitEvent(st, ev_phi[buf], 0));
+    }
     const float* Xc = X + s * d;
     const float* ec = err + s;
     if (d <= 4) rc = launch_gp2<1>(pl, Xc, ec, rows, RB, FB, nkb, PhT, BtT, m, cmax, R, st);
@@ -710,8 +683,8 @@ int tc_gradpass(const rr_plan* pl, const float* X, const float* y, int64_t N,
     else if (d <= 16) rc = launch_gp2<4>(pl, Xc, ec, rows, RB, FB, nkb, PhT, BtT, m, cmax, R, st);
     else if (d <= 24) rc = launch_gp2<6>(pl, Xc, ec, rows, RB, FB, nkb, PhT, BtT, m, cmax, R, st);
     else rc = launch_gp2<8>(pl, Xc, ec, rows, RB, FB, nkb, PhT, BtT, m, cmax, R, st);
-    if (rc) return rc;
-    RR_CUDA_CHECK(cudaEventRecord(aux->gemm[buf], st));
+    if (rc) return join_helper(rc, overlap, sp, st, ev_fork);
+    if (overlap) RR_CUDA_CHECK(cudaEventRecord(ev_gemm[buf], st));
   }
   return RR_OK;
 }

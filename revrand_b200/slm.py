@@ -51,9 +51,11 @@ class _SLMProblem(object):
         self.Xhost_probe = np.asarray(X[:1], dtype=float)
         hyp0 = basis.params_values()
         self.plan = basis._plan(self.d, hyp0)
-        if self.plan.next and self.plan.ktot and self.d <= 32:
-            # concatenated bases: the fused value pass carries the Linear / Bias
-            # columns as pseudo-frequency slots scaled by max |X[:, i]| of the job
+        self.engine = config.engine_code()
+        if (self.engine in eng._FUSED16 and self.plan.next and self.plan.ktot
+                and self.d <= 32):
+            # round-1 fused kind::f16 kernel only: Linear / Bias columns ride as
+            # pseudo-frequency slots scaled by max |X[:, i]| of the job
             amax = (self.Xd.abs().amax(dim=0) if self.Xd.shape[0]
                     else t.zeros(self.d, device=self.Xd.device)).double()
             if self.world > 1:
@@ -67,16 +69,24 @@ class _SLMProblem(object):
         self.R = self.rflat[:nfl - 1].view(self.plan.d, max(self.plan.ktot, 1))
         self.sqerr = self.rflat[nfl - 1:]
         self.yy = None
-        self.engine = config.engine_code()
 
     def uses_tcgen05(self):
-        """True when RR_ENGINE_AUTO / tcgen05 routes this problem's value pass
-        to the fused tensor-core kernel (mirrors pick_engine in rr_slm.cu)."""
+        """True when this problem's value pass runs on the tensor cores
+        (mirrors pick_engine in rr_slm.cu)."""
         from . import _cabi
-        if self.engine == _cabi.RR_ENGINE_SIMT or not self.plan.tcgen05_ok():
+        if self.engine == _cabi.RR_ENGINE_SIMT:
+            return False
+        if self.engine in eng._FUSED16:
+            return True
+        if not self.plan.tcgen05_ok():
             return False
         return (self.engine != _cabi.RR_ENGINE_AUTO
-                or self.Xd.shape[0] >= eng.TC_AUTO_MIN_ROWS)
+                or self.Xd.shape[0] >= eng.auto_min_rows())
+
+    def needs_polish(self):
+        """Only the round-1 fused kind::f16 value pass has a noise floor that
+        an ill-conditioned posterior can amplify past 1e-4 (config.POLISH_COND)."""
+        return self.engine in eng._FUSED16
 
     def polish(self, var, regs, hypers):
         """Posterior at the given hyper-parameters from the SIMT engine's
@@ -280,14 +290,13 @@ class StandardLinearModel(BaseEstimator, RegressorMixin):
         return -ELBO, [-dvar, dL, dhypers]
 
     def _sync_posterior(self, prob=None):
-        """Materialise the cached best posterior as numpy attributes.  If it came
-        from the fused tcgen05 value pass at an ill-conditioned point
-        (config.POLISH_COND), recompute it once with the SIMT engine: the fast
-        engine's log-ML and gradients hold 1e-4 everywhere, its posterior
-        moments only where the conditioning is moderate."""
+        """Materialise the cached best posterior as numpy attributes.  (If it came
+        from the round-1 fused kind::f16 value pass at an ill-conditioned point
+        it is recomputed once with the SIMT engine; the default fixed-point
+        engine needs no such step)"""
         best = getattr(self, "_best_point", None)
         if (prob is not None and best is not None and config.POLISH_COND > 0
-                and best[3] > config.POLISH_COND and prob.uses_tcgen05()):
+                and best[3] > config.POLISH_COND and prob.needs_polish()):
             post = prob.polish(best[0], best[1], best[2])
             self._m_dev, self._post = post.m, post
             self._best_point = best[:3] + (0.0,)
