@@ -669,7 +669,7 @@ extern "C" int rr_tcgen05_i8_selftest(int32_t kblocks, int64_t* mismatches) {
   const int D = s.D, Fp = s.Fp;
   const size_t img_bytes = (size_t)3 * kblocks * Fp * 64;
   const size_t t_bytes = (size_t)(D + 1) * s.ldT * sizeof(double);
-  int8_t* hd = (int8_t*)malloc((size_t)3 * N * Fp);        // [plane][row n][feature f]
+  int8_t* hd = (int8_t*)malloc((size_t)3 * N * Fp);        // [plane][feature f][row n]
   uint8_t* himg = (uint8_t*)calloc(img_bytes, 1);
   double* hT = (double*)malloc(t_bytes);
   uint8_t* dimg = nullptr;
@@ -685,7 +685,7 @@ extern "C" int rr_tcgen05_i8_selftest(int32_t kblocks, int64_t* mismatches) {
     for (int64_t n = 0; n < N; ++n)
       for (int f = 0; f < Fp; ++f) {
         const int8_t v = (int8_t)((f <= D) ? rnd() : 0);
-        hd[((size_t)j * N + n) * Fp + f] = v;
+        hd[((size_t)j * Fp + f) * N + n] = v;
         const int64_t kb = n / S3_KB;
         const uint32_t r = (uint32_t)(n % S3_KB);
         himg[(((size_t)kb * 3 + j) * Fp + f) * 64 + (((r >> 4) ^ (((uint32_t)f >> 1) & 3u)) << 4) + (r & 15u)] =
@@ -706,13 +706,17 @@ extern "C" int rr_tcgen05_i8_selftest(int32_t kblocks, int64_t* mismatches) {
       for (int fa = 0; fa < D; ++fa) {
         long long ref = 0;
         if (fb >= fa) {
+          const int8_t *a0 = hd + ((size_t)0 * Fp + fa) * N, *a1 = hd + ((size_t)1 * Fp + fa) * N,
+                       *a2 = hd + ((size_t)2 * Fp + fa) * N;
+          const int8_t *b0 = hd + ((size_t)0 * Fp + fb) * N, *b1 = hd + ((size_t)1 * Fp + fb) * N,
+                       *b2 = hd + ((size_t)2 * Fp + fb) * N;
+          long long s00 = 0, s01 = 0, s11 = 0;
           for (int64_t n = 0; n < N; ++n) {
-            const long long a0 = hd[((size_t)0 * N + n) * Fp + fa], a1 = hd[((size_t)1 * N + n) * Fp + fa],
-                            a2 = hd[((size_t)2 * N + n) * Fp + fa];
-            const long long b0 = hd[((size_t)0 * N + n) * Fp + fb], b1 = hd[((size_t)1 * N + n) * Fp + fb],
-                            b2 = hd[((size_t)2 * N + n) * Fp + fb];
-            ref += a0 * b0 * 65536ll + (a0 * b1 + a1 * b0) * 256ll + (a1 * b1 + a0 * b2 + a2 * b0);
+            s00 += (int)a0[n] * (int)b0[n];
+            s01 += (int)a0[n] * (int)b1[n] + (int)a1[n] * (int)b0[n];
+            s11 += (int)a1[n] * (int)b1[n] + (int)a0[n] * (int)b2[n] + (int)a2[n] * (int)b0[n];
           }
+          ref = s00 * 65536ll + s01 * 256ll + s11;
         }
         if (hT[(size_t)fb * s.ldT + fa] != (double)ref) ++bad;
       }

@@ -12,8 +12,9 @@ def smse(y_true, y_pred):
 
 
 def mll(y_true, y_pred, y_var):
-    """Mean Gaussian predictive log-likelihood."""
-    return np.mean(norm.logpdf(y_true, loc=y_pred, scale=np.sqrt(y_var)))
+    """Mean log LOSS under a Gaussian predictive distribution: the mean
+    NEGATIVE log-likelihood, lower is better (revrand/metrics.py:38-66)."""
+    return -np.mean(norm.logpdf(y_true, loc=y_pred, scale=np.sqrt(y_var)))
 
 
 def msll(y_true, y_pred, y_var, y_train):

@@ -38,7 +38,9 @@ def test_library_exports_every_declared_symbol():
     assert ctypes.sizeof(_cabi.RRPlan) == 16 + 8 * ctypes.sizeof(ctypes.c_void_p)
     # shape queries need no GPU
     assert lib.rr_tcgen05_supported(21, 2048, 0, 4096) == 1
-    assert lib.rr_tcgen05_supported(21, 2048, 22, 4118) == 0
+    assert lib.rr_tcgen05_supported(21, 2048, 22, 4118) == 1   # affine columns ride along
+    assert lib.rr_tcgen05_supported(21, 2048, 22, 4000) == 0   # inconsistent plan
+    assert lib.rr_engine_auto_min_rows() > 0
     assert lib.rr_workspace_bytes(_cabi.RR_OP_GRADPASS, 10 ** 6, 21, 2048, 4096,
                                   0, 0, _cabi.RR_ENGINE_AUTO) > 0
 
@@ -330,3 +332,25 @@ def test_bench_reference_arm_prints_the_contract_line():
     assert line["impl"] == "reference" and line["value"] > 0
     assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
     assert line["e2e"]["h2d_bytes_per_step"] == 0
+
+
+def test_metrics_match_reference_docstring_examples():
+    """revrand/metrics.py:25-31, 58-64, 91-95, 125-129 (doctest examples) plus
+    closed-form values: mll is a LOSS (negative log-likelihood)."""
+    from scipy.stats import norm
+    from revrand_b200 import metrics
+    rs = np.random.RandomState(3)
+    y = rs.randn(100)
+    assert metrics.smse(y, y) == 0.0
+    assert metrics.smse(y, rs.randn(100)) >= 1.0
+    mean_prob = -norm.logpdf(1e-2, loc=0)
+    assert metrics.mll(y, y, 1) <= mean_prob
+    assert metrics.mll(y, rs.randn(100), 1) >= mean_prob
+    np.testing.assert_allclose(metrics.mll(y, y, 1.0), 0.5 * np.log(2 * np.pi))
+    assert metrics.msll(y, y, 1, y) < 0
+    assert metrics.msll(y, rs.randn(100), 1, y) >= 0
+    np.testing.assert_allclose(
+        metrics.msll(y, y, 1.0, y),
+        metrics.mll(y, y, 1.0) + np.mean(norm.logpdf(y, y.mean(), y.std())))
+    assert metrics.lins_ccc(y, y) > 0.99
+    assert metrics.lins_ccc(y, np.zeros_like(y)) < 0.01
