@@ -285,7 +285,8 @@ def slm_elbo(X, y, var, regs, blocks):
             "TrGC": TrGC, "logdetiC": logdetiC}
 
 
-def slm_elbo_chunked(X, y, var, regs, blocks, chunk=20000, grads=True):
+def slm_elbo_chunked(X, y, var, regs, blocks, chunk=20000, grads=True,
+                     budget=None):
     """Row-chunked sufficient-statistics restatement of ``_elbo``.
 
     Pass 1 accumulates G, Phi^T y over row chunks (slm.py:145-146,157);
@@ -294,24 +295,40 @@ def slm_elbo_chunked(X, y, var, regs, blocks, chunk=20000, grads=True):
     chunk by chunk, which are sums over rows.  Equal to :func:`slm_elbo` up
     to summation order; used where Phi does not fit in memory and as the
     timed CPU baseline in ``bench.py``.
+
+    ``budget=(seconds_pass1, seconds_pass2)`` is for TIMING runs only: each
+    pass stops taking new chunks once its budget is spent, and the returned
+    ``"timing"`` entry says how many rows each pass covered and how long it
+    and the solve took (the numerical results then describe the rows seen).
     """
+    import time
     N = X.shape[0]
     D = concat_features(X[:1], blocks).shape[1]
     G = np.zeros((D, D))
     p = np.zeros(D)
+    t0 = time.perf_counter()
+    rows1 = 0
     for s in range(0, N, chunk):
         Phi = concat_features(X[s:s + chunk], blocks)
         G += Phi.T.dot(Phi)
         p += Phi.T.dot(y[s:s + chunk])
+        rows1 = min(N, s + chunk)
+        if budget is not None and time.perf_counter() - t0 > budget[0]:
+            break
+    t_pass1 = time.perf_counter() - t0
+    t0 = time.perf_counter()
     Ld, slices = regularizer_diagonal(X[:1], blocks, regs)
     iL = 1.0 / Ld
     iC = np.diag(iL) + G / var
     C, logdetiC = solve_posdef(iC, np.eye(D))
     m = C.dot(p) / var
     TrGC = (G * C).sum()
+    t_solve = time.perf_counter() - t0
     sqErr = 0.0
     dh = None
-    for s in range(0, N, chunk):
+    t0 = time.perf_counter()
+    rows2 = 0
+    for s in range(0, rows1, chunk):
         Xc, yc = X[s:s + chunk], y[s:s + chunk]
         Phi = concat_features(Xc, blocks)
         Err = yc - Phi.dot(m)
@@ -322,15 +339,23 @@ def slm_elbo_chunked(X, y, var, regs, blocks, chunk=20000, grads=True):
                          - (dPhi.T.dot(Phi) * C).sum()) / var
             part = [_apply_grad(dhyp, g) for g in concat_grads(Xc, blocks)]
             dh = part if dh is None else [a + b for a, b in zip(dh, part)]
-    ELBO = -0.5 * (N * np.log(2 * np.pi * var) + sqErr / var + TrGC / var
+        rows2 = min(rows1, s + chunk)
+        if budget is not None and time.perf_counter() - t0 > budget[1]:
+            break
+    t_pass2 = time.perf_counter() - t0
+    Nn = rows1
+    ELBO = -0.5 * (Nn * np.log(2 * np.pi * var) + sqErr / var + TrGC / var
                    + ((m ** 2 + C.diagonal()) * iL).sum() + logdetiC
                    + np.log(Ld).sum() - D)
-    dvar = 0.5 * (-N + (sqErr + TrGC) / var) / var
+    dvar = 0.5 * (-Nn + (sqErr + TrGC) / var) / var
     dreg = [-0.5 * (((m[s] ** 2 + C[s, s].diagonal()) * iL[s] ** 2).sum()
                     - iL[s].sum()) for s in slices]
     return {"neg_elbo": -ELBO, "dvar": -dvar, "dreg": dreg,
             "dhyp": dh if dh is not None else [], "m": m, "C": C, "G": G,
-            "Phiy": p, "sqErr": sqErr, "TrGC": TrGC, "logdetiC": logdetiC}
+            "Phiy": p, "sqErr": sqErr, "TrGC": TrGC, "logdetiC": logdetiC,
+            "timing": {"rows_pass1": rows1, "rows_pass2": rows2,
+                       "t_pass1": t_pass1, "t_solve": t_solve,
+                       "t_pass2": t_pass2}}
 
 
 def slm_predict_moments(Xs, blocks, m, C, var):

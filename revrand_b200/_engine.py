@@ -680,6 +680,44 @@ def allreduce_sum_(flat):
     return flat
 
 
+def _coll_device():
+    """Device for small collective payloads: CUDA under NCCL, CPU under gloo."""
+    t = torch()
+    if t.distributed.get_backend() == "nccl":
+        return t.device("cuda", t.cuda.current_device())
+    return t.device("cpu")
+
+
+def sync_random_state(random_state):
+    """Row-sharded jobs: every rank must draw the same x0 / random starts (and
+    the same basis weights when ``random_state`` seeds them), or the ranks'
+    optimiser iterates diverge while they all receive rank 0's objective.  Copies
+    rank 0's generator state to every rank; rank 0's own stream is untouched."""
+    t = torch()
+    rank, ws = world()
+    if ws == 1:
+        return random_state
+    obj = [random_state.get_state() if rank == 0 else None]
+    t.distributed.broadcast_object_list(obj, src=0, device=_coll_device())
+    random_state.set_state(obj[0])
+    return random_state
+
+
+def assert_same_on_all_ranks(value, what):
+    """Raise on every rank if a float64 summary differs between ranks."""
+    t = torch()
+    if world()[1] == 1:
+        return
+    v = t.tensor([float(value), -float(value)], dtype=t.float64, device=_coll_device())
+    t.distributed.all_reduce(v, op=t.distributed.ReduceOp.MAX)
+    hi, lo = v[0].item(), -v[1].item()
+    if hi != lo:
+        raise RevrandB200Error(
+            "%s differs between ranks (%r .. %r): with row sharding every rank "
+            "must hold the same basis (seed `random_state`, or build the basis "
+            "once and broadcast it)" % (what, lo, hi))
+
+
 def shard_rows(N, rank, world_size):
     """Contiguous row range [lo, hi) owned by ``rank``."""
     base, rem = divmod(int(N), int(world_size))

@@ -35,3 +35,8 @@ GLM_HOST_RNG = os.environ.get("REVRAND_B200_HOST_RNG", "0") == "1"
 # reported posterior is recomputed once with the SIMT engine.  The default engine
 # (24-bit fixed point on kind::i8) meets 1e-4 everywhere and never polishes.
 POLISH_COND = float(os.environ.get("REVRAND_B200_POLISH_COND", "1e3"))
+
+# Direct ``StandardLinearModel._elbo(X, y, ...)`` calls keep X and y resident on
+# the device between calls while the same host arrays are passed (identity plus
+# a content fingerprint).  False: upload the rows on every call.
+CACHE_DEVICE_DATA = os.environ.get("REVRAND_B200_CACHE_DATA", "1") != "0"

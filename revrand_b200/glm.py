@@ -39,6 +39,31 @@ COVRND = gamma(a=2, scale=0.5)  # initial distribution of mixture variances
 LOGITER = 500                   # iterations between ELBO log lines
 
 
+_DEVICE_LIKELIHOODS = None
+
+
+def _check_device_likelihood(likelihood, lpars, largs):
+    """The SVI step evaluates the likelihood ON THE DEVICE, selected by
+    ``_lik_id``, with at most one scalar parameter and one per-row argument.
+    A subclass that overrides loglike / df / dp, or a likelihood with more
+    parameters, would silently train on the wrong function (the reference calls
+    the object's own methods, likelihoods.py:36-44): refuse instead."""
+    global _DEVICE_LIKELIHOODS
+    if _DEVICE_LIKELIHOODS is None:
+        from . import likelihoods as lk
+        _DEVICE_LIKELIHOODS = (lk.Gaussian, lk.Bernoulli, lk.Binomial, lk.Poisson)
+    if type(likelihood) not in _DEVICE_LIKELIHOODS:
+        raise NotImplementedError(
+            "GeneralizedLinearModel runs its likelihood on the device and knows "
+            "Gaussian, Bernoulli, Binomial and Poisson; %s is not one of them "
+            "(subclasses are not dispatched to their overridden methods)"
+            % type(likelihood).__name__)
+    if sum(1 for p in lpars if np.size(p) > 0) > 1 or any(np.size(p) > 1 for p in lpars):
+        raise NotImplementedError("device likelihoods take at most one scalar parameter")
+    if len(largs) > 1:
+        raise NotImplementedError("device likelihoods take at most one per-row argument")
+
+
 def _aslist(a):
     return a if isinstance(a, list) else [a]
 
@@ -178,6 +203,7 @@ class GeneralizedLinearModel(BaseEstimator, RegressorMixin):
             hyps = []
         plan = self._get_plan(Xd.shape[1], hyps)
         lpl = _aslist(lpars)
+        _check_device_likelihood(self.likelihood, lpl, largs)
         has_lpar = len(lpl) > 0 and np.size(lpl[0]) > 0
         lik_param = float(lpl[0]) if has_lpar else 1.0
 

@@ -51,6 +51,9 @@ class _SLMProblem(object):
         self.Xhost_probe = np.asarray(X[:1], dtype=float)
         hyp0 = basis.params_values()
         self.plan = basis._plan(self.d, hyp0)
+        if self.world > 1:   # the all-reduced Gram must not mix different feature maps
+            eng.assert_same_on_all_ranks(np.abs(self.plan.Wfull).sum(),
+                                         "the basis frequency matrix W")
         self.engine = config.engine_code()
         if (self.engine in eng._FUSED16 and self.plan.next and self.plan.ktot
                 and self.d <= 32):
@@ -69,6 +72,22 @@ class _SLMProblem(object):
         self.R = self.rflat[:nfl - 1].view(self.plan.d, max(self.plan.ktot, 1))
         self.sqerr = self.rflat[nfl - 1:]
         self.yy = None
+
+    def upload(self, X, y):
+        """Replace the device-resident rows by new host data of the same shape
+        (one H2D copy each, into the existing buffers)."""
+        t = eng.torch()
+        lo, hi = eng.shard_rows(self.N_total, self.rank, self.world)
+
+        def host(a):
+            a = np.ascontiguousarray(a[lo:hi])
+            if a.dtype not in (np.float32, np.float64):
+                a = a.astype(np.float64)
+            return t.from_numpy(a)
+        self.Xd.copy_(host(X), non_blocking=True)
+        self.yd.copy_(host(y), non_blocking=True)
+        self.yy = None
+        self.Xhost_probe = np.asarray(X[:1], dtype=float)
 
     def uses_tcgen05(self):
         """True when this problem's value pass runs on the tensor cores
@@ -188,6 +207,8 @@ class StandardLinearModel(BaseEstimator, RegressorMixin):
         self.obj_ = -np.inf
         self._problem = _SLMProblem(self.basis, X, y)
         self._problem_key = None
+        # ranks of a row-sharded job share rank 0's random starts (no-op otherwise)
+        eng.sync_random_state(self.random_)
         params = [self.var, self.basis.regularizer, self.basis.params]
         nmin = structured_minimizer(logtrick_minimizer(minimize))
 
@@ -210,17 +231,42 @@ class StandardLinearModel(BaseEstimator, RegressorMixin):
         self._problem = None
         return self
 
+    @staticmethod
+    def _fingerprint(X, y):
+        """Identity + cheap content fingerprint of host data: the array objects'
+        addresses and shapes, plus a strided sample of 64 values of each.  Guards
+        the device-resident copy against in-place edits and recycled ids."""
+        def sample(a):
+            a = np.asarray(a)
+            flat = a.reshape(-1)
+            if flat.size == 0:
+                return ()
+            idx = np.linspace(0, flat.size - 1, num=min(64, flat.size)).astype(np.int64)
+            return tuple(np.asarray(flat[idx], dtype=np.float64).tolist())
+        return (id(X), id(y), np.shape(X), np.shape(y),
+                getattr(X, "ctypes", None) and X.ctypes.data,
+                sample(X), sample(y))
+
     def _get_problem(self, X, y):
+        """Device-resident problem for (X, y).  Inside ``fit`` it is built once;
+        for direct ``_elbo`` calls it is kept between calls while the same data
+        is passed (config.CACHE_DEVICE_DATA), otherwise the rows are uploaded
+        again into the existing buffers."""
         prob = getattr(self, "_problem", None)
         if prob is not None:
             return prob
-        key = (id(X), id(y), np.shape(X))
-        if getattr(self, "_problem_key", None) != key or \
-                getattr(self, "_cached_problem", None) is None:
-            self._cached_problem = _SLMProblem(self.basis, np.asarray(X, float),
-                                               np.asarray(y, float))
-            self._problem_key = key
-        return self._cached_problem
+        cached = getattr(self, "_cached_problem", None)
+        key = self._fingerprint(X, y) if config.CACHE_DEVICE_DATA else None
+        if cached is not None and key is not None and \
+                getattr(self, "_problem_key", None) == key:
+            return cached
+        if cached is not None and cached.basis is self.basis and \
+                (cached.N_total, cached.d) == tuple(np.shape(X)):
+            cached.upload(X, y)
+        else:
+            self._cached_problem = cached = _SLMProblem(self.basis, X, y)
+        self._problem_key = key
+        return cached
 
     def _elbo(self, X, y, var, reg, hypers, want_grad=True):
         """(-ELBO, [-dvar, dreg, dhypers]) at the given hyper-parameters; same
@@ -295,8 +341,10 @@ class StandardLinearModel(BaseEstimator, RegressorMixin):
         it is recomputed once with the SIMT engine; the default fixed-point
         engine needs no such step)"""
         best = getattr(self, "_best_point", None)
+        # (the Cholesky-diagonal conditioning estimate is only a lower bound on
+        # cond(iC), so the legacy engine is polished whenever polishing is on)
         if (prob is not None and best is not None and config.POLISH_COND > 0
-                and best[3] > config.POLISH_COND and prob.needs_polish()):
+                and prob.needs_polish()):
             post = prob.polish(best[0], best[1], best[2])
             self._m_dev, self._post = post.m, post
             self._best_point = best[:3] + (0.0,)

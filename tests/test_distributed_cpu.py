@@ -56,6 +56,18 @@ def _worker(rank, world, port, ret):
         post2 = _engine.solve_posterior(torch.from_numpy(A), torch.from_numpy(Pf.T.dot(y)),
                                         0.3, torch.from_numpy(lam))
         ok = ok and np.allclose(post2.C.numpy(), Cref, rtol=1e-9, atol=1e-12)
+        # ranks of a sharded fit share rank 0's random starts, and a basis that
+        # differs between ranks is refused
+        mine = np.random.RandomState(100 + rank)
+        first_of_rank0 = np.random.RandomState(100).randn(3)
+        _engine.sync_random_state(mine)
+        ok = ok and np.array_equal(mine.randn(3), first_of_rank0)
+        _engine.assert_same_on_all_ranks(np.abs(W).sum(), "W")
+        try:
+            _engine.assert_same_on_all_ranks(np.abs(W).sum() + rank, "W")
+            ok = False
+        except Exception as e:
+            ok = ok and "differs between ranks" in str(e)
         ret[rank] = bool(ok)
     finally:
         dist.destroy_process_group()

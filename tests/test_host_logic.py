@@ -354,3 +354,35 @@ def test_metrics_match_reference_docstring_examples():
         metrics.mll(y, y, 1.0) + np.mean(norm.logpdf(y, y.mean(), y.std())))
     assert metrics.lins_ccc(y, y) > 0.99
     assert metrics.lins_ccc(y, np.zeros_like(y)) < 0.01
+
+
+def test_glm_refuses_likelihoods_the_device_kernel_does_not_know():
+    from revrand_b200 import glm, likelihoods as lk
+
+    class Tweaked(lk.Gaussian):
+        def df(self, y, f, var):
+            return 2 * super().df(y, f, var)
+
+    with pytest.raises(NotImplementedError):
+        glm._check_device_likelihood(Tweaked(), [1.0], ())
+    with pytest.raises(NotImplementedError):
+        glm._check_device_likelihood(lk.Gaussian(), [1.0, 2.0], ())
+    with pytest.raises(NotImplementedError):
+        glm._check_device_likelihood(lk.Binomial(), [], (np.ones(3), np.ones(3)))
+    glm._check_device_likelihood(lk.Binomial(), [], (np.ones(3),))
+    glm._check_device_likelihood(lk.Gaussian(), [0.5], ())
+
+
+def test_device_data_cache_key_sees_in_place_edits():
+    """The device-resident copy behind direct ``_elbo`` calls is keyed on array
+    identity AND a content fingerprint."""
+    from revrand_b200.slm import StandardLinearModel
+    X = np.random.RandomState(0).randn(500, 3)
+    y = np.random.RandomState(1).randn(500)
+    k0 = StandardLinearModel._fingerprint(X, y)
+    assert k0 == StandardLinearModel._fingerprint(X, y)
+    X[0, 0] += 1.0
+    assert k0 != StandardLinearModel._fingerprint(X, y)
+    X[0, 0] -= 1.0
+    y[-1] = 7.0
+    assert k0 != StandardLinearModel._fingerprint(X, y)
