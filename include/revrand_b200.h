@@ -79,6 +79,9 @@ typedef struct rr_plan {
    *   2: constant slot -- the single feature amp[k] in col_cos[k]; col_sin[k] = -1
    * A plan with kind != NULL must have next == 0 (the affine columns ARE slots). */
   const uint8_t* kind;  /* (ktot) or NULL                                    */
+  /* Optional (NULL = all 1): integer power of extra column j, i.e. the column is
+   * X[n, ext_src[j]] ^ ext_pow[j] -- PolynomialBasis (basis_functions.py:537-566). */
+  const int32_t* ext_pow; /* (next) or NULL                                   */
 } rr_plan;
 
 /* Likelihood ids for rr_glm_step; revrand/likelihoods.py:18-545. */
@@ -151,6 +154,31 @@ int rr_fastfood_features(const float* Xs, int64_t N, int32_t d, int32_t d2,
                          int32_t k, const float* B, const float* G,
                          const int32_t* PI, const float* S, float* Phi,
                          float* VX_out, void* stream);
+
+/*
+ * Centre-based bases (basis_functions.py:616-815).  C is (M, d) centres, lenscale
+ * has n_ls entries (1 or d).
+ *   kind 0, RadialBasis   :665-688   Phi = exp(-sum_i ((x_i - c_i) / (2 l_i^2))^2)
+ *                         :690-722   dPhi_i = Phi (x_i - c_i)^2 / l_i^6
+ *   kind 1, SigmoidalBasis:770-790   Phi = expit(sqrt(sum_i ((x_i - c_i) / l_i)^2))
+ *                         :792-815   dPhi_i = -|x_i - c_i| / l_i^2 Phi (1 - Phi)
+ * Phi is (N, M); dPhi (optional) is (N, M) for n_ls == 1 -- where, as in the
+ * reference, only input dimension 0 contributes -- else (N, M, d).
+ */
+int rr_centre_features(const float* X, int64_t N, int32_t d, const float* C,
+                       int32_t M, const float* lenscale, int32_t n_ls,
+                       int32_t kind, float* Phi, float* dPhi, void* stream);
+
+/*
+ * Gradients of one Gaussian spectral-mixture component (FastFoodGM.grad,
+ * basis_functions.py:1474-1527) from the dense image V (d, n) of its FastFood
+ * projection: phases p = x (V / l), q = x . mean; outputs (N, 4n, d) (or (N, 4n)
+ * for d == 1) wrt the means and wrt the lengthscales, block order
+ * [cos(p+q) | sin(p+q) | cos(p-q) | sin(p-q)] / sqrt(2n).
+ */
+int rr_gm_grad(const float* X, int64_t N, int32_t d, const float* V, int32_t n,
+               const float* mean, const float* lenscale, float* dmean,
+               float* dlen, void* stream);
 
 /*
  * Value pass of StandardLinearModel._elbo: G += Phi^T Phi, p += Phi^T y,

@@ -127,6 +127,96 @@ def fastfood_feature_grads(X, B, G, PI, S, lenscale):
     return np.dstack(out) if len(ls) != 1 else out[0]
 
 
+def polynomial_features(X, order, include_bias=True):
+    """[1, X^1 .. X^order] with the powers of one input column adjacent.
+
+    revrand/basis_functions.py:537-566 (``PolynomialBasis.transform``).
+    """
+    N, d = X.shape
+    Phi = (X[:, :, None] ** (np.arange(order) + 1)).reshape(N, d * order)
+    if include_bias:
+        Phi = np.hstack((np.ones((N, 1)), Phi))
+    return Phi
+
+
+def radial_features(X, C, lenscale):
+    """exp(-|| (x - c) / (2 l^2) ||^2): the reference divides by ``2 l^2``
+    BEFORE squaring (revrand/basis_functions.py:665-688), reproduced as is."""
+    ls = _as_lenscale(lenscale, X.shape[1])
+    den = 2.0 * ls ** 2
+    diff = X[:, None, :] / den - C[None, :, :] / den
+    return np.exp(-(diff ** 2).sum(axis=2))
+
+
+def radial_feature_grads(X, C, lenscale):
+    """revrand/basis_functions.py:690-722: Phi * (x_i - c_i)^2 / l_i^6 per
+    lengthscale; a scalar lengthscale only sees input dimension 0."""
+    ls = _as_lenscale(lenscale, X.shape[1])
+    Phi = radial_features(X, C, lenscale)
+    out = []
+    for i, l in enumerate(ls):
+        ldist = (X[:, [i]] / l ** 3 - C[:, [i]].T / l ** 3) ** 2
+        out.append(Phi * ldist)
+    return np.dstack(out) if len(ls) != 1 else out[0]
+
+
+def sigmoidal_features(X, C, lenscale):
+    """expit(|| (x - c) / l ||); revrand/basis_functions.py:770-790."""
+    ls = _as_lenscale(lenscale, X.shape[1])
+    diff = X[:, None, :] / ls - C[None, :, :] / ls
+    return expit(np.sqrt((diff ** 2).sum(axis=2)))
+
+
+def sigmoidal_feature_grads(X, C, lenscale):
+    """revrand/basis_functions.py:792-815: -|x_i - c_i| / l_i^2 Phi (1 - Phi)."""
+    ls = _as_lenscale(lenscale, X.shape[1])
+    Phi = sigmoidal_features(X, C, lenscale)
+    out = []
+    for i, l in enumerate(ls):
+        ldist = np.abs(X[:, [i]] / l ** 2 - C[:, [i]].T / l ** 2)
+        out.append(-ldist * Phi * (1 - Phi))
+    return np.dstack(out) if len(ls) != 1 else out[0]
+
+
+def fastfood_gm_features(X, B, G, PI, S, mean, lenscale):
+    """One Gaussian spectral-mixture component: [cos(VX + Xm) | sin(VX + Xm) |
+    cos(VX - Xm) | sin(VX - Xm)] / sqrt(2 n).
+
+    revrand/basis_functions.py:1458-1472 (``FastFoodGM.transform``).
+    """
+    VX = fastfood_vx(X / lenscale, B, G, PI, S)
+    mX = X.dot(mean)[:, None]
+    n = B.size
+    return np.hstack((np.cos(VX + mX), np.sin(VX + mX),
+                      np.cos(VX - mX), np.sin(VX - mX))) / math.sqrt(2 * n)
+
+
+def fastfood_gm_feature_grads(X, B, G, PI, S, mean, lenscale):
+    """(d Phi / d mean, d Phi / d lenscale), each (N, 4n, d) (2-D for d = 1).
+
+    revrand/basis_functions.py:1474-1527 (``FastFoodGM.grad``).
+    """
+    d = X.shape[1]
+    VX = fastfood_vx(X / lenscale, B, G, PI, S)
+    mX = X.dot(mean)[:, None]
+    sp, sm = -np.sin(VX + mX), -np.sin(VX - mX)
+    cp, cm = np.cos(VX + mX), np.cos(VX - mX)
+    n = B.size
+    dmean, dlen = [], []
+    for i, l in enumerate(np.atleast_1d(lenscale)):
+        dmX = X[:, [i]]
+        dmean.append(np.hstack((dmX * sp, dmX * cp, -dmX * sm, -dmX * cm))
+                     / math.sqrt(2 * n))
+        ind = np.zeros(d)
+        ind[i] = 1.0 / l ** 2
+        dVX = -fastfood_vx(X * ind, B, G, PI, S)
+        dlen.append(np.hstack((dVX * sp, dVX * cp, dVX * sm, dVX * cm))
+                    / math.sqrt(2 * n))
+    if d != 1:
+        return np.dstack(dmean), np.dstack(dlen)
+    return dmean[0], dlen[0]
+
+
 def linear_features(X, onescol=True):
     """revrand/basis_functions.py:468-485."""
     return np.hstack((np.ones((len(X), 1)), X)) if onescol else X

@@ -32,6 +32,7 @@ class RRPlan(C.Structure):
         ("ext_src", C.c_void_p), ("ext_val", C.c_void_p),
         ("ext_col", C.c_void_p),
         ("kind", C.c_void_p),
+        ("ext_pow", C.c_void_p),
     ]
 
 
@@ -49,6 +50,8 @@ SIGNATURES = {
     "rr_trig_grad": (C.c_int, [_P, _I64, _I32, _P, _I32, _P, _I32, _I32, _P, _P]),
     "rr_fastfood_features": (C.c_int, [_P, _I64, _I32, _I32, _I32, _P, _P, _P,
                                        _P, _P, _P, _P]),
+    "rr_centre_features": (C.c_int, [_P, _I64, _I32, _P, _I32, _P, _I32, _I32, _P, _P, _P]),
+    "rr_gm_grad": (C.c_int, [_P, _I64, _I32, _P, _I32, _P, _P, _P, _P, _P]),
     "rr_context_create": (C.c_int, [C.POINTER(_P)]),
     "rr_context_destroy": (C.c_int, [_P]),
     "rr_engine_auto_min_rows": (_I64, []),

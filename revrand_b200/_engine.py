@@ -117,21 +117,26 @@ class TrigBlock(object):
     """
     kind = "trig"
 
-    def __init__(self, W, lenscale, cols=None):
+    def __init__(self, W, lenscale, cols=None, amp=None):
         self.W = np.asarray(W, dtype=np.float64)
         self.cols = None if cols is None else np.asarray(cols, dtype=np.int64)
         self.lenscale = np.atleast_1d(np.asarray(lenscale, dtype=np.float64))
         self.K = self.W.shape[1]
         self.width = 2 * self.K
+        # feature amplitude; None = 1 / sqrt(K) (basis_functions.py:864)
+        self.amp = amp
 
 
 class ExtraBlock(object):
-    """Affine columns: ``src[j] >= 0`` copies X[:, src[j]], else constant."""
+    """Affine columns: ``src[j] >= 0`` copies X[:, src[j]] (raised to the integer
+    power ``pow[j]`` when given), else the constant ``val[j]``."""
     kind = "extra"
 
-    def __init__(self, src, val):
+    def __init__(self, src, val, pow=None):
         self.src = np.asarray(src, dtype=np.int32)
         self.val = np.asarray(val, dtype=np.float32)
+        self.pow = (np.ones(len(self.src), dtype=np.int32) if pow is None
+                    else np.asarray(pow, dtype=np.int32))
         self.width = len(self.src)
 
 
@@ -146,7 +151,7 @@ class FeaturePlan(object):
         self.ktot = int(sum(b.K for b in self.trig))
         self.D = int(sum(b.width for b in self.blocks))
         col_cos, col_sin, amp = [], [], []
-        ext_src, ext_val, ext_col = [], [], []
+        ext_src, ext_val, ext_col, ext_pow = [], [], [], []
         self.block_offsets = []
         self.freq_offsets = []
         off = 0
@@ -157,11 +162,13 @@ class FeaturePlan(object):
                 self.freq_offsets.append(koff)
                 col_cos.append(off + np.arange(b.K))
                 col_sin.append(off + b.K + np.arange(b.K))
-                amp.append(np.full(b.K, 1.0 / math.sqrt(b.K)))
+                amp.append(np.full(b.K, 1.0 / math.sqrt(b.K) if b.amp is None
+                                   else float(b.amp)))
                 koff += b.K
             else:
                 ext_src.append(b.src)
                 ext_val.append(b.val)
+                ext_pow.append(b.pow)
                 ext_col.append(off + np.arange(b.width))
             off += b.width
         self.next = int(sum(len(s) for s in ext_src))
@@ -176,6 +183,8 @@ class FeaturePlan(object):
         self._ext_src = to_device(cat(ext_src, np.int32), i32)
         self._ext_val = to_device(cat(ext_val, np.float32), f32)
         self._ext_col = to_device(cat(ext_col, np.int32), i32)
+        pw = cat(ext_pow, np.int32)
+        self._ext_pow = to_device(pw, i32) if (len(pw) and np.any(pw != 1)) else None
         # full-d raw frequency matrix (zeros outside each block's columns)
         Wfull = np.zeros((self.d, max(self.ktot, 1)))
         for b, ko in zip(self.trig, self.freq_offsets):
@@ -199,7 +208,7 @@ class FeaturePlan(object):
         columns are slots of kind 2.  ``col_absmax``: (d,) max |X[:, i]| over
         ALL rows of the job (all ranks)."""
         t = torch()
-        if not (self.next and self.ktot):
+        if not (self.next and self.ktot) or self._ext_pow is not None:
             return
         src, val, col = self._ext_host
         ktx = self.ktot + self.next
@@ -229,7 +238,7 @@ class FeaturePlan(object):
         s.amp = self._amp_x.data_ptr()
         s.col_cos = self._col_cos_x.data_ptr()
         s.col_sin = self._col_sin_x.data_ptr()
-        s.ext_src = s.ext_val = s.ext_col = None
+        s.ext_src = s.ext_val = s.ext_col = s.ext_pow = None
         s.kind = self._kind_x.data_ptr()
         self.struct_tc = s
         self.refresh()
@@ -270,6 +279,7 @@ class FeaturePlan(object):
         s.ext_val = self._ext_val.data_ptr()
         s.ext_col = self._ext_col.data_ptr()
         s.kind = None
+        s.ext_pow = None if self._ext_pow is None else self._ext_pow.data_ptr()
         if self.struct_tc is not None:
             self._Wt_x[:, :self.ktot].copy_(self._Wt)
 
@@ -334,6 +344,41 @@ def trig_grad(Xd, W, lenscale, compat=True):
                            1 if compat else 0, _ptr(out), _stream_ptr()),
           "rr_trig_grad")
     return out
+
+
+def centre_features(Xd, centres, lenscale, kind, want_grad=False):
+    """Radial (kind 0) / sigmoidal (kind 1) basis and, optionally, its
+    lengthscale gradient in the reference's layout."""
+    t = require_cuda()
+    lib = _cabi.load()
+    N, d = Xd.shape
+    M = centres.shape[0]
+    ls = np.atleast_1d(np.asarray(lenscale, dtype=np.float64))
+    P = len(ls)
+    Cd, lsd = to_device(centres), to_device(ls)
+    Phi = t.empty((N, M), dtype=t.float32, device=Xd.device)
+    dPhi = None
+    if want_grad:
+        dPhi = t.empty((N, M) if P == 1 else (N, M, P), dtype=t.float32, device=Xd.device)
+    check(lib.rr_centre_features(_ptr(Xd), N, d, _ptr(Cd), M, _ptr(lsd), P, int(kind),
+                                 _ptr(Phi), _ptr(dPhi), _stream_ptr()),
+          "rr_centre_features")
+    return (Phi, dPhi) if want_grad else Phi
+
+
+def gm_grad(Xd, V, mean, lenscale):
+    """(d Phi / d mean, d Phi / d lenscale) of a FastFoodGM component."""
+    t = require_cuda()
+    lib = _cabi.load()
+    N, d = Xd.shape
+    n = V.shape[1]
+    shape = (N, 4 * n) if d == 1 else (N, 4 * n, d)
+    dm = t.empty(shape, dtype=t.float32, device=Xd.device)
+    dl = t.empty(shape, dtype=t.float32, device=Xd.device)
+    check(lib.rr_gm_grad(_ptr(Xd), N, d, _ptr(to_device(V)), n, _ptr(to_device(mean)),
+                         _ptr(to_device(lenscale)), _ptr(dm), _ptr(dl), _stream_ptr()),
+          "rr_gm_grad")
+    return dm, dl
 
 
 def fastfood_features(Xs_d, B, G, PI, S, want_vx=False):

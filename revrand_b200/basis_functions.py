@@ -23,11 +23,12 @@ import numpy as np
 from scipy.linalg import hadamard as _sylvester
 from scipy.linalg import qr
 from scipy.stats import gamma
+from scipy.stats import norm as norm_dist
 from sklearn.utils import check_random_state
 
 from . import _engine as eng
 from . import config
-from .btypes import Parameter, Positive
+from .btypes import Bound, Parameter, Positive
 
 
 def _issequence(obj):
@@ -54,6 +55,18 @@ def apply_grad(fun, grad):
     if nd == 3:
         return np.array([fun(grad[:, :, i]) for i in range(grad.shape[2])])
     raise ValueError("Only up to 3d gradients allowed!")
+
+
+def require_model_support(basis):
+    """Raise NotImplementedError if ``basis`` (or a member of a concatenation)
+    is a feature map only, i.e. cannot run inside the fused model passes."""
+    for b in getattr(basis, "bases", [basis]):
+        if not getattr(b, "_model_ok", True):
+            raise NotImplementedError(
+                "%s is available as a feature map (transform / grad) only: the "
+                "fused StandardLinearModel / GeneralizedLinearModel passes handle "
+                "trigonometric, linear, bias and polynomial columns"
+                % type(b).__name__)
 
 
 def _as_2d(X):
@@ -194,6 +207,36 @@ class LinearBasis(Basis):
             type(self).__name__, self.onescol, self.regularizer)
 
 
+class PolynomialBasis(Basis):
+    """[1, X^1, ..., X^order], the powers of one input column adjacent
+    (reference :496-576).  Rides inside fused plans as affine columns with an
+    integer power."""
+
+    def __init__(self, order, include_bias=True, regularizer=None, apply_ind=None):
+        if order < 0:
+            raise ValueError("Polynomial order must be positive")
+        self.order = order
+        self.include_bias = include_bias
+        self._set_common(regularizer, apply_ind)
+
+    def _blocks(self, d, hypers):
+        cols = self._cols(d)
+        cols = list(np.arange(d) if cols is None else cols)
+        src, val, pw = [], [], []
+        if self.include_bias:
+            src, val, pw = [-1], [1.0], [1]
+        for c in cols:
+            for p in range(1, self.order + 1):
+                src.append(c)
+                val.append(0.0)
+                pw.append(p)
+        return [eng.ExtraBlock(src, val, pw)]
+
+    def __repr__(self):
+        return "{}(order={}, include_bias={}, regularizer={})".format(
+            type(self).__name__, self.order, self.include_bias, self.regularizer)
+
+
 class _LengthScaleBasis(Basis):
     """Shared lengthscale handling (reference :579-613)."""
 
@@ -222,6 +265,57 @@ class _LengthScaleBasis(Basis):
     def _eff_d(self, d):
         cols = self._cols(d)
         return d if cols is None else len(cols)
+
+
+class RadialBasis(_LengthScaleBasis):
+    """exp(-||(x - c) / (2 l^2)||^2) around fixed centres (reference :616-731;
+    the division by 2 l^2 before squaring is the reference's, :686-688).
+
+    ``transform`` / ``grad`` run on the device; the fused model passes only
+    know trigonometric and affine columns, so a model built on this basis
+    raises NotImplementedError.
+    """
+    _kind = 0
+    _model_ok = False
+
+    def __init__(self, centres, lenscale=Parameter(gamma(1.), Positive()),
+                 regularizer=None, apply_ind=None):
+        centres = np.asarray(centres, dtype=float)
+        self.M, self.d = centres.shape
+        self.C = centres
+        self._init_lenscale(lenscale)
+        self._set_common(regularizer, apply_ind)
+
+    def get_dim(self, X):
+        return self.M
+
+    def _blocks(self, d, hypers):
+        raise NotImplementedError(
+            "%s is available as a feature map (transform / grad) only: the fused "
+            "StandardLinearModel / GeneralizedLinearModel passes handle "
+            "trigonometric, linear, bias and polynomial columns" % type(self).__name__)
+
+    def transform(self, X, lenscale=None):
+        Xv = self._view(_as_2d(X))
+        ls = self._check_dim(Xv.shape[1], lenscale)
+        Phi = eng.centre_features(eng.to_device(Xv), self.C, ls, self._kind)
+        return Phi.double().cpu().numpy()
+
+    def grad(self, X, lenscale=None):
+        Xv = self._view(_as_2d(X))
+        ls = self._check_dim(Xv.shape[1], lenscale)
+        _, dPhi = eng.centre_features(eng.to_device(Xv), self.C, ls, self._kind,
+                                      want_grad=True)
+        return dPhi.double().cpu().numpy()
+
+    def __repr__(self):
+        return "{}(centres={}, lenscale={}, regularizer={})".format(
+            type(self).__name__, self.C, self.params, self.regularizer)
+
+
+class SigmoidalBasis(RadialBasis):
+    """expit(||(x - c) / l||) around fixed centres (reference :734-815)."""
+    _kind = 1
 
 
 class _RandomKernelBasis(_LengthScaleBasis):
@@ -395,6 +489,86 @@ class FastFoodRBF(_LengthScaleBasis):
             "random_state={})".format(type(self).__name__, self.nbases, self.d,
                                       self.params, self.regularizer,
                                       self.random_state)
+
+
+class FastFoodGM(FastFoodRBF):
+    """One component of a Gaussian spectral-mixture kernel approximation
+    (reference :1386-1562): [cos(VX + Xm) | sin(VX + Xm) | cos(VX - Xm) |
+    sin(VX - Xm)] / sqrt(2n) with learnable frequency means ``m`` and ARD
+    lengthscales (both always of shape (d,)).
+
+    ``transform`` evaluates the two phase families as two trigonometric plan
+    blocks with frequency matrices V/l + m and V/l - m; ``grad`` returns
+    (d Phi / d mean, d Phi / d lenscale).  As in the reference (Appendix B #6 of
+    SURVEY.md) the pair of parameters does not fit the models' single-Parameter
+    assumption, so this basis is a feature map only.
+    """
+    _n_hypers = 2
+    _model_ok = False
+
+    def __init__(self, nbases, Xdim, mean=Parameter(norm_dist(), Bound()),
+                 lenscale=Parameter(gamma(1.), Positive()), regularizer=None,
+                 random_state=None, apply_ind=None):
+        # same draw order as the reference: dims, then matrices (:1436-1443)
+        super(FastFoodGM, self).__init__(nbases, Xdim, lenscale=Parameter(1., Positive()),
+                                         regularizer=regularizer,
+                                         random_state=random_state, apply_ind=apply_ind)
+        self._params = [self._init_param(mean), self._init_param(lenscale)]
+
+    def _init_param(self, param):
+        if param.shape == (self.d,):
+            return param
+        if param.shape in ((), (1,)):
+            # scalar initial value -> the same value for every dimension (:1529-1538)
+            if param.dist is not None:
+                return Parameter(param.dist, param.bounds, shape=(self.d,))
+            return Parameter(np.ones(self.d) * param.value, param.bounds)
+        raise ValueError("Parameter dimension doesn't agree with X dimensions!")
+
+    def _check_pair(self, Xdim, mean, lenscale):
+        if Xdim != self.d:
+            raise ValueError("Dimensions of data inconsistent!")
+        out = []
+        for v, p in zip((mean, lenscale), self._params):
+            v = p.value if v is None else v
+            v = np.atleast_1d(np.asarray(v, dtype=float))
+            if v.shape != (self.d,):
+                raise ValueError("Dimension of input parameter is inconsistent!")
+            out.append(v)
+        return out
+
+    def _blocks(self, d, hypers):
+        hypers = list(hypers) + [None] * (2 - len(hypers))
+        mean, ls = self._check_pair(self._eff_d(d), hypers[0], hypers[1])
+        V = self._freqs() / ls[:, None]
+        amp = 1.0 / math.sqrt(2 * self.n)
+        cols = self._cols(d)
+        return [eng.TrigBlock(V + mean[:, None], 1.0, cols, amp=amp),
+                eng.TrigBlock(V - mean[:, None], 1.0, cols, amp=amp)]
+
+    def get_dim(self, X):
+        return 4 * self.n
+
+    def transform(self, X, mean=None, lenscale=None):
+        X = _as_2d(X)
+        plan = eng.FeaturePlan(self._blocks(X.shape[1], [mean, lenscale]), X.shape[1])
+        return eng.features(plan, eng.to_device(X)).double().cpu().numpy()
+
+    def grad(self, X, mean=None, lenscale=None):
+        Xv = self._view(_as_2d(X))
+        mean, ls = self._check_pair(Xv.shape[1], mean, lenscale)
+        dm, dl = eng.gm_grad(eng.to_device(Xv), self._freqs(), mean, ls)
+        return dm.double().cpu().numpy(), dl.double().cpu().numpy()
+
+    @property
+    def params(self):
+        return self._params
+
+    def __repr__(self):
+        return "{}(nbases={}, Xdim={}, mean={}, lenscale={}, regularizer={}, " \
+            "random_state={})".format(type(self).__name__, self.nbases, self.d,
+                                      self.params[0], self.params[1],
+                                      self.regularizer, self.random_state)
 
 
 class BasisCat(object):

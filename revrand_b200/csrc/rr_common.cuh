@@ -74,6 +74,21 @@ __device__ __forceinline__ void sincos_turns(float u, float* s, float* c) {
   sincospif(2.0f * r, s, c);
 }
 
+// x^p for a small non-negative integer p (polynomial columns of a plan).
+__device__ __forceinline__ float ipowf(float x, int p) {
+  float r = 1.0f;
+  for (int i = 0; i < p; ++i) r *= x;
+  return r;
+}
+// value of extra (affine / polynomial / constant) column j of a plan for one row
+__device__ __forceinline__ float ext_value(const rr_plan& plan, int j, const float* xrow,
+                                           int stride) {
+  const int src = plan.ext_src[j];
+  if (src < 0) return plan.ext_val[j];
+  const float x = xrow[src * stride];
+  return plan.ext_pow ? ipowf(x, plan.ext_pow[j]) : x;
+}
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

@@ -50,9 +50,7 @@ features_kernel(rr_plan plan, const float* __restrict__ X, int64_t N,
   }
   for (int t = threadIdx.x; t < rows * plan.next; t += blockDim.x) {
     int r = t / plan.next, j = t - r * plan.next;
-    int src = plan.ext_src[j];
-    float v = src >= 0 ? xs[r * d + src] : plan.ext_val[j];
-    Phi[(n0 + r) * ldphi + plan.ext_col[j]] = v;
+    Phi[(n0 + r) * ldphi + plan.ext_col[j]] = ext_value(plan, j, xs + r * d, 1);
   }
 }
 
@@ -115,6 +113,80 @@ trig_grad_kernel(const float* __restrict__ X, int64_t N, int d,
         os[i] = g * c * amp;
       }
     }
+  }
+}
+
+// Radial / sigmoidal bases: thread per (row, centre).
+__global__ void __launch_bounds__(256)
+centre_features_kernel(const float* __restrict__ X, int64_t N, int d,
+                       const float* __restrict__ C, int M, const float* __restrict__ ls,
+                       int P, int kind, float* __restrict__ Phi, float* __restrict__ dPhi) {
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= N * M) return;
+  const int64_t n = idx / M;
+  const int c = (int)(idx - n * M);
+  const float* x = X + n * d;
+  const float* cc = C + (int64_t)c * d;
+  float acc = 0.0f;
+  for (int i = 0; i < d; ++i) {
+    const float l = ls[P == 1 ? 0 : i];
+    // radial: the reference divides by 2 l^2 BEFORE squaring (:686-688)
+    const float t = (x[i] - cc[i]) / (kind == 0 ? 2.0f * l * l : l);
+    acc = fmaf(t, t, acc);
+  }
+  const float phi = kind == 0 ? expf(-acc) : 1.0f / (1.0f + expf(-sqrtf(acc)));
+  Phi[idx] = phi;
+  if (dPhi) {
+    for (int i = 0; i < P; ++i) {      // P == 1: input dimension 0 only, as the reference
+      const float l = ls[i];
+      const float df = x[i] - cc[i];
+      float g;
+      if (kind == 0) {
+        const float l3 = l * l * l;
+        g = phi * (df / l3) * (df / l3);
+      } else {
+        g = -fabsf(df) / (l * l) * phi * (1.0f - phi);
+      }
+      dPhi[idx * P + i] = g;
+    }
+  }
+}
+
+// FastFoodGM.grad from the dense projection image: thread per (row, frequency).
+__global__ void __launch_bounds__(256)
+gm_grad_kernel(const float* __restrict__ X, int64_t N, int d, const float* __restrict__ V,
+               int n, const float* __restrict__ mean, const float* __restrict__ ls,
+               float* __restrict__ dmean, float* __restrict__ dlen) {
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= N * n) return;
+  const int64_t r = idx / n;
+  const int k = (int)(idx - r * n);
+  const float* x = X + r * d;
+  const float inv2pi = 0.15915494309189535f;
+  float p = 0.0f, q = 0.0f;          // phases in turns
+  for (int i = 0; i < d; ++i) {
+    p = fmaf(x[i], V[(int64_t)i * n + k] / ls[i] * inv2pi, p);
+    q = fmaf(x[i], mean[i] * inv2pi, q);
+  }
+  float sp, cp, sm, cm;
+  sincos_turns(p + q, &sp, &cp);
+  sincos_turns(p - q, &sm, &cm);
+  const float amp = rsqrtf(2.0f * (float)n);
+  const int64_t F = 4 * (int64_t)n;
+  for (int i = 0; i < d; ++i) {
+    const float dmx = x[i];
+    const float dvx = -x[i] * V[(int64_t)i * n + k] / (ls[i] * ls[i]);
+    // blocks [cos(p+q) | sin(p+q) | cos(p-q) | sin(p-q)]; d/dphase cos = -sin, sin = cos
+    float* om = dmean + (r * F) * d + i;
+    float* ol = dlen + (r * F) * d + i;
+    om[(int64_t)(k) * d] = amp * dmx * (-sp);
+    om[(int64_t)(n + k) * d] = amp * dmx * cp;
+    om[(int64_t)(2 * n + k) * d] = amp * (-dmx) * (-sm);
+    om[(int64_t)(3 * n + k) * d] = amp * (-dmx) * cm;
+    ol[(int64_t)(k) * d] = amp * dvx * (-sp);
+    ol[(int64_t)(n + k) * d] = amp * dvx * cp;
+    ol[(int64_t)(2 * n + k) * d] = amp * dvx * (-sm);
+    ol[(int64_t)(3 * n + k) * d] = amp * dvx * cm;
   }
 }
 
@@ -210,5 +282,34 @@ extern "C" int rr_fastfood_features(const float* Xs, int64_t N, int32_t d,
   rr::fastfood_kernel<<<(unsigned)N, 256, smem, (cudaStream_t)stream>>>(
       Xs, N, d, d2, k, B, G, PI, S, Phi, VX_out);
   RR_LAUNCH_CHECK("fastfood_kernel");
+  return RR_OK;
+}
+
+extern "C" int rr_centre_features(const float* X, int64_t N, int32_t d, const float* C,
+                                  int32_t M, const float* lenscale, int32_t n_ls,
+                                  int32_t kind, float* Phi, float* dPhi, void* stream) {
+  using namespace rr;
+  RR_REQUIRE(X && C && lenscale && Phi, "null pointer");
+  RR_REQUIRE(d > 0 && M > 0 && (n_ls == 1 || n_ls == d), "bad shape");
+  RR_REQUIRE(kind == 0 || kind == 1, "kind must be 0 (radial) or 1 (sigmoidal)");
+  if (N == 0) return RR_OK;
+  const int64_t total = N * M;
+  centre_features_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+      X, N, d, C, M, lenscale, n_ls, kind, Phi, dPhi);
+  RR_LAUNCH_CHECK("centre_features_kernel");
+  return RR_OK;
+}
+
+extern "C" int rr_gm_grad(const float* X, int64_t N, int32_t d, const float* V, int32_t n,
+                          const float* mean, const float* lenscale, float* dmean,
+                          float* dlen, void* stream) {
+  using namespace rr;
+  RR_REQUIRE(X && V && mean && lenscale && dmean && dlen, "null pointer");
+  RR_REQUIRE(d > 0 && n > 0, "bad shape");
+  if (N == 0) return RR_OK;
+  const int64_t total = N * n;
+  gm_grad_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+      X, N, d, V, n, mean, lenscale, dmean, dlen);
+  RR_LAUNCH_CHECK("gm_grad_kernel");
   return RR_OK;
 }

@@ -856,7 +856,7 @@ t2_finalize_kernel(const double* __restrict__ T, const float* __restrict__ camp,
 int tc_suffstats_supported(const rr_plan* pl) {
   // pure trigonometric plans, or plans whose affine columns ride along as
   // pseudo-frequency slots (kind != NULL; then D <= 2 * ktot)
-  if (pl->d < 1 || pl->d > 32 || pl->ktot < 1 || pl->next != 0) return 0;
+  if (pl->d < 1 || pl->d > 32 || pl->ktot < 1 || pl->next != 0 || pl->ext_pow != nullptr) return 0;
   return (pl->kind != nullptr ? pl->D <= 2 * pl->ktot : pl->D == 2 * pl->ktot) ? 1 : 0;
 }
 

@@ -53,6 +53,9 @@ constexpr int S3_CHAIN = 32768;                   // rows per exact int32 accumu
 constexpr int S3_CHAIN_KB = S3_CHAIN / S3_KB;     // 512
 constexpr float S3_SCALE = 8322560.0f;            // S = 2^23 - 2^16 - 2^9: |d0| <= 127
 constexpr int S3_GROUP_CHAINS = 8;                // chains per generator / GEMM launch
+constexpr int S3_FIRST_CHAINS = 1;                // ... of the first launch: its generator
+                                                  // pass is the only one not hidden behind
+                                                  // tensor-core work
 constexpr size_t S3_GROUP_BYTES_MAX = (size_t)4 << 30;   // digit image budget per buffer
 
 static_assert(S3_A_PLANE % 512 == 0 && S3_B_PLANE % 512 == 0, "64B-swizzle tiles are 512-byte aligned");
@@ -107,7 +110,8 @@ __global__ void t3_colamp_kernel(rr_plan plan, const unsigned int* __restrict__ 
   }
   if (t < plan.next) {
     const int src = plan.ext_src[t];
-    camp[plan.ext_col[t]] = src >= 0 ? __uint_as_float(scales[src]) : plan.ext_val[t];
+    const int pw = plan.ext_pow ? plan.ext_pow[t] : 1;
+    camp[plan.ext_col[t]] = src >= 0 ? ipowf(__uint_as_float(scales[src]), pw) : plan.ext_val[t];
   }
   if (t == 0) camp[plan.D] = __uint_as_float(scales[plan.d]);
 }
@@ -174,6 +178,7 @@ t3_digits_kernel(rr_plan plan, const float* __restrict__ X, const float* __restr
     if (e < plan.next) {
       f = plan.ext_col[e];
       const int src = plan.ext_src[e];
+      const int pw = plan.ext_pow ? plan.ext_pow[e] : 1;
       float inv = 0.0f;
       if (src >= 0) {
         const float sc = __uint_as_float(scales[src]);
@@ -181,7 +186,8 @@ t3_digits_kernel(rr_plan plan, const float* __restrict__ X, const float* __restr
       }
 #pragma unroll
       for (int r = 0; r < 16; ++r) {
-        float v = src >= 0 ? xs[src * S3_KB + 16 * rg + r] * inv : 1.0f;
+        // (x / max|x|)^p in [-1, 1]; the amplitude max|x|^p is applied at the end
+        float v = src >= 0 ? ipowf(xs[src * S3_KB + 16 * rg + r] * inv, pw) : 1.0f;
         v = fminf(1.0f, fmaxf(-1.0f, v));
         vals[r] = (nrow0 + r < rows) ? v : 0.0f;
       }
@@ -568,8 +574,13 @@ static int tc3_groups(const rr_plan* pl, const S3Shape& s, const float* X, const
   const int gy_other = (nother + T3_FREQS - 1) / T3_FREQS;
   const size_t dsmem = (size_t)S3_KB * d * sizeof(float);
   int g = 0;
-  for (int64_t r0 = 0; r0 < N; r0 += s.group_rows, ++g) {
-    const int64_t rows = (N - r0) < s.group_rows ? (N - r0) : s.group_rows;
+  int64_t step = 0;
+  for (int64_t r0 = 0; r0 < N; r0 += step, ++g) {
+    // group 0 is short (little exposed generator time); a job that fits one group anyway
+    // is not split
+    step = (g == 0 && N > s.group_rows) ? (int64_t)S3_FIRST_CHAINS * S3_CHAIN : s.group_rows;
+    if (step > s.group_rows) step = s.group_rows;
+    const int64_t rows = (N - r0) < step ? (N - r0) : step;
     const int nkb = (int)((rows + S3_KB - 1) / S3_KB);
     const int buf = g & 1;
     if (overlap && g >= 2) RR_CUDA_CHECK(cudaStreamWaitEvent(sg, ev_mma[buf], 0));

@@ -144,8 +144,8 @@ phi_fit_kernel(rr_plan plan, const float* __restrict__ X, int rows, int Dp, int 
 #pragma unroll
       for (int r = 0; r < PE_ROWS; ++r) {
         const bool live = n0 + r < rows;
-        const float v0 = !live ? 0.0f : (s0 >= 0 ? xs[r * d + s0] : c0);
-        const float v1 = !live ? 0.0f : (s1 >= 0 ? xs[r * d + s1] : c1);
+        const float v0 = !live ? 0.0f : (in0 ? ext_value(plan, e0, xs + r * d, 1) : c0);
+        const float v1 = !live ? 0.0f : (in1 ? ext_value(plan, e0 + 1, xs + r * d, 1) : c1);
         *reinterpret_cast<__half2*>(img + r * 128 + (c4 ^ ((uint32_t)(r & 7) << 4)) + inner) =
             __floats2half2_rn(v0, v1);
       }
@@ -219,11 +219,10 @@ phi_fit_kernel(rr_plan plan, const float* __restrict__ X, int rows, int Dp, int 
   // extra (non-trigonometric) columns: Linear / Bias bases (first frequency slice only)
   if (blockIdx.y == 0) {
     for (int j = tid; j < plan.next; j += PE_PAIRS) {
-      const int src = plan.ext_src[j];
       const float mj = m[plan.ext_col[j]];
 #pragma unroll
       for (int r = 0; r < PE_ROWS; ++r)
-        f[r] = fmaf(src >= 0 ? xs[r * d + src] : plan.ext_val[j], mj, f[r]);
+        f[r] = fmaf(ext_value(plan, j, xs + r * d, 1), mj, f[r]);
     }
   }
 #pragma unroll

@@ -127,6 +127,8 @@ class GeneralizedLinearModel(BaseEstimator, RegressorMixin):
     def fit(self, X, y, likelihood_args=()):
         """Learn variational posterior and hyper-parameters (glm.py:139-203)."""
         X, y = check_X_y(X, y)
+        from .basis_functions import require_model_support
+        require_model_support(self.basis)
         N, _ = X.shape
         self.B_ = N / self.batch_size
         self.D_ = self.basis.get_dim(X)

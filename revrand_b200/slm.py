@@ -42,6 +42,8 @@ class _SLMProblem(object):
 
     def __init__(self, basis, X, y, shard=True):
         t = eng.require_cuda()
+        from .basis_functions import require_model_support
+        require_model_support(basis)
         self.basis = basis
         self.N_total, self.d = X.shape
         self.rank, self.world = eng.world() if shard else (0, 1)

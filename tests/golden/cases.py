@@ -119,3 +119,21 @@ def glm_case_inputs(name):
     ls = 1.0 + 0.2 * np.arange(d)
     return dict(X=X, y=y, n=n, m=m, C=C, eps=eps, ls=ls, reg=1.7,
                 B=sh["N"] / M)
+
+
+# ---- the remaining bases ----------------------------------
+# (d, N); centres are seeded (M, d) draws; FastFoodGM uses nbases = 12
+BASES2_SHAPES = [(1, 40), (3, 40), (6, 32)]
+BASES2_M = 7
+BASES2_NBASES = 12
+BASES2_ORDER = 3
+
+
+def bases2_inputs(d, N):
+    rs = np.random.RandomState(7000 + d)
+    X = rs.randn(N, d)
+    C = rs.randn(BASES2_M, d)
+    ls_iso = 0.8 + 0.4 * rs.rand()
+    ls_ard = 0.6 + rs.rand(d)
+    mean = 0.5 * rs.randn(d)
+    return X, C, ls_iso, ls_ard, mean

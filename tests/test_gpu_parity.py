@@ -585,3 +585,100 @@ def test_glm_fit_poisson_small():
     assert np.all(Vy >= 0)
     p, _, _ = glm.predict_cdf(Xs, 2.0)
     assert np.all((p >= 0) & (p <= 1))
+
+
+# ---- the remaining bases: feature maps + gradients --------------
+
+def _bases2():
+    import os
+    return np.load(os.path.join(os.path.dirname(__file__), "golden", "bases2.npz"))
+
+
+@pytest.mark.parametrize("d,N", cases.BASES2_SHAPES)
+def test_polynomial_radial_sigmoidal_vs_reference(d, N):
+    g = _bases2()
+    X, C, ls_iso, ls_ard, mean = cases.bases2_inputs(d, N)
+    tag = "d%d" % d
+    poly = bf.PolynomialBasis(order=cases.BASES2_ORDER, include_bias=True)
+    Phi = poly.transform(X)
+    ref = g[tag + "/poly/Phi"]
+    assert Phi.shape == ref.shape and poly.get_dim(X) == ref.shape[1]
+    np.testing.assert_allclose(Phi, ref, rtol=2e-6, atol=1e-6)
+    for ard in (False, True):
+        ls = ls_ard if ard else ls_iso
+        key = tag + ("/ard" if ard else "/iso")
+        lsp = Parameter(np.asarray(ls, dtype=float) if ard else float(ls), Positive())
+        for name, cls in (("radial", bf.RadialBasis), ("sigmoid", bf.SigmoidalBasis)):
+            b = cls(centres=C, lenscale=lsp)
+            Phi, dPhi = b.transform(X, ls), b.grad(X, ls)
+            rP, rG = g[key + "/" + name + "/Phi"], g[key + "/" + name + "/dPhi"]
+            assert Phi.shape == rP.shape and dPhi.shape == rG.shape
+            np.testing.assert_allclose(Phi, rP, rtol=1e-5, atol=1e-6)
+            np.testing.assert_allclose(dPhi, rG, rtol=1e-4, atol=1e-6 * (1 + np.abs(rG).max()))
+
+
+@pytest.mark.parametrize("d,N", cases.BASES2_SHAPES)
+def test_fastfood_gm_vs_reference(d, N):
+    """FastFoodGM (one spectral-mixture component): seeded matrices bit-equal to the
+    reference's, features and both gradients against its outputs."""
+    g = _bases2()
+    X, C, ls_iso, ls_ard, mean = cases.bases2_inputs(d, N)
+    tag = "d%d/gm" % d
+    gm = bf.FastFoodGM(nbases=cases.BASES2_NBASES, Xdim=d, random_state=3,
+                       mean=Parameter(mean.copy(), rr.Bound()),
+                       lenscale=Parameter(ls_ard.copy(), Positive()))
+    assert np.array_equal(gm.B, g[tag + "/B"]) and np.array_equal(gm.PI, g[tag + "/PI"])
+    np.testing.assert_array_equal(gm.G, g[tag + "/G"])
+    np.testing.assert_array_equal(gm.S, g[tag + "/S"])
+    Phi = gm.transform(X, mean, ls_ard)
+    ref = g[tag + "/Phi"]
+    assert Phi.shape == ref.shape == (N, gm.get_dim(X))
+    assert np.max(np.abs(Phi - ref)) < 5e-6
+    dm, dl = gm.grad(X, mean, ls_ard)
+    assert dm.shape == g[tag + "/dmean"].shape and dl.shape == g[tag + "/dlen"].shape
+    assert np.max(np.abs(dm - g[tag + "/dmean"])) < 2e-5 * (1 + np.abs(g[tag + "/dmean"]).max())
+    assert np.max(np.abs(dl - g[tag + "/dlen"])) < 2e-5 * (1 + np.abs(g[tag + "/dlen"]).max())
+    # defaults: (d,) parameters from scalar initial values
+    gm2 = bf.FastFoodGM(nbases=8, Xdim=d, random_state=0)
+    assert [p.shape for p in gm2.params] == [(d,), (d,)]
+    assert gm2.transform(X).shape == (N, gm2.get_dim(X))
+
+
+def test_polynomial_basis_rides_the_tensor_core_passes():
+    """BasisCat(RandomRBF + PolynomialBasis(order 3)): polynomial columns are
+    fixed-point features of the int8 value pass and extra reduction columns of
+    the gradient pass; whole evaluation against the float64 oracle."""
+    N, d, K = 20011, 5, 96
+    X, y = _synthetic(N, d, seed=21)
+    ls = 1.5 * (1.0 + 0.1 * np.arange(d))
+    rbf = bf.RandomRBF(nbases=K, Xdim=d, random_state=6, lenscale=Parameter(ls, Positive()),
+                       regularizer=Parameter(1.3, Positive()))
+    poly = bf.PolynomialBasis(order=3, regularizer=Parameter(2.0, Positive()))
+    old = config.ENGINE
+    config.ENGINE = "tcgen05"
+    try:
+        slm = rr.StandardLinearModel(basis=rbf + poly)
+        slm.obj_ = -np.inf
+        nelbo, (dv, dr, dl) = slm._elbo(X, y, 0.05, [1.3, 2.0], ls)
+    finally:
+        config.ENGINE = old
+    Phi = np.hstack((orc.trig_features(X, rbf.W, ls), orc.polynomial_features(X, 3)))
+    D = Phi.shape[1]
+    lam = np.concatenate((np.full(2 * K, 1.3), np.full(D - 2 * K, 2.0)))
+    iC = np.diag(1.0 / lam) + Phi.T.dot(Phi) / 0.05
+    Cm = np.linalg.inv(iC)
+    m = Cm.dot(Phi.T.dot(y)) / 0.05
+    assert relerr(slm.weights_, m) < 1e-4
+    np.testing.assert_allclose(slm.covariance_.diagonal(), Cm.diagonal(), rtol=1e-4)
+    err = y - Phi.dot(m)
+    ref_nelbo = 0.5 * (N * np.log(2 * np.pi * 0.05) + err.dot(err) / 0.05
+                       + (Phi.T.dot(Phi) * Cm).sum() / 0.05 + ((m ** 2 + Cm.diagonal()) / lam).sum()
+                       + np.linalg.slogdet(iC)[1] + np.log(lam).sum() - D)
+    assert abs(nelbo - ref_nelbo) <= 1e-4 * abs(ref_nelbo)
+
+
+def test_models_refuse_feature_map_only_bases():
+    X, y = _synthetic(200, 2, seed=1)
+    b = bf.RadialBasis(centres=np.zeros((3, 2)))
+    with pytest.raises(NotImplementedError):
+        rr.StandardLinearModel(basis=b).fit(X, y)

@@ -35,7 +35,7 @@ def test_library_exports_every_declared_symbol():
     for name in declared:
         assert getattr(lib, name) is not None
     assert lib.rr_version() >= 100
-    assert ctypes.sizeof(_cabi.RRPlan) == 16 + 8 * ctypes.sizeof(ctypes.c_void_p)
+    assert ctypes.sizeof(_cabi.RRPlan) == 16 + 9 * ctypes.sizeof(ctypes.c_void_p)
     # shape queries need no GPU
     assert lib.rr_tcgen05_supported(21, 2048, 0, 4096) == 1
     assert lib.rr_tcgen05_supported(21, 2048, 22, 4118) == 1   # affine columns ride along
