@@ -18,9 +18,10 @@
 // and added (RED.F64, also exact: |sum| < 2^53) to a float64 image T of the
 // upper triangle; a finalize kernel applies 2^16 / S^2 and the amplitudes.
 //
-// Phi itself is produced once per (row, frequency) by t3_digits_kernel -- fp32
-// projection, exact range reduction in turns, sincospif -- as a tile-major
-// int8 image that the GEMM streams with bulk copies.  In the previous design
+// Phi itself is produced once per (row, frequency) by t3_digits_kernel -- tf32
+// tensor-core projection with a three-product split (fp32 grade), exact range
+// reduction in turns, polynomial sin/cos -- as a tile-major int8 image that the
+// GEMM streams with bulk copies.  In the previous design
 // the trigonometric generators sat inside the tensor-core kernel and
 // re-evaluated every feature for each of the ~18 output tiles it takes part
 // in; at 2 x 10^9 (row, frequency) pairs per pass that made the generators,
@@ -148,33 +149,113 @@ __device__ __forceinline__ void t3_store_planes(uint8_t* __restrict__ img, int64
   *reinterpret_cast<uint4*>(base + 2 * plane) = d2;
 }
 
-constexpr int T3_FREQS = 64;     // frequencies (or affine / padding features) per block
+constexpr int T3_FREQS = 128;    // frequencies per trigonometric block (16 per warp)
+constexpr int T3_OTHER = 64;     // affine / y / padding features per "other" block
 
-// Block = one K block (64 rows) x 64 frequencies; thread = one frequency x 16 rows
-// (one 16-byte chunk of each of its six digit lines).  grid.y counts the
-// trigonometric blocks first, then the blocks of "other" features: affine
-// columns, the y column and the zero padding.
-__global__ void __launch_bounds__(256)
+// Row <-> byte mapping inside a K block (any fixed bijection works: the Gram sum
+// over rows does not care about their order, as long as EVERY feature uses the
+// same one).  Byte b of chunk q holds row 8 (b >> 1) + 2 q + (b & 1): exactly the
+// rows one lane of an m16n8k8 accumulator fragment owns across the eight row
+// tiles, so a generator thread packs its sixteen values without any shuffle.
+__device__ __forceinline__ int t3_row_of(int q, int b) { return 8 * (b >> 1) + 2 * q + (b & 1); }
+
+// round an fp32 value to tf32 (10 explicit mantissa bits), ties away from zero
+__device__ __forceinline__ float t3_tf32(float x) {
+  return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xFFFFE000u);
+}
+__device__ __forceinline__ void t3_mma_tf32(float (&c)[4], const uint32_t (&a)[4], uint32_t b0,
+                                            uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, "
+      "{%8, %9}, {%0, %1, %2, %3};"
+      : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
+// sin and cos of 2 pi u (u in turns), |error| ~ 1e-7: exact reduction to
+// v in [-1/8, 1/8] turns around the nearest quarter turn j, degree-9 / degree-8
+// Taylor polynomials in 2 pi v (truncation 2e-9 / 2.4e-8 at |v| = 1/8), then the
+// rotation by j quarter turns as a swap and two sign flips.  ~25 instructions on
+// the FMA / ALU pipes (sincospif: ~100).
+__device__ __forceinline__ void t3_sincos_turns(float u, float& s, float& c) {
+  const float MAGIC = 12582912.0f;                 // 1.5 * 2^23
+  const float r = u - ((u + MAGIC) - MAGIC);       // u - rint(u): exact, in [-0.5, 0.5]
+  const float t = fmaf(r, 4.0f, MAGIC);            // low mantissa bits = rint(4 r)
+  const int j = (int)__float_as_uint(t);           // two's complement in the low bits
+  const float v = fmaf(t - MAGIC, -0.25f, r);      // exact, in [-1/8, 1/8]
+  const float z = v * v;
+  float ps = fmaf(z, 42.058693944897654f, -76.70585975306136f);     // (2pi)^9/9!, -(2pi)^7/7!
+  ps = fmaf(ps, z, 81.60524927607504f);                             // (2pi)^5/5!
+  ps = fmaf(ps, z, -41.341702240399755f);                           // -(2pi)^3/3!
+  ps = fmaf(ps, z, 6.283185307179586f);
+  const float sn = ps * v;
+  float pc = fmaf(z, 60.24464137187666f, -85.45681720669373f);      // (2pi)^8/8!, -(2pi)^6/6!
+  pc = fmaf(pc, z, 64.93939402266829f);                             // (2pi)^4/4!
+  pc = fmaf(pc, z, -19.739208802178716f);                           // -(2pi)^2/2!
+  const float cs = fmaf(pc, z, 1.0f);
+  // rotate (cs, sn) by j quarter turns: j = 0: (cs, sn), 1: (-sn, cs), 2: (-cs, -sn), 3: (sn, -cs)
+  const bool odd = (j & 1) != 0;
+  const uint32_t cb = __float_as_uint(odd ? sn : cs), sb = __float_as_uint(odd ? cs : sn);
+  c = __uint_as_float(cb ^ (((uint32_t)(j + 1) << 30) & 0x80000000u));
+  s = __uint_as_float(sb ^ (((uint32_t)j << 30) & 0x80000000u));
+}
+
+// sixteen values of one feature (bytes 0..15 of one chunk) -> its three digit planes
+__device__ __forceinline__ void t3_emit(uint8_t* __restrict__ img, int64_t kb, int Fp, int f,
+                                        int chunk, const int (&k)[16]) {
+  uint4 q0, q1, q2;
+  uint32_t* w0 = reinterpret_cast<uint32_t*>(&q0);
+  uint32_t* w1 = reinterpret_cast<uint32_t*>(&q1);
+  uint32_t* w2 = reinterpret_cast<uint32_t*>(&q2);
+#pragma unroll
+  for (int g = 0; g < 4; ++g)
+    t3_pack4(k[4 * g], k[4 * g + 1], k[4 * g + 2], k[4 * g + 3], w0[g], w1[g], w2[g]);
+  t3_store_planes(img, kb, Fp, f, chunk, q0, q1, q2);
+}
+
+// Digit image of one K block (64 rows).  grid.y counts the trigonometric blocks
+// (128 frequencies, 16 per warp) first, then the blocks of "other" features:
+// affine columns, the y column and the zero padding (64 per block, thread =
+// feature x chunk).
+//
+// Trigonometric block: the projection u = X Wt runs on the tensor cores
+// (mma.sync m16n8k8 tf32, frequencies = M, rows = N, input dimensions = K) with
+// the three-product split hi*hi + lo*hi + hi*lo of tf32-rounded operands, which
+// carries ~22 bits per product like the fp32 FMA chain it replaces; a lane ends
+// up with two frequencies x sixteen rows, i.e. one 16-byte chunk of each of the
+// twelve digit lines it then fills.
+__global__ void __launch_bounds__(256, 2)
 t3_digits_kernel(rr_plan plan, const float* __restrict__ X, const float* __restrict__ y,
                  int64_t rows, int Fp, int gy_trig, const unsigned int* __restrict__ scales,
                  uint8_t* __restrict__ img) {
-  extern __shared__ float xs[];            // [d][64]: column i of the slab, rows fastest
+  extern __shared__ float xs[];            // [2][64][stride]: tf32 hi and lo parts of the slab
   const int d = plan.d, ktot = plan.ktot;
-  const int tid = threadIdx.x;
+  const int kp = (d + 7) & ~7;             // input dimensions padded to whole k-steps
+  const int stride = kp + 4;               // (stride / 4 odd: fragment loads hit 32 banks)
+  float* xh = xs;
+  float* xl = xs + S3_KB * stride;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int64_t kb = blockIdx.x;
   const int64_t n0 = kb * S3_KB;
-  for (int e = tid; e < S3_KB * d; e += 256) {
-    const int r = e / d, i = e - r * d;
-    xs[i * S3_KB + r] = (n0 + r < rows) ? X[n0 * d + e] : 0.0f;
+  const bool trig = (int)blockIdx.y < gy_trig;
+  for (int e = tid; e < S3_KB * kp; e += 256) {
+    const int r = e / kp, i = e - r * kp;
+    const float x = (i < d && n0 + r < rows) ? X[(n0 + r) * d + i] : 0.0f;
+    if (trig) {
+      const float h = t3_tf32(x);
+      xh[r * stride + i] = h;
+      xl[r * stride + i] = t3_tf32(x - h);
+    } else {
+      xh[r * stride + i] = x;
+    }
   }
   __syncthreads();
-  const int fl = tid >> 2, rg = tid & 3;
-  const int64_t nrow0 = n0 + 16 * rg;      // first row of this thread's chunk
-  if ((int)blockIdx.y >= gy_trig) {
+  if (!trig) {
     // ---- affine columns, y, padding -------------------------------------------
-    const int e = ((int)blockIdx.y - gy_trig) * T3_FREQS + fl;
+    const int fl = tid >> 2, q = tid & 3;
+    const int e = ((int)blockIdx.y - gy_trig) * T3_OTHER + fl;
     int f;
-    float vals[16];
+    int kq[16];
     if (e < plan.next) {
       f = plan.ext_col[e];
       const int src = plan.ext_src[e];
@@ -185,82 +266,83 @@ t3_digits_kernel(rr_plan plan, const float* __restrict__ X, const float* __restr
         inv = sc > 0.0f ? 1.0f / sc : 0.0f;
       }
 #pragma unroll
-      for (int r = 0; r < 16; ++r) {
+      for (int b = 0; b < 16; ++b) {
+        const int r = t3_row_of(q, b);
         // (x / max|x|)^p in [-1, 1]; the amplitude max|x|^p is applied at the end
-        float v = src >= 0 ? ipowf(xs[src * S3_KB + 16 * rg + r] * inv, pw) : 1.0f;
+        float v = src >= 0 ? ipowf(xh[r * stride + src] * inv, pw) : 1.0f;
         v = fminf(1.0f, fmaxf(-1.0f, v));
-        vals[r] = (nrow0 + r < rows) ? v : 0.0f;
+        kq[b] = t3_quant((n0 + r < rows) ? v : 0.0f);
       }
     } else if (e == plan.next) {
       f = plan.D;
       const float sc = __uint_as_float(scales[d]);
       const float inv = (y != nullptr && sc > 0.0f) ? 1.0f / sc : 0.0f;
 #pragma unroll
-      for (int r = 0; r < 16; ++r) {
-        float v = (y != nullptr && nrow0 + r < rows) ? y[nrow0 + r] * inv : 0.0f;
-        vals[r] = fminf(1.0f, fmaxf(-1.0f, v));
+      for (int b = 0; b < 16; ++b) {
+        const int r = t3_row_of(q, b);
+        const float v = (y != nullptr && n0 + r < rows) ? y[n0 + r] * inv : 0.0f;
+        kq[b] = t3_quant(fminf(1.0f, fmaxf(-1.0f, v)));
       }
     } else {
       f = plan.D + (e - plan.next);
       if (f >= Fp) return;
 #pragma unroll
-      for (int r = 0; r < 16; ++r) vals[r] = 0.0f;
+      for (int b = 0; b < 16; ++b) kq[b] = 0;
     }
-    uint4 q0, q1, q2;
-    uint32_t* w0 = reinterpret_cast<uint32_t*>(&q0);
-    uint32_t* w1 = reinterpret_cast<uint32_t*>(&q1);
-    uint32_t* w2 = reinterpret_cast<uint32_t*>(&q2);
-#pragma unroll
-    for (int g = 0; g < 4; ++g)
-      t3_pack4(t3_quant(vals[4 * g]), t3_quant(vals[4 * g + 1]), t3_quant(vals[4 * g + 2]),
-               t3_quant(vals[4 * g + 3]), w0[g], w1[g], w2[g]);
-    t3_store_planes(img, kb, Fp, f, rg, q0, q1, q2);
+    t3_emit(img, kb, Fp, f, q, kq);
     return;
   }
   // ---- trigonometric features ------------------------------------------------------
-  const int k = (int)blockIdx.y * T3_FREQS + fl;
-  if (k >= ktot) return;
-  float u[16];
+  const int g = lane >> 2, q = lane & 3;
+  const int f0 = (int)blockIdx.y * T3_FREQS + 16 * warp;     // first frequency of this warp
+  if (f0 >= ktot) return;
+  const int fA = f0 + g, fB = f0 + g + 8;
+  float acc[8][4];
 #pragma unroll
-  for (int r = 0; r < 16; ++r) u[r] = 0.0f;
-  const float* xr = xs + 16 * rg;
-  for (int i = 0; i < d; ++i) {
-    const float w = __ldg(plan.Wt + (int64_t)i * ktot + k);
-    const float4* x4 = reinterpret_cast<const float4*>(xr + i * S3_KB);
+  for (int nt = 0; nt < 8; ++nt)
 #pragma unroll
-    for (int g = 0; g < 4; ++g) {
-      const float4 xv = x4[g];
-      u[4 * g + 0] = fmaf(xv.x, w, u[4 * g + 0]);
-      u[4 * g + 1] = fmaf(xv.y, w, u[4 * g + 1]);
-      u[4 * g + 2] = fmaf(xv.z, w, u[4 * g + 2]);
-      u[4 * g + 3] = fmaf(xv.w, w, u[4 * g + 3]);
-    }
-  }
-  const int fc = plan.col_cos[k], fs = plan.col_sin[k];
-  uint4 c0, c1, c2, s0, s1, s2;
-  uint32_t* cw0 = reinterpret_cast<uint32_t*>(&c0);
-  uint32_t* cw1 = reinterpret_cast<uint32_t*>(&c1);
-  uint32_t* cw2 = reinterpret_cast<uint32_t*>(&c2);
-  uint32_t* sw0 = reinterpret_cast<uint32_t*>(&s0);
-  uint32_t* sw1 = reinterpret_cast<uint32_t*>(&s1);
-  uint32_t* sw2 = reinterpret_cast<uint32_t*>(&s2);
-#pragma unroll
-  for (int g = 0; g < 4; ++g) {
-    int kc[4], ks[4];
+    for (int j = 0; j < 4; ++j) acc[nt][j] = 0.0f;
+  for (int ks = 0; ks < kp; ks += 8) {
+    // A fragment (frequencies x input dimensions): a0 (g, q), a1 (g+8, q), a2 (g, q+4), a3 (g+8, q+4)
+    uint32_t ah[4], al[4];
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-      const int r = 4 * g + j;
-      float sv, cv;
-      sincos_turns(u[r], &sv, &cv);
-      const bool live = nrow0 + r < rows;
-      kc[j] = t3_quant(live ? cv : 0.0f);
-      ks[j] = t3_quant(live ? sv : 0.0f);
+      const int fi = (j & 1) ? fB : fA;
+      const int ki = ks + q + ((j & 2) ? 4 : 0);
+      const float w = (fi < ktot && ki < d) ? __ldg(plan.Wt + (int64_t)ki * ktot + fi) : 0.0f;
+      const float h = t3_tf32(w);
+      ah[j] = __float_as_uint(h);
+      al[j] = __float_as_uint(t3_tf32(w - h));
     }
-    t3_pack4(kc[0], kc[1], kc[2], kc[3], cw0[g], cw1[g], cw2[g]);
-    t3_pack4(ks[0], ks[1], ks[2], ks[3], sw0[g], sw1[g], sw2[g]);
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt) {
+      // B fragment (input dimensions x rows): b0 (k = q, n = g), b1 (k = q + 4, n = g)
+      const int o = (8 * nt + g) * stride + ks + q;
+      const uint32_t bh0 = __float_as_uint(xh[o]), bh1 = __float_as_uint(xh[o + 4]);
+      const uint32_t bl0 = __float_as_uint(xl[o]), bl1 = __float_as_uint(xl[o + 4]);
+      t3_mma_tf32(acc[nt], al, bh0, bh1);
+      t3_mma_tf32(acc[nt], ah, bl0, bl1);
+      t3_mma_tf32(acc[nt], ah, bh0, bh1);
+    }
   }
-  if (fc >= 0) t3_store_planes(img, kb, Fp, fc, rg, c0, c1, c2);
-  if (fs >= 0) t3_store_planes(img, kb, Fp, fs, rg, s0, s1, s2);
+  // accumulator fragment: c0 (g, 2q), c1 (g, 2q+1), c2 (g+8, 2q), c3 (g+8, 2q+1) of row tile nt
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    const int k = h ? fB : fA;
+    if (k >= ktot) continue;
+    int kc[16], ksn[16];
+#pragma unroll
+    for (int b = 0; b < 16; ++b) {
+      float sv, cv;
+      t3_sincos_turns(acc[b >> 1][2 * h + (b & 1)], sv, cv);
+      const bool live = n0 + t3_row_of(q, b) < rows;
+      kc[b] = t3_quant(live ? cv : 0.0f);
+      ksn[b] = t3_quant(live ? sv : 0.0f);
+    }
+    const int fc = plan.col_cos[k], fs = plan.col_sin[k];
+    if (fc >= 0) t3_emit(img, kb, Fp, fc, q, kc);
+    if (fs >= 0) t3_emit(img, kb, Fp, fs, q, ksn);
+  }
 }
 
 // ---- int8 SYRK ----------------------------------------------------------------------
@@ -571,8 +653,11 @@ static int tc3_groups(const rr_plan* pl, const S3Shape& s, const float* X, const
   const int d = pl->d, D = s.D;
   const int gy_trig = (pl->ktot + T3_FREQS - 1) / T3_FREQS;
   const int nother = pl->next + 1 + (s.Fp - (D + 1));
-  const int gy_other = (nother + T3_FREQS - 1) / T3_FREQS;
-  const size_t dsmem = (size_t)S3_KB * d * sizeof(float);
+  const int gy_other = (nother + T3_OTHER - 1) / T3_OTHER;
+  const size_t dsmem = (size_t)2 * S3_KB * (((d + 7) & ~7) + 4) * sizeof(float);
+  if (dsmem > 48 * 1024)
+    RR_CUDA_CHECK(cudaFuncSetAttribute(t3_digits_kernel,
+                                       cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dsmem));
   int g = 0;
   int64_t step = 0;
   for (int64_t r0 = 0; r0 < N; r0 += step, ++g) {
