@@ -254,6 +254,27 @@ int rr_glm_predict(const rr_plan* plan, const float* X, int64_t N,
                    const float* larg, float* Ey, float* Ey2, void* workspace,
                    size_t workspace_bytes, void* stream);
 
+/*
+ * Monte-Carlo predictive CDF (glm.py:468-516): for latent draws F (N, S) --
+ * f = Phi(X*) w_s, as rr_glm_predict forms them -- mean / min / max over the draws
+ * of likelihood.cdf(quantile, f) (likelihoods.py:129-146, 235-254, 398-419,
+ * 523-541).  p_min / p_max may be NULL.
+ */
+int rr_glm_cdf(const float* F, int64_t N, int32_t S, int32_t lik, float lik_param,
+               const float* larg, double quantile, float* p_mean, float* p_min,
+               float* p_max, void* stream);
+
+/*
+ * Predictive interval (glm.py:518-570 with _rootfinding :669-694): per row the two
+ * roots of  mean_s cdf(q | f_s) = lo_p, hi_p  inside +-1000 max(mean_s Ey(f_s), 1),
+ * all rows bisected concurrently on the device instead of brentq in a process
+ * pool.  NaN where the bracket holds no sign change (the reference's ValueError
+ * branch).  ql, qu: (N) float64.
+ */
+int rr_glm_quantiles(const float* F, int64_t N, int32_t S, int32_t lik, float lik_param,
+                     const float* larg, double lo_p, double hi_p, double* ql, double* qu,
+                     void* stream);
+
 /* Workspace query: op is one of the RR_OP_* codes. */
 #define RR_OP_SUFFSTATS 1
 #define RR_OP_GRADPASS 2

@@ -545,6 +545,62 @@ def lik_Ey(lik, f, arg=None):
 # Generalised linear model: AEVB ELBO step
 # --------------------------------------------------------------------------
 
+def lik_cdf(lik, q, f, lik_param=None, arg=None):
+    """Likelihood CDFs: revrand/likelihoods.py:129-146 (Bernoulli), :235-254
+    (Binomial), :398-419 (Gaussian), :523-541 (Poisson)."""
+    from scipy.stats import bernoulli, binom, norm, poisson
+    if lik == LIK_GAUSSIAN:
+        return norm.cdf(q, loc=f, scale=np.sqrt(lik_param))
+    if lik == LIK_BERNOULLI:
+        return bernoulli.cdf(q, expit(f))
+    if lik == LIK_BINOMIAL:
+        return binom.cdf(q, n=arg, p=expit(f))
+    if lik == LIK_POISSON_EXP:
+        return poisson.cdf(q, mu=np.exp(f))
+    if lik == LIK_POISSON_SOFTPLUS:
+        return poisson.cdf(q, mu=softplus(f))
+    raise ValueError(lik)
+
+
+def glm_predict_moments(F, lik, arg=None):
+    """Ey, Vy from latent draws F (N, S); revrand/glm.py:404-418."""
+    a = None if arg is None else np.asarray(arg)[:, None]
+    ys = lik_Ey(lik, F, a)
+    Ey = ys.mean(axis=1)
+    return Ey, ((ys - Ey[:, None]) ** 2).mean(axis=1)
+
+
+def glm_predict_cdf(F, lik, quantile, lik_param=None, arg=None):
+    """(mean, min, max) over the draws of cdf(quantile | f); revrand/glm.py:499-516."""
+    a = None if arg is None else np.asarray(arg)[:, None]
+    ps = lik_cdf(lik, quantile, F, lik_param, a)
+    return ps.mean(axis=1), ps.min(axis=1), ps.max(axis=1)
+
+
+def glm_predict_interval(F, lik, percentile, lik_param=None, arg=None):
+    """Per-row brentq roots of the Monte-Carlo CDF; revrand/glm.py:669-694
+    (``_rootfinding``) applied to every row as :546-570 does."""
+    from scipy.optimize import brentq
+    N = F.shape[0]
+    lp = (1 - percentile) / 2
+    up = 1 - lp
+    ql, qu = np.empty(N), np.empty(N)
+    for n in range(N):
+        fn = F[n]
+        an = None if arg is None else arg[n]
+
+        def gap(q, pct):
+            return lik_cdf(lik, q, fn, lik_param, an).mean() - pct
+        Eyn = lik_Ey(lik, fn, an).mean()
+        lb, ub = -1000 * max(Eyn, 1), 1000 * max(Eyn, 1)
+        for out, pct in ((ql, lp), (qu, up)):
+            try:
+                out[n] = brentq(gap, a=lb, b=ub, args=(pct,))
+            except ValueError:
+                out[n] = np.nan
+    return ql, qu
+
+
 def qmatrix(m, C):
     """log N(m_i; m_j, diag(C_i + C_j)); revrand/glm.py:697-712."""
     K = m.shape[1]

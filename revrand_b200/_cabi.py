@@ -65,6 +65,9 @@ SIGNATURES = {
                               _I32, _F32, _P, _P, _P, _P, _P, _P, _SZ, _P]),
     "rr_glm_predict": (C.c_int, [_PLAN, _P, _I64, _P, _I32, _I32, _F32, _P, _P,
                                  _P, _P, _SZ, _P]),
+    "rr_glm_cdf": (C.c_int, [_P, _I64, _I32, _I32, _F32, _P, C.c_double, _P, _P, _P, _P]),
+    "rr_glm_quantiles": (C.c_int, [_P, _I64, _I32, _I32, _F32, _P, C.c_double,
+                                   C.c_double, _P, _P, _P]),
     "rr_workspace_bytes": (_SZ, [_I32, _I64, _I32, _I32, _I32, _I32, _I32, _I32]),
     "rr_tcgen05_supported": (C.c_int, [_I32, _I32, _I32, _I32]),
     "rr_tcgen05_selftest": (C.c_int, [C.POINTER(C.c_double)]),

@@ -375,9 +375,11 @@ def gm_grad(Xd, V, mean, lenscale):
     shape = (N, 4 * n) if d == 1 else (N, 4 * n, d)
     dm = t.empty(shape, dtype=t.float32, device=Xd.device)
     dl = t.empty(shape, dtype=t.float32, device=Xd.device)
-    check(lib.rr_gm_grad(_ptr(Xd), N, d, _ptr(to_device(V)), n, _ptr(to_device(mean)),
-                         _ptr(to_device(lenscale)), _ptr(dm), _ptr(dl), _stream_ptr()),
-          "rr_gm_grad")
+    # (keep the uploads alive until the launch: a temporary's block would be
+    # recycled by the next upload)
+    Vd, md, ld = to_device(V), to_device(mean), to_device(lenscale)
+    check(lib.rr_gm_grad(_ptr(Xd), N, d, _ptr(Vd), n, _ptr(md), _ptr(ld), _ptr(dm),
+                         _ptr(dl), _stream_ptr()), "rr_gm_grad")
     return dm, dl
 
 
@@ -512,6 +514,29 @@ def glm_predict(plan, Xd, ws_draws, lik, lik_param, largd=None, want_sq=False):
                              _ptr(Ey), _ptr(Ey2), _ptr(wsb), wsb.numel(),
                              _stream_ptr()), "rr_glm_predict")
     return Ey, Ey2
+
+
+def glm_cdf(Fd, lik, lik_param, quantile, largd=None):
+    """mean / min / max over the draws (columns of Fd) of cdf(quantile | f)."""
+    t = require_cuda()
+    N, S = Fd.shape
+    out = [t.empty(N, dtype=t.float32, device=Fd.device) for _ in range(3)]
+    check(_cabi.load().rr_glm_cdf(_ptr(Fd), N, S, int(lik), float(lik_param), _ptr(largd),
+                                  float(quantile), _ptr(out[0]), _ptr(out[1]), _ptr(out[2]),
+                                  _stream_ptr()), "rr_glm_cdf")
+    return out
+
+
+def glm_quantiles(Fd, lik, lik_param, lo_p, hi_p, largd=None):
+    """Per-row roots of the Monte-Carlo predictive CDF at lo_p and hi_p."""
+    t = require_cuda()
+    N, S = Fd.shape
+    ql = t.empty(N, dtype=t.float64, device=Fd.device)
+    qu = t.empty(N, dtype=t.float64, device=Fd.device)
+    check(_cabi.load().rr_glm_quantiles(_ptr(Fd), N, S, int(lik), float(lik_param),
+                                        _ptr(largd), float(lo_p), float(hi_p), _ptr(ql),
+                                        _ptr(qu), _stream_ptr()), "rr_glm_quantiles")
+    return ql, qu
 
 
 def tcgen05_selftest():

@@ -173,6 +173,169 @@ predict_reduce_kernel(const float* __restrict__ F, int rows, int S, int lik,
   }
 }
 
+// ---- predictive CDF and quantiles (glm.py:468-570, 669-694) ---------------------
+// Discrete CDFs sum the pmf outward from the side of floor(q) that holds the
+// smaller tail, in float64, starting from a log-space pmf value: O(sqrt(mean))
+// terms, no under/overflow for any rate.
+
+// P(Y <= q), Y ~ Poisson(mu)                               (scipy.stats.poisson.cdf)
+__device__ double poisson_cdf(double q, double mu) {
+  if (q < 0.0) return 0.0;
+  if (!(mu > 0.0)) return 1.0;
+  const double kq = floor(q);
+  const double span = 12.0 * sqrt(mu) + 40.0;
+  if (kq >= mu + span) return 1.0;
+  if (kq < mu - span) return 0.0;
+  if (kq >= floor(mu)) {       // upper tail is the small side: 1 - sum_{k > kq} pmf
+    double k = kq + 1.0;
+    double p = exp(k * log(mu) - mu - lgamma(k + 1.0));
+    double tail = 0.0;
+    for (int it = 0; it < 100000 && p > 1e-18 * (tail + 1e-300); ++it) {
+      tail += p;
+      k += 1.0;
+      p *= mu / k;
+    }
+    return fmax(0.0, 1.0 - tail);
+  }
+  double k = kq;
+  double p = exp(k * log(mu) - mu - lgamma(k + 1.0));
+  double sum = 0.0;
+  for (int it = 0; it < 100000 && k >= 0.0 && p > 1e-18 * (sum + 1e-300); ++it) {
+    sum += p;
+    p *= k / mu;
+    k -= 1.0;
+  }
+  return fmin(1.0, sum);
+}
+
+// P(Y <= q), Y ~ Binomial(n, pr)                             (scipy.stats.binom.cdf)
+__device__ double binom_cdf(double q, double n, double pr) {
+  if (q < 0.0) return 0.0;
+  const double kq = floor(q);
+  if (kq >= n) return 1.0;
+  if (pr <= 0.0) return 1.0;
+  if (pr >= 1.0) return 0.0;
+  const double lp = log(pr), lq = log1p(-pr), odds = pr / (1.0 - pr);
+  const double mode = floor((n + 1.0) * pr);
+  auto lpmf = [&](double k) {
+    return lgamma(n + 1.0) - lgamma(k + 1.0) - lgamma(n - k + 1.0) + k * lp + (n - k) * lq;
+  };
+  if (kq >= mode) {
+    double k = kq + 1.0;
+    double p = exp(lpmf(k));
+    double tail = 0.0;
+    for (int it = 0; it < 100000 && k <= n && p > 1e-18 * (tail + 1e-300); ++it) {
+      tail += p;
+      p *= (n - k) / (k + 1.0) * odds;
+      k += 1.0;
+    }
+    return fmax(0.0, 1.0 - tail);
+  }
+  double k = kq;
+  double p = exp(lpmf(k));
+  double sum = 0.0;
+  for (int it = 0; it < 100000 && k >= 0.0 && p > 1e-18 * (sum + 1e-300); ++it) {
+    sum += p;
+    p *= k / ((n - k + 1.0) * odds);
+    k -= 1.0;
+  }
+  return fmin(1.0, sum);
+}
+
+// likelihoods.py: cdf of Bernoulli :129-146, Binomial :235-254, Gaussian :398-419,
+// Poisson :523-541.
+__device__ double lik_cdf(int lik, double q, float f, float par, float arg) {
+  switch (lik) {
+    case RR_LIK_GAUSSIAN:
+      return normcdf((q - (double)f) / sqrt((double)par));
+    case RR_LIK_BERNOULLI: {
+      const double pr = 1.0 / (1.0 + exp(-(double)f));
+      return q < 0.0 ? 0.0 : (q < 1.0 ? 1.0 - pr : 1.0);
+    }
+    case RR_LIK_BINOMIAL:
+      return binom_cdf(q, (double)arg, 1.0 / (1.0 + exp(-(double)f)));
+    case RR_LIK_POISSON_EXP:
+      return poisson_cdf(q, exp((double)f));
+    default: {
+      const double ff = (double)f;
+      return poisson_cdf(q, fmax(ff, 0.0) + log1p(exp(-fabs(ff))));
+    }
+  }
+}
+
+// Warp per row: mean / min / max over the draws of cdf(quantile | f).
+__global__ void __launch_bounds__(256)
+glm_cdf_kernel(const float* __restrict__ F, int rows, int S, int lik, float par,
+               const float* __restrict__ larg, double quantile, float* __restrict__ pm,
+               float* __restrict__ pmin, float* __restrict__ pmax) {
+  const int r = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (r >= rows) return;
+  const float arg = larg ? larg[r] : 0.0f;
+  double a = 0.0, lo = 2.0, hi = -1.0;
+  for (int s = lane; s < S; s += 32) {
+    const double c = lik_cdf(lik, quantile, F[(int64_t)r * S + s], par, arg);
+    a += c;
+    lo = fmin(lo, c);
+    hi = fmax(hi, c);
+  }
+  a = warp_sum(a);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    lo = fmin(lo, __shfl_xor_sync(0xffffffffu, lo, o));
+    hi = fmax(hi, __shfl_xor_sync(0xffffffffu, hi, o));
+  }
+  if (lane == 0) {
+    pm[r] = (float)(a / S);
+    if (pmin) pmin[r] = (float)lo;
+    if (pmax) pmax[r] = (float)hi;
+  }
+}
+
+// Warp per row: both ends of the central `percentile` interval of the Monte-Carlo
+// predictive distribution, i.e. the roots of  mean_s cdf(q | f_s) - p  for
+// p = (1 -+ percentile) / 2 inside the reference's bracket +-1000 max(E[y], 1)
+// (glm.py:681-683), by bisection (the function is monotone in q; for discrete
+// likelihoods it is a step function and the root is the jump that brentq also
+// converges to).  NaN where the bracket holds no sign change, as the reference.
+__global__ void __launch_bounds__(256)
+glm_quantile_kernel(const float* __restrict__ F, int rows, int S, int lik, float par,
+                    const float* __restrict__ larg, double lo_p, double hi_p,
+                    double* __restrict__ ql, double* __restrict__ qu) {
+  const int r = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (r >= rows) return;
+  const float arg = larg ? larg[r] : 0.0f;
+  const float* fr = F + (int64_t)r * S;
+  double ey = 0.0;
+  for (int s = lane; s < S; s += 32) ey += (double)lik_Ey(lik, fr[s], arg);
+  ey = warp_sum(ey) / S;
+  const double bound = 1000.0 * fmax(ey, 1.0);
+  auto gap = [&](double q, double pct) {
+    double a = 0.0;
+    for (int s = lane; s < S; s += 32) a += lik_cdf(lik, q, fr[s], par, arg);
+    return warp_sum(a) / S - pct;
+  };
+  for (int side = 0; side < 2; ++side) {
+    const double pct = side ? hi_p : lo_p;
+    double a = -bound, b = bound;
+    const double ga = gap(a, pct), gb = gap(b, pct);
+    double root = nan("");
+    if (ga == 0.0) root = a;
+    else if (gb == 0.0) root = b;
+    else if ((ga < 0.0) != (gb < 0.0)) {
+      for (int it = 0; it < 200 && (b - a) > 4e-12 + 8.9e-16 * fabs(b); ++it) {   // brentq's xtol, 4 rtol
+        const double mid = 0.5 * (a + b);
+        const double gm = gap(mid, pct);
+        if ((gm < 0.0) == (ga < 0.0)) a = mid;
+        else b = mid;
+      }
+      root = 0.5 * (a + b);
+    }
+    if (lane == 0) (side ? qu : ql)[r] = root;
+  }
+}
+
 size_t glm_workspace_bytes(int op, int64_t M, const rr_plan* pl, int S) {
   int64_t R = M < GLM_CHUNK ? M : GLM_CHUNK;
   if (R < 1) R = 1;
@@ -278,5 +441,33 @@ extern "C" int rr_glm_predict(const rr_plan* plan, const float* X, int64_t N,
         F, rows, S, lik, larg ? larg + s : nullptr, Ey + s, Ey2 ? Ey2 + s : nullptr);
     RR_LAUNCH_CHECK("predict_reduce_kernel");
   }
+  return RR_OK;
+}
+
+extern "C" int rr_glm_cdf(const float* F, int64_t N, int32_t S, int32_t lik, float lik_param,
+                          const float* larg, double quantile, float* p_mean, float* p_min,
+                          float* p_max, void* stream) {
+  RR_REQUIRE(F && p_mean, "null pointer");
+  RR_REQUIRE(S > 0, "no draws");
+  RR_REQUIRE(lik >= 0 && lik <= RR_LIK_POISSON_SOFTPLUS, "unknown likelihood");
+  RR_REQUIRE(lik != RR_LIK_BINOMIAL || larg, "Binomial needs its n argument");
+  if (N == 0) return RR_OK;
+  glm_cdf_kernel<<<(unsigned)((N + 7) / 8), 256, 0, (cudaStream_t)stream>>>(
+      F, (int)N, S, lik, lik_param, larg, quantile, p_mean, p_min, p_max);
+  RR_LAUNCH_CHECK("glm_cdf_kernel");
+  return RR_OK;
+}
+
+extern "C" int rr_glm_quantiles(const float* F, int64_t N, int32_t S, int32_t lik,
+                                float lik_param, const float* larg, double lo_p, double hi_p,
+                                double* ql, double* qu, void* stream) {
+  RR_REQUIRE(F && ql && qu, "null pointer");
+  RR_REQUIRE(S > 0, "no draws");
+  RR_REQUIRE(lik >= 0 && lik <= RR_LIK_POISSON_SOFTPLUS, "unknown likelihood");
+  RR_REQUIRE(lik != RR_LIK_BINOMIAL || larg, "Binomial needs its n argument");
+  if (N == 0) return RR_OK;
+  glm_quantile_kernel<<<(unsigned)((N + 7) / 8), 256, 0, (cudaStream_t)stream>>>(
+      F, (int)N, S, lik, lik_param, larg, lo_p, hi_p, ql, qu);
+  RR_LAUNCH_CHECK("glm_quantile_kernel");
   return RR_OK;
 }

@@ -18,7 +18,6 @@ import logging
 from itertools import chain
 
 import numpy as np
-from scipy.optimize import brentq
 from scipy.stats.distributions import gamma, norm
 from sklearn.base import BaseEstimator, RegressorMixin
 from sklearn.utils import check_random_state
@@ -329,8 +328,8 @@ class GeneralizedLinearModel(BaseEstimator, RegressorMixin):
         Vy = np.maximum(Ey2.double().cpu().numpy() - Ey ** 2, 0.0)
         return Ey, Vy
 
-    def _sample_f(self, X, nsamples):
-        """Latent function draws f (N, nsamples) as a numpy array."""
+    def _sample_f_dev(self, X, nsamples):
+        """Latent function draws f (N, nsamples), float32, on the device."""
         check_is_fitted(self, ['weights_', 'covariance_', 'basis_hypers_',
                                'like_hypers_', 'regularizer_'])
         X = check_array(X)
@@ -338,7 +337,11 @@ class GeneralizedLinearModel(BaseEstimator, RegressorMixin):
         plan = self._fitted_plan(X.shape[1])
         Phi = eng.features(plan, eng.to_device(X)).double()
         F = Phi @ eng.to_device(w, eng.torch().float64)
-        return F.cpu().numpy()
+        return F.float().contiguous()
+
+    def _sample_f(self, X, nsamples):
+        """Latent function draws f (N, nsamples) as a numpy array."""
+        return self._sample_f_dev(X, nsamples).double().cpu().numpy()
 
     def _sample_func(self, X, nsamples, genaxis=1):
         F = self._sample_f(X, nsamples)
@@ -359,38 +362,36 @@ class GeneralizedLinearModel(BaseEstimator, RegressorMixin):
             for a in self._largs_tuple(likelihood_args)])
         return ps.mean(axis=1), ps.min(axis=1), ps.max(axis=1)
 
+    def _larg_dev(self, likelihood_args, N):
+        largs = _reshape_likelihood_args(likelihood_args, N)
+        if len(largs) > 1:
+            raise NotImplementedError("device likelihoods take at most one per-row argument")
+        return eng.to_device(np.asarray(largs[0], float)) if largs else None
+
     def predict_cdf(self, X, quantile, nsamples=200, likelihood_args=()):
-        F = self._sample_f(X, nsamples)
-        ps = self.likelihood.cdf(quantile, F, *[
-            np.asarray(a)[:, None] if np.ndim(a) else a
-            for a in self._largs_tuple(likelihood_args)])
-        return ps.mean(axis=1), ps.min(axis=1), ps.max(axis=1)
+        """Monte-Carlo predictive CDF P(y* <= quantile) and its min / max over
+        the draws (glm.py:468-516); the likelihood CDF runs on the device."""
+        _check_device_likelihood(self.likelihood, _aslist(self.like_hypers_),
+                                 likelihood_args)
+        F = self._sample_f_dev(X, nsamples)
+        p, pmin, pmax = eng.glm_cdf(F, self.likelihood._lik_id, self._lik_param(),
+                                    quantile, self._larg_dev(likelihood_args, F.shape[0]))
+        return tuple(v.double().cpu().numpy() for v in (p, pmin, pmax))
 
     def predict_interval(self, X, percentile, nsamples=200, likelihood_args=(),
                          multiproc=True):
-        """Predictive quantile interval by root finding on the Monte-Carlo CDF
-        (glm.py:518-570, 669-694); rows are processed serially on the host."""
-        N = np.shape(X)[0]
-        F = self._sample_f(X, nsamples)
-        largs = _reshape_likelihood_args(likelihood_args, N)
-        hyp = _aslist(self.like_hypers_)
+        """Predictive quantile interval (glm.py:518-570, 669-694): the roots of
+        the Monte-Carlo CDF at (1 -+ percentile) / 2 inside the reference's
+        bracket, all query rows bisected concurrently on the device (the
+        reference farms brentq out to a process pool; ``multiproc`` is accepted
+        and ignored)."""
+        _check_device_likelihood(self.likelihood, _aslist(self.like_hypers_),
+                                 likelihood_args)
+        F = self._sample_f_dev(X, nsamples)
         lo_p = (1 - percentile) / 2
-        hi_p = 1 - lo_p
-        ql, qu = np.empty(N), np.empty(N)
-        for n in range(N):
-            args = tuple(chain(hyp, (a[n] for a in largs)))
-            fn = F[n]
-            Eyn = np.mean(self.likelihood.Ey(fn, *args))
-            lb, ub = -1000 * max(Eyn, 1), 1000 * max(Eyn, 1)
-
-            def gap(q, pct):
-                return np.mean(self.likelihood.cdf(q, fn, *args)) - pct
-            for arr, pct in ((ql, lo_p), (qu, hi_p)):
-                try:
-                    arr[n] = brentq(gap, a=lb, b=ub, args=(pct,))
-                except ValueError:
-                    arr[n] = np.nan
-        return ql, qu
+        ql, qu = eng.glm_quantiles(F, self.likelihood._lik_id, self._lik_param(), lo_p,
+                                   1 - lo_p, self._larg_dev(likelihood_args, F.shape[0]))
+        return ql.cpu().numpy(), qu.cpu().numpy()
 
     def __getstate__(self):
         state = dict(self.__dict__)

@@ -137,3 +137,20 @@ def bases2_inputs(d, N):
     ls_ard = 0.6 + rs.rand(d)
     mean = 0.5 * rs.randn(d)
     return X, C, ls_iso, ls_ard, mean
+
+
+# ---- GLM predictive paths ----------------------------
+GLM_PREDICT = dict(N=48, d=3, K=16, Kmix=3, S=150, seed=77, quantile=1.5, percentile=0.9)
+GLM_PREDICT_LIKS = ["gaussian", "bernoulli", "binomial", "poisson_exp", "poisson_softplus"]
+
+
+def glm_predict_inputs(name):
+    sh = GLM_PREDICT
+    rs = np.random.RandomState(8000 + GLM_PREDICT_LIKS.index(name))
+    X = rs.randn(sh["N"], sh["d"])
+    D = 2 * sh["K"]
+    w = 0.6 * rs.randn(D, sh["Kmix"])
+    C = 0.02 + 0.05 * rs.rand(D, sh["Kmix"])
+    ls = 0.8 + 0.4 * rs.rand(sh["d"])
+    n = rs.randint(3, 12, size=sh["N"]).astype(float)
+    return dict(X=X, w=w, C=C, ls=ls, n=n, var=0.35)

@@ -682,3 +682,40 @@ def test_models_refuse_feature_map_only_bases():
     b = bf.RadialBasis(centres=np.zeros((3, 2)))
     with pytest.raises(NotImplementedError):
         rr.StandardLinearModel(basis=b).fit(X, y)
+
+
+# ---- GLM predictive paths against the unmodified reference's outputs ---------------
+
+@pytest.mark.parametrize("name", cases.GLM_PREDICT_LIKS)
+def test_glm_predict_moments_cdf_interval_vs_reference(name):
+    """predict_moments / predict_cdf / predict_interval (glm.py:349-418, 468-570)
+    for a hand-set posterior and the reference's seeded weight draws: the feature
+    map, the likelihood link / CDF and the per-row root finding all run on the
+    device; the reference ran brentq per row."""
+    import os
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "glm_predict.npz"))
+    sh = cases.GLM_PREDICT
+    inp = cases.glm_predict_inputs(name)
+    basis = bf.RandomRBF(nbases=sh["K"], Xdim=sh["d"], random_state=31,
+                         lenscale=Parameter(inp["ls"], Positive()))
+    glm = rr.GeneralizedLinearModel(likelihood=LIK[name](), basis=basis, K=sh["Kmix"])
+    glm.weights_, glm.covariance_ = inp["w"], inp["C"]
+    glm.basis_hypers_, glm.regularizer_ = inp["ls"], 1.0
+    glm.like_hypers_ = inp["var"] if name == "gaussian" else []
+    largs = (inp["n"],) if name == "binomial" else ()
+    glm.random_ = np.random.RandomState(sh["seed"])
+    Ey, Vy = glm.predict_moments(inp["X"], nsamples=sh["S"], likelihood_args=largs)
+    p, pmin, pmax = glm.predict_cdf(inp["X"], sh["quantile"], nsamples=sh["S"],
+                                    likelihood_args=largs)
+    ql, qu = glm.predict_interval(inp["X"], sh["percentile"], nsamples=sh["S"],
+                                  likelihood_args=largs)
+    np.testing.assert_allclose(Ey, g[name + "/Ey"], rtol=1e-5, atol=1e-6)
+    np.testing.assert_allclose(Vy, g[name + "/Vy"], rtol=2e-4, atol=1e-6)
+    for got, key in ((p, "p"), (pmin, "pmin"), (pmax, "pmax")):
+        np.testing.assert_allclose(got, g[name + "/" + key], rtol=1e-5, atol=2e-6)
+    for got, key in ((ql, "ql"), (qu, "qu")):
+        ref = g[name + "/" + key]
+        assert np.array_equal(np.isnan(got), np.isnan(ref))
+        ok = ~np.isnan(ref)
+        # continuous (Gaussian): the root itself; discrete: the jump both methods sit on
+        np.testing.assert_allclose(got[ok], ref[ok], rtol=1e-4, atol=1e-4)
