@@ -156,6 +156,37 @@ class GeneralizedLinearModel(BaseEstimator, RegressorMixin):
         self._plan_cache = None
         return self
 
+    def svi_stepper(self, X, y, likelihood_args=(), maxiter=10 ** 9):
+        """The loop body of ``fit`` as an object: ``step()`` runs ONE SVI
+        iteration (fresh minibatch gathered on the device, ``_elbo``, update)
+        through exactly the wrappers ``fit`` composes.  For benchmarks and for
+        callers that interleave training with other work."""
+        X, y = check_X_y(X, y)
+        from .basis_functions import require_model_support
+        from .optimize.sgd import SGDRun
+        require_model_support(self.basis)
+        N, _ = X.shape
+        self.B_ = N / self.batch_size
+        self.D_ = self.basis.get_dim(X)
+        likelihood_args = _reshape_likelihood_args(likelihood_args, N)
+        data = (eng.to_device(X), eng.to_device(y)) + tuple(
+            eng.to_device(np.asarray(a, dtype=float)) for a in likelihood_args)
+        params = [Parameter(WGTRND, Bound(), shape=(self.D_, self.K)),
+                  Parameter(COVRND, Positive(), shape=(self.D_, self.K)),
+                  self.basis.regularizer, self.likelihood.params,
+                  self.basis.params]
+        self._it = 1            # > 0: no ELBO logging evaluation on benchmark steps
+        self._plan_cache = None
+        holder = {}
+
+        def capture(fun, x0, data, **kw):
+            holder["run"] = SGDRun(fun, x0, data, **kw)
+            return holder["run"].result()
+        structured_sgd(logtrick_sgd(capture))(
+            self._elbo, params, data, eval_obj=True, maxiter=maxiter, updater=self.updater,
+            batch_size=self.batch_size, random_state=self.random_, nstarts=0)
+        return _SVIStepper(self, holder["run"], X.shape[1])
+
     def _noise(self, Kmix, L, D, dev):
         """Reparameterisation noise eps (K_mix, L, D) as a device tensor.
 
@@ -405,6 +436,47 @@ class GeneralizedLinearModel(BaseEstimator, RegressorMixin):
                 type(self).__name__, self.likelihood, self.basis, self.K,
                 self.maxiter, self.batch_size, self.updater, self.nsamples,
                 self.nstarts, self.random_state)
+
+
+class _SVIStepper(object):
+    """See ``GeneralizedLinearModel.svi_stepper``."""
+
+    def __init__(self, glm, run, d):
+        self.glm, self.run, self.d = glm, run, d
+        D, K = glm.D_, glm.K
+        self.h2d_bytes = int(2 * D * K * 4)            # m, C as float32
+        self.d2h_bytes = int(2 * D * K * 8 + 8 * 64)   # Edm, EdC and the scalars, float64
+
+    def step(self):
+        glm = self.glm
+        if glm._it % LOGITER == 0:   # keep benchmark steps free of the logging ELBO
+            glm._it += 1
+        return self.run.step()
+
+    def device_ms(self, reps=5):
+        """CUDA-event time of the device part of a step (``rr_glm_step`` on one
+        minibatch), without the host assembly and the update."""
+        t = eng.torch()
+        glm = self.glm
+        D, K, L = glm.D_, glm.K, glm.nsamples
+        rs = np.random.RandomState(0)
+        m = eng.to_device(0.1 * rs.randn(D, K))
+        C = eng.to_device(0.05 + 0.1 * np.abs(rs.randn(D, K)))
+        M = glm.batch_size
+        Xb = eng.to_device(rs.randn(M, self.d))
+        yb = eng.to_device(rs.poisson(1.0, size=M).astype(float))
+        plan = glm._get_plan(Xb.shape[1], glm.basis.params_values())
+        eps = glm._noise(K, L, D, Xb.device)
+        lik = glm.likelihood._lik_id
+        ts = []
+        for _ in range(reps + 1):
+            a, b = t.cuda.Event(enable_timing=True), t.cuda.Event(enable_timing=True)
+            a.record()
+            eng.glm_step(plan, Xb, yb, None, m, C, eps, lik, 1.0, want_ll=False, want_R=True)
+            b.record()
+            t.cuda.synchronize()
+            ts.append(a.elapsed_time(b))
+        return float(np.mean(ts[1:]))
 
 
 class GeneralisedLinearModel(GeneralizedLinearModel):

@@ -172,37 +172,62 @@ def gen_batch(data, batch_size, maxiter=np.inf, random_state=None):
             yield [dd[ind] for dd in data]
 
 
+class SGDRun(object):
+    """State of one SGD run, advanced one minibatch at a time (``sgd`` below is
+    the loop over it; benchmarks call ``step`` themselves)."""
+
+    def __init__(self, fun, x0, data, args=(), bounds=None, batch_size=10,
+                 maxiter=5000, updater=None, eval_obj=False, random_state=None):
+        self.fun, self.args, self.eval_obj = fun, args, eval_obj
+        self.updater = Adam() if updater is None else updater
+        self.updater.reset()
+        N = _len_data(data)
+        self.x = np.array(x0, copy=True, dtype=float)
+        self.lower = self.upper = None
+        if bounds is not None:
+            if len(bounds) != self.x.shape[0]:
+                raise ValueError("The dimension of the bounds does not match x0!")
+            self.lower = np.array([-np.inf if b[0] is None else b[0] for b in bounds])
+            self.upper = np.array([np.inf if b[1] is None else b[1] for b in bounds])
+        self.obj, self.objs, self.norms = None, [], []
+        self.batches = gen_batch(data, min(batch_size, N), maxiter, random_state)
+
+    def step(self):
+        """One minibatch: objective / gradient, bound-aware truncation, update,
+        clip (sgd.py:380-415).  Returns False when the batches are exhausted."""
+        batch = next(self.batches, None)
+        if batch is None:
+            return False
+        x = self.x
+        if self.eval_obj:
+            self.obj, grad = self.fun(x, *chain(batch, self.args))
+            self.objs.append(self.obj)
+        else:
+            grad = self.fun(x, *chain(batch, self.args))
+        self.norms.append(np.linalg.norm(grad))
+        if self.lower is not None:
+            at_lo, at_hi = x <= self.lower, x >= self.upper
+            grad[at_lo] = np.minimum(grad[at_lo], 0)
+            grad[at_hi] = np.maximum(grad[at_hi], 0)
+        x = self.updater(x, grad)
+        if self.lower is not None:
+            x = np.clip(x, self.lower, self.upper)
+        self.x = x
+        return True
+
+    def result(self):
+        return OptimizeResult(x=self.x, norms=self.norms, message='maxiter reached',
+                              fun=self.obj, objs=self.objs)
+
+
 def sgd(fun, x0, data, args=(), bounds=None, batch_size=10, maxiter=5000,
         updater=None, eval_obj=False, random_state=None):
     """Minimise ``fun`` by SGD over minibatches of ``data`` (sgd.py:311-425):
     bound-aware gradient truncation, update, clip; returns an
     ``OptimizeResult`` with ``x``, ``norms``, ``objs``, ``fun``."""
-    if updater is None:
-        updater = Adam()
-    updater.reset()
-    N = _len_data(data)
-    x = np.array(x0, copy=True, dtype=float)
-    batch_size = min(batch_size, N)
-    lower = upper = None
-    if bounds is not None:
-        if len(bounds) != x.shape[0]:
-            raise ValueError("The dimension of the bounds does not match x0!")
-        lower = np.array([-np.inf if b[0] is None else b[0] for b in bounds])
-        upper = np.array([np.inf if b[1] is None else b[1] for b in bounds])
-    obj, objs, norms = None, [], []
-    for batch in gen_batch(data, batch_size, maxiter, random_state):
-        if eval_obj:
-            obj, grad = fun(x, *chain(batch, args))
-            objs.append(obj)
-        else:
-            grad = fun(x, *chain(batch, args))
-        norms.append(np.linalg.norm(grad))
-        if bounds is not None:
-            at_lo, at_hi = x <= lower, x >= upper
-            grad[at_lo] = np.minimum(grad[at_lo], 0)
-            grad[at_hi] = np.maximum(grad[at_hi], 0)
-        x = updater(x, grad)
-        if bounds is not None:
-            x = np.clip(x, lower, upper)
-    return OptimizeResult(x=x, norms=norms, message='maxiter reached', fun=obj,
-                          objs=objs)
+    run = SGDRun(fun, x0, data, args=args, bounds=bounds, batch_size=batch_size,
+                 maxiter=maxiter, updater=updater, eval_obj=eval_obj,
+                 random_state=random_state)
+    while run.step():
+        pass
+    return run.result()
