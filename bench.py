@@ -12,7 +12,7 @@ pass, second allreduce, host assembly.  Rows of X are sharded contiguously over
 the ranks (total N fixed => strong scaling).
 
   python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
-                  [--workload config2|config4]
+                  [--workload config2|config4|config5]
 """
 
 from __future__ import annotations
@@ -353,7 +353,7 @@ def run_ours(args):
     del prob
     Xh = torch.from_numpy(X).pin_memory()
     yh = torch.from_numpy(y).pin_memory()
-    Xn, yn = Xh.numpy(), yh.numpy()          # numpy views of the pinned buffers
+    Xn, yn = Xh, yh                          # pinned host tensors (array-likes of the API)
     slm = StandardLinearModel(basis=basis)
     slm.obj_ = -np.inf
     old_cache = config.CACHE_DEVICE_DATA
@@ -430,8 +430,10 @@ def main():
     ap.add_argument("--steps", type=int, default=6)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="config2", choices=["config2", "config4"])
-    ap.add_argument("--N", type=int, default=1000000)
+    ap.add_argument("--workload", default="config2", choices=["config2", "config4", "config5"])
+    ap.add_argument("--N", type=int, default=None)
+    ap.add_argument("--Ks", default="512,1024,2048,4096,8192",
+                    help="config5: comma-separated list of nbases to sweep")
     ap.add_argument("--d", type=int, default=21)
     ap.add_argument("--K", type=int, default=2048)
     ap.add_argument("--cpu-sample", type=int, default=40000)
@@ -441,11 +443,16 @@ def main():
                     help="--impl reference: also time the unmodified reference where importable")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
+    if args.N is None:
+        args.N = 10000000 if args.workload == "config5" else 1000000
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3
     if args.workload == "config4":
         import bench_glm
         return bench_glm.main(args)
+    if args.workload == "config5":
+        import bench_config5
+        return bench_config5.main(args)
     if args.impl == "reference":
         run_reference(args)
     else:

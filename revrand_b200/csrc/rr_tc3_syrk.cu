@@ -96,8 +96,16 @@ t3_scales_kernel(const float* __restrict__ X, const float* __restrict__ y, int64
     }
   }
   __syncthreads();
+  // The scale is the next power of two >= the maximum: row shards of one data set
+  // (ranks of a sharded job) then almost always agree on it although their maxima
+  // differ, which makes their quantised statistics add up to the one-process result
+  // bit for bit; the price is at most one of the 23 bits.
   for (int i = threadIdx.x; i <= d; i += blockDim.x)
-    if (smax[i]) atomicMax(&scales[i], smax[i]);
+    if (smax[i]) {
+      const uint32_t b = smax[i];
+      const uint32_t up = (b & 0x007FFFFFu) ? ((b & 0x7F800000u) + 0x00800000u) : b;
+      atomicMax(&scales[i], up < 0x7F800000u ? up : b);
+    }
 }
 
 // camp[f] = real amplitude of integer feature f (f <= D; f == D is the y column).

@@ -82,6 +82,8 @@ class _SLMProblem(object):
         lo, hi = eng.shard_rows(self.N_total, self.rank, self.world)
 
         def host(a):
+            if isinstance(a, t.Tensor):          # e.g. a pinned staging tensor
+                return a[lo:hi]
             a = np.ascontiguousarray(a[lo:hi])
             if a.dtype not in (np.float32, np.float64):
                 a = a.astype(np.float64)
@@ -89,7 +91,7 @@ class _SLMProblem(object):
         self.Xd.copy_(host(X), non_blocking=True)
         self.yd.copy_(host(y), non_blocking=True)
         self.yy = None
-        self.Xhost_probe = np.asarray(X[:1], dtype=float)
+        self.Xhost_probe = np.asarray(X[:1], dtype=float).reshape(1, -1)
 
     def uses_tcgen05(self):
         """True when this problem's value pass runs on the tensor cores
@@ -257,13 +259,17 @@ class StandardLinearModel(BaseEstimator, RegressorMixin):
         prob = getattr(self, "_problem", None)
         if prob is not None:
             return prob
+        if not hasattr(X, "shape"):
+            X = np.asarray(X, dtype=float)
+        if not hasattr(y, "shape"):
+            y = np.asarray(y, dtype=float)
         cached = getattr(self, "_cached_problem", None)
         key = self._fingerprint(X, y) if config.CACHE_DEVICE_DATA else None
         if cached is not None and key is not None and \
                 getattr(self, "_problem_key", None) == key:
             return cached
         if cached is not None and cached.basis is self.basis and \
-                (cached.N_total, cached.d) == tuple(np.shape(X)):
+                (cached.N_total, cached.d) == tuple(X.shape):
             cached.upload(X, y)
         else:
             self._cached_problem = cached = _SLMProblem(self.basis, X, y)
