@@ -109,6 +109,9 @@ int sgemm(int M, int N, int K, float alpha, const float* A, int64_t sAm,
           int64_t sAk, const float* B, int64_t sBk, int64_t sBn, float* Cf,
           double* Cd, int64_t ldc, int accumulate, cudaStream_t st);
 
+// R (d x kt, float64) += X^T Q for row-major fp32 X (rows x d), Q (rows x kt).
+int xtq(const float* X, const float* Q, int rows, int d, int kt, double* R, cudaStream_t st);
+
 int launch_features(const rr_plan* plan, const float* X, int64_t N, float* Phi,
                     int64_t ldphi, cudaStream_t st);
 

@@ -404,8 +404,7 @@ extern "C" int rr_glm_step(const rr_plan* plan, const float* X, const float* y,
       dim3 qg((kt + 255) / 256, rows);
       q_plain_kernel<<<qg, 256, 0, st>>>(*plan, Phi, T, D, rows, Q);
       RR_LAUNCH_CHECK("q_plain_kernel");
-      rc = sgemm(d, kt, rows, 1.0f, X + s * d, 1, d, Q, kt, 1, nullptr, Rout, kt,
-                 1, st);
+      rc = xtq(X + s * d, Q, rows, d, kt, Rout, st);
       if (rc) return rc;
     }
   }

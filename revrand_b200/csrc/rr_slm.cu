@@ -159,7 +159,7 @@ static int simt_gradpass(const rr_plan* pl, const float* X, const float* y,
     q_kernel<<<grid, 256, 0, st>>>(*pl, Phi, T, D, rows, err + s, m, Q);
     RR_LAUNCH_CHECK("q_kernel");
     // R += X^T Q : A'(i,r) = X[r*d + i], B'(r,k) = Q[r*kt + k]
-    rc = sgemm(d, kt, rows, 1.0f, X + s * d, 1, d, Q, kt, 1, nullptr, Rout, kt, 1, st);
+    rc = xtq(X + s * d, Q, rows, d, kt, Rout, st);
     if (rc) return rc;
   }
   return RR_OK;
