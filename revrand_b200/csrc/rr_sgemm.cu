@@ -1,8 +1,10 @@
-// Generic strided fp32 GEMM, used by the chunked SIMT engine (any feature plan)
-// and by the GLM step.  128x128x16 block tile, 256 threads.  float64 outputs
-// (long row sums feeding the posterior solve) accumulate exact fp32 products in
-// float64 on the CUDA cores, 8x8 register tile per thread; fp32 outputs run on
-// the tensor cores (mma.sync tf32, three-product split).
+// Generic strided fp32 GEMM on CUDA cores (FFMA), used by the chunked SIMT
+// engine (any feature plan) and by the GLM step.  128x128x16 block tile, 256
+// threads, 8x8 register tile per thread, fp32 accumulation, optional float64
+// read-modify-write epilogue so long row sums are carried in double.  (An
+// mma.sync tf32 three-product variant for the fp32 outputs was measured at
+// 1.65 ms against 0.99 ms for this kernel on the GLM step's GEMMs -- 182
+// registers, one block per SM -- and dropped.)
 #include <type_traits>
 
 #include "rr_common.cuh"
@@ -101,124 +103,6 @@ sgemm_kernel(int M, int N, int K, float alpha, const float* __restrict__ A,
   }
 }
 
-// ---------------------------------------------------------------------------
-// fp32-output variant on the tensor cores: mma.sync m16n8k8 tf32 with the
-// three-product split  hi*hi + lo*hi + hi*lo  of tf32-rounded operands (about 21
-// bits per product: fp32 grade for the fp32 outputs it serves).  Same block tile
-// and global -> shared staging as above; the operands are split once when they
-// are staged.  8 warps as 2 x 4, warp tile 64 x 32 = 4 x 4 mma tiles.
-// ---------------------------------------------------------------------------
-constexpr int GT_PAD = 8;    // row pitch 136 floats: fragment loads touch 32 distinct banks
-
-__device__ __forceinline__ float tf32_round(float x) {
-  return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xFFFFE000u);
-}
-__device__ __forceinline__ void mma_tf32(float (&c)[4], const uint32_t (&a)[4], uint32_t b0,
-                                         uint32_t b1) {
-  asm volatile(
-      "mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, "
-      "{%8, %9}, {%0, %1, %2, %3};"
-      : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
-      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
-}
-
-__global__ void __launch_bounds__(G_THREADS)
-sgemm_tf32x3_kernel(int M, int N, int K, float alpha, const float* __restrict__ A,
-                    int64_t sAm, int64_t sAk, const float* __restrict__ B, int64_t sBk,
-                    int64_t sBn, float* __restrict__ Cf, int64_t ldc, int accumulate) {
-  __shared__ float Ah[GB_K][GB_M + GT_PAD], Al[GB_K][GB_M + GT_PAD];
-  __shared__ float Bh[GB_K][GB_N + GT_PAD], Bl[GB_K][GB_N + GT_PAD];
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int m0 = blockIdx.y * GB_M, n0 = blockIdx.x * GB_N;
-  const int wm = (warp >> 2) * 64, wn = (warp & 3) * 32;   // warp tile origin in the block tile
-  const int g = lane >> 2, q = lane & 3;
-  float acc[4][4][4];
-#pragma unroll
-  for (int i = 0; i < 4; ++i)
-#pragma unroll
-    for (int j = 0; j < 4; ++j)
-#pragma unroll
-      for (int e = 0; e < 4; ++e) acc[i][j][e] = 0.0f;
-  const bool a_m_fast = (sAm == 1);
-  const bool b_n_fast = (sBn == 1);
-  for (int k0 = 0; k0 < K; k0 += GB_K) {
-#pragma unroll
-    for (int it = 0; it < (GB_M * GB_K) / G_THREADS; ++it) {
-      int e = tid + it * G_THREADS;
-      int mm, kk;
-      if (a_m_fast) { mm = e % GB_M; kk = e / GB_M; }
-      else          { kk = e % GB_K; mm = e / GB_K; }
-      int gm = m0 + mm, gk = k0 + kk;
-      const float v = (gm < M && gk < K) ? A[gm * sAm + gk * sAk] : 0.0f;
-      const float h = tf32_round(v);
-      Ah[kk][mm] = h;
-      Al[kk][mm] = tf32_round(v - h);
-    }
-#pragma unroll
-    for (int it = 0; it < (GB_N * GB_K) / G_THREADS; ++it) {
-      int e = tid + it * G_THREADS;
-      int nn, kk;
-      if (b_n_fast) { nn = e % GB_N; kk = e / GB_N; }
-      else          { kk = e % GB_K; nn = e / GB_K; }
-      int gn = n0 + nn, gk = k0 + kk;
-      const float v = (gn < N && gk < K) ? B[gk * sBk + gn * sBn] : 0.0f;
-      const float h = tf32_round(v);
-      Bh[kk][nn] = h;
-      Bl[kk][nn] = tf32_round(v - h);
-    }
-    __syncthreads();
-#pragma unroll
-    for (int ks = 0; ks < GB_K; ks += 8) {
-      // B fragments (k x n, "col"): b0 = (k = q, n = g), b1 = (k = q + 4, n = g)
-      uint32_t bh[4][2], bl[4][2];
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const int n = wn + 8 * j + g;
-        bh[j][0] = __float_as_uint(Bh[ks + q][n]);
-        bh[j][1] = __float_as_uint(Bh[ks + q + 4][n]);
-        bl[j][0] = __float_as_uint(Bl[ks + q][n]);
-        bl[j][1] = __float_as_uint(Bl[ks + q + 4][n]);
-      }
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        // A fragment (m x k, "row"): a0 = (g, q), a1 = (g + 8, q), a2 = (g, q + 4), a3 = (g + 8, q + 4)
-        const int m = wm + 16 * i + g;
-        uint32_t ah[4], al[4];
-        ah[0] = __float_as_uint(Ah[ks + q][m]);
-        ah[1] = __float_as_uint(Ah[ks + q][m + 8]);
-        ah[2] = __float_as_uint(Ah[ks + q + 4][m]);
-        ah[3] = __float_as_uint(Ah[ks + q + 4][m + 8]);
-        al[0] = __float_as_uint(Al[ks + q][m]);
-        al[1] = __float_as_uint(Al[ks + q][m + 8]);
-        al[2] = __float_as_uint(Al[ks + q + 4][m]);
-        al[3] = __float_as_uint(Al[ks + q + 4][m + 8]);
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          mma_tf32(acc[i][j], al, bh[j][0], bh[j][1]);
-          mma_tf32(acc[i][j], ah, bl[j][0], bl[j][1]);
-          mma_tf32(acc[i][j], ah, bh[j][0], bh[j][1]);
-        }
-      }
-    }
-    __syncthreads();
-  }
-  // accumulator fragment: c0 = (g, 2q), c1 = (g, 2q + 1), c2 = (g + 8, 2q), c3 = (g + 8, 2q + 1)
-#pragma unroll
-  for (int i = 0; i < 4; ++i)
-#pragma unroll
-    for (int j = 0; j < 4; ++j)
-#pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        const int gm = m0 + wm + 16 * i + g + ((e & 2) ? 8 : 0);
-        const int gn = n0 + wn + 8 * j + 2 * q + (e & 1);
-        if (gm < M && gn < N) {
-          float* c = Cf + (int64_t)gm * ldc + gn;
-          const float v = alpha * acc[i][j][e];
-          *c = accumulate ? (*c + v) : v;
-        }
-      }
-}
-
 // R[i][k] += sum_r X[r][i] * Q[r][k]  (d x kt float64, rows x d and rows x kt
 // fp32 inputs): the X^T Q reduction of the hyper-gradient.  The generic kernel
 // above would run this short-and-wide product on kt / 128 blocks; here the rows
@@ -273,8 +157,9 @@ int sgemm(int M, int N, int K, float alpha, const float* A, int64_t sAm,
                                                   sBk, sBn, nullptr, Cd, ldc,
                                                   accumulate);
   else
-    sgemm_tf32x3_kernel<<<grid, G_THREADS, 0, st>>>(M, N, K, alpha, A, sAm, sAk, B, sBk,
-                                                   sBn, Cf, ldc, accumulate);
+    sgemm_kernel<false><<<grid, G_THREADS, 0, st>>>(M, N, K, alpha, A, sAm, sAk,
+                                                   B, sBk, sBn, Cf, nullptr, ldc,
+                                                   accumulate);
   RR_LAUNCH_CHECK("sgemm_kernel");
   return RR_OK;
 }

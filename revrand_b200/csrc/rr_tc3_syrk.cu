@@ -19,7 +19,7 @@
 // upper triangle; a finalize kernel applies 2^16 / S^2 and the amplitudes.
 //
 // Phi itself is produced once per (row, frequency) by t3_digits_kernel -- tf32
-// tensor-core projection with a three-product split (fp32 grade), exact range
+// tensor-core projection with an exact three-part split (fp32 grade), exact range
 // reduction in turns, polynomial sin/cos -- as a tile-major int8 image that the
 // GEMM streams with bulk copies.  In the previous design
 // the trigonometric generators sat inside the tensor-core kernel and
@@ -227,21 +227,24 @@ __device__ __forceinline__ void t3_emit(uint8_t* __restrict__ img, int64_t kb, i
 // feature x chunk).
 //
 // Trigonometric block: the projection u = X Wt runs on the tensor cores
-// (mma.sync m16n8k8 tf32, frequencies = M, rows = N, input dimensions = K) with
-// the three-product split hi*hi + lo*hi + hi*lo of tf32-rounded operands, which
-// carries ~22 bits per product like the fp32 FMA chain it replaces; a lane ends
-// up with two frequencies x sixteen rows, i.e. one 16-byte chunk of each of the
-// twelve digit lines it then fills.
+// (mma.sync m16n8k8 tf32, frequencies = M, rows = N, input dimensions = K).  Both
+// operands are split EXACTLY into three tf32 parts (11 + 11 + 2 bits) and the six
+// products down to 2^-22 |x w| are accumulated: every product is then as
+// accurate as in the fp32 FMA chain this replaces (a two-part split left
+// 2^-21 |x w| and moved the posterior mean of a 1-D, 256-frequency, N = 1000
+// problem by 1.5e-4).  A lane ends up with two frequencies x sixteen rows, i.e.
+// one 16-byte chunk of each of the twelve digit lines it then fills.
 __global__ void __launch_bounds__(256, 2)
 t3_digits_kernel(rr_plan plan, const float* __restrict__ X, const float* __restrict__ y,
                  int64_t rows, int Fp, int gy_trig, const unsigned int* __restrict__ scales,
                  uint8_t* __restrict__ img) {
-  extern __shared__ float xs[];            // [2][64][stride]: tf32 hi and lo parts of the slab
+  extern __shared__ float xs[];            // [3][64][stride]: tf32 hi / mid / lo parts of the slab
   const int d = plan.d, ktot = plan.ktot;
   const int kp = (d + 7) & ~7;             // input dimensions padded to whole k-steps
   const int stride = kp + 4;               // (stride / 4 odd: fragment loads hit 32 banks)
   float* xh = xs;
-  float* xl = xs + S3_KB * stride;
+  float* xm = xs + S3_KB * stride;
+  float* xl = xs + 2 * S3_KB * stride;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int64_t kb = blockIdx.x;
   const int64_t n0 = kb * S3_KB;
@@ -251,8 +254,10 @@ t3_digits_kernel(rr_plan plan, const float* __restrict__ X, const float* __restr
     const float x = (i < d && n0 + r < rows) ? X[(n0 + r) * d + i] : 0.0f;
     if (trig) {
       const float h = t3_tf32(x);
+      const float m = t3_tf32(x - h);
       xh[r * stride + i] = h;
-      xl[r * stride + i] = t3_tf32(x - h);
+      xm[r * stride + i] = m;
+      xl[r * stride + i] = (x - h) - m;    // <= 3 significant bits: exact in tf32
     } else {
       xh[r * stride + i] = x;
     }
@@ -312,24 +317,31 @@ t3_digits_kernel(rr_plan plan, const float* __restrict__ X, const float* __restr
     for (int j = 0; j < 4; ++j) acc[nt][j] = 0.0f;
   for (int ks = 0; ks < kp; ks += 8) {
     // A fragment (frequencies x input dimensions): a0 (g, q), a1 (g+8, q), a2 (g, q+4), a3 (g+8, q+4)
-    uint32_t ah[4], al[4];
+    uint32_t ah[4], am[4], al[4];
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       const int fi = (j & 1) ? fB : fA;
       const int ki = ks + q + ((j & 2) ? 4 : 0);
       const float w = (fi < ktot && ki < d) ? __ldg(plan.Wt + (int64_t)ki * ktot + fi) : 0.0f;
       const float h = t3_tf32(w);
+      const float m = t3_tf32(w - h);
       ah[j] = __float_as_uint(h);
-      al[j] = __float_as_uint(t3_tf32(w - h));
+      am[j] = __float_as_uint(m);
+      al[j] = __float_as_uint((w - h) - m);
     }
 #pragma unroll
     for (int nt = 0; nt < 8; ++nt) {
       // B fragment (input dimensions x rows): b0 (k = q, n = g), b1 (k = q + 4, n = g)
       const int o = (8 * nt + g) * stride + ks + q;
       const uint32_t bh0 = __float_as_uint(xh[o]), bh1 = __float_as_uint(xh[o + 4]);
+      const uint32_t bm0 = __float_as_uint(xm[o]), bm1 = __float_as_uint(xm[o + 4]);
       const uint32_t bl0 = __float_as_uint(xl[o]), bl1 = __float_as_uint(xl[o + 4]);
+      // x w = (xh + xm + xl)(wh + wm + wl): every product down to 2^-22 |x w|, small first
+      t3_mma_tf32(acc[nt], am, bm0, bm1);
       t3_mma_tf32(acc[nt], al, bh0, bh1);
       t3_mma_tf32(acc[nt], ah, bl0, bl1);
+      t3_mma_tf32(acc[nt], am, bh0, bh1);
+      t3_mma_tf32(acc[nt], ah, bm0, bm1);
       t3_mma_tf32(acc[nt], ah, bh0, bh1);
     }
   }
@@ -662,7 +674,7 @@ static int tc3_groups(const rr_plan* pl, const S3Shape& s, const float* X, const
   const int gy_trig = (pl->ktot + T3_FREQS - 1) / T3_FREQS;
   const int nother = pl->next + 1 + (s.Fp - (D + 1));
   const int gy_other = (nother + T3_OTHER - 1) / T3_OTHER;
-  const size_t dsmem = (size_t)2 * S3_KB * (((d + 7) & ~7) + 4) * sizeof(float);
+  const size_t dsmem = (size_t)3 * S3_KB * (((d + 7) & ~7) + 4) * sizeof(float);
   if (dsmem > 48 * 1024)
     RR_CUDA_CHECK(cudaFuncSetAttribute(t3_digits_kernel,
                                        cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dsmem));
