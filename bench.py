@@ -12,7 +12,7 @@ pass, second allreduce, host assembly.  Rows of X are sharded contiguously over
 the ranks (total N fixed => strong scaling).
 
   python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
-                  [--workload config2|config4|config5]
+                  [--workload config2|config4|config5|fit]
 """
 
 from __future__ import annotations
@@ -430,7 +430,7 @@ def main():
     ap.add_argument("--steps", type=int, default=6)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="config2", choices=["config2", "config4", "config5"])
+    ap.add_argument("--workload", default="config2", choices=["config2", "config4", "config5", "fit"])
     ap.add_argument("--N", type=int, default=None)
     ap.add_argument("--Ks", default="512,1024,2048,4096,8192",
                     help="config5: comma-separated list of nbases to sweep")
@@ -453,6 +453,9 @@ def main():
     if args.workload == "config5":
         import bench_config5
         return bench_config5.main(args)
+    if args.workload == "fit":
+        import bench_fit
+        return bench_fit.main(args)
     if args.impl == "reference":
         run_reference(args)
     else:

@@ -19,7 +19,7 @@
 // upper triangle; a finalize kernel applies 2^16 / S^2 and the amplitudes.
 //
 // Phi itself is produced once per (row, frequency) by t3_digits_kernel -- tf32
-// tensor-core projection with an exact three-part split (fp32 grade), exact range
+// tensor-core projection on split operands (three products), exact range
 // reduction in turns, polynomial sin/cos -- as a tile-major int8 image that the
 // GEMM streams with bulk copies.  In the previous design
 // the trigonometric generators sat inside the tensor-core kernel and
@@ -27,8 +27,14 @@
 // in; at 2 x 10^9 (row, frequency) pairs per pass that made the generators,
 // not the tensor pipe, the bound.
 //
-// y rides along as feature column D of the B side, so Phi^T y comes out of
-// the same exact arithmetic.
+// y rides along on the B side as THREE feature columns D, D+1, D+2 holding its
+// digits one at a time, (y0, 0, 0), (y1, 0, 0), (y2, 0, 0).  With b1 = b2 = 0 none
+// of a column's products is dropped, so sum_n I_a y_k is exact for each digit and
+//     Phi^T y = V0 * 65536 + V1 * 256 + V2
+// carries the FULL 24 x 24-bit products.  (With y as one ordinary column the
+// dropped bracket of p is not a Gram-consistent perturbation: it moved the
+// posterior mean of a 1-D, 256-frequency, N = 1000 problem by 1.5e-4; the columns
+// are free, they sit in the zero padding of the last B tile.)
 //
 // Replaces: revrand/slm.py:145-146, :157 and basis_functions.py:859-864,
 // 1622-1627 (BasisCat.transform), 468-485 (LinearBasis), 415-432 (BiasBasis).
@@ -127,8 +133,8 @@ __global__ void t3_colamp_kernel(rr_plan plan, const unsigned int* __restrict__ 
 
 // ---- digit image ------------------------------------------------------------------
 // img[kb][plane][f][64 bytes]: K block kb = 64 consecutive rows, plane 0..2 = d0,
-// d1, d2, feature f in Phi's own column order (f == D: y, f > D: zero padding up
-// to Fp).  Inside a 64-byte line the 16-byte chunk of rows 16c .. 16c+15 sits at
+// d1, d2, feature f in Phi's own column order (f == D .. D+2: the digits of y,
+// f > D + 2: zero padding up to Fp).  Inside a 64-byte line the 16-byte chunk of rows 16c .. 16c+15 sits at
 // chunk position c ^ ((f >> 1) & 3): the SWIZZLE_64B image of a tile whose first
 // feature is a multiple of 8, so ANY run of features (8-aligned) of one plane and
 // K block is one contiguous, ready-to-use operand tile.
@@ -223,28 +229,38 @@ __device__ __forceinline__ void t3_emit(uint8_t* __restrict__ img, int64_t kb, i
 
 // Digit image of one K block (64 rows).  grid.y counts the trigonometric blocks
 // (128 frequencies, 16 per warp) first, then the blocks of "other" features:
-// affine columns, the y column and the zero padding (64 per block, thread =
+// affine columns, the three y digit columns and the zero padding (64 per block, thread =
 // feature x chunk).
 //
 // Trigonometric block: the projection u = X Wt runs on the tensor cores
-// (mma.sync m16n8k8 tf32, frequencies = M, rows = N, input dimensions = K).  Both
-// operands are split EXACTLY into three tf32 parts (11 + 11 + 2 bits) and the six
-// products down to 2^-22 |x w| are accumulated: every product is then as
-// accurate as in the fp32 FMA chain this replaces (a two-part split left
-// 2^-21 |x w| and moved the posterior mean of a 1-D, 256-frequency, N = 1000
-// problem by 1.5e-4).  A lane ends up with two frequencies x sixteen rows, i.e.
-// one 16-byte chunk of each of the twelve digit lines it then fills.
+// (mma.sync m16n8k8 tf32, frequencies = M, rows = N, input dimensions = K) on
+// operands split into tf32 parts.  EXACT = false (the default): two parts
+// (11 + 11 bits) and the three products hi*hi + lo*hi + hi*lo, i.e. every product
+// to ~2^-21 |x w|: a phase error of a few 1e-6 rad per unit of |u|, which moves
+// the config-2 posterior by less than the digit rounding does (DESIGN.md section 4:
+// the same 2.0e-5 worst case as an fp32 FMA chain) and costs 3.5 ms less per
+// value pass than EXACT = true (compile with -DRR_T3_EXACT_PROJECTION=1): an exact
+// three-part split (11 + 11 + 2 bits) and the six products down to 2^-22 |x w|,
+// as accurate as the fp32 FMA chain.  A lane ends up with two frequencies x
+// sixteen rows, i.e. one 16-byte chunk of each of the twelve digit lines it then
+// fills.
+#ifndef RR_T3_EXACT_PROJECTION
+#define RR_T3_EXACT_PROJECTION 0
+#endif
+constexpr bool T3_EXACT = RR_T3_EXACT_PROJECTION != 0;
+constexpr int T3_PARTS = T3_EXACT ? 3 : 2;
+
 __global__ void __launch_bounds__(256, 2)
 t3_digits_kernel(rr_plan plan, const float* __restrict__ X, const float* __restrict__ y,
                  int64_t rows, int Fp, int gy_trig, const unsigned int* __restrict__ scales,
                  uint8_t* __restrict__ img) {
-  extern __shared__ float xs[];            // [3][64][stride]: tf32 hi / mid / lo parts of the slab
+  extern __shared__ float xs[];            // [T3_PARTS][64][stride]: tf32 parts of the slab
   const int d = plan.d, ktot = plan.ktot;
   const int kp = (d + 7) & ~7;             // input dimensions padded to whole k-steps
   const int stride = kp + 4;               // (stride / 4 odd: fragment loads hit 32 banks)
   float* xh = xs;
   float* xm = xs + S3_KB * stride;
-  float* xl = xs + 2 * S3_KB * stride;
+  float* xl = xs + (T3_PARTS - 1) * S3_KB * stride;    // EXACT only (aliases xm otherwise)
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int64_t kb = blockIdx.x;
   const int64_t n0 = kb * S3_KB;
@@ -257,7 +273,7 @@ t3_digits_kernel(rr_plan plan, const float* __restrict__ X, const float* __restr
       const float m = t3_tf32(x - h);
       xh[r * stride + i] = h;
       xm[r * stride + i] = m;
-      xl[r * stride + i] = (x - h) - m;    // <= 3 significant bits: exact in tf32
+      if (T3_EXACT) xl[r * stride + i] = (x - h) - m;    // <= 3 significant bits: exact in tf32
     } else {
       xh[r * stride + i] = x;
     }
@@ -286,8 +302,10 @@ t3_digits_kernel(rr_plan plan, const float* __restrict__ X, const float* __restr
         v = fminf(1.0f, fmaxf(-1.0f, v));
         kq[b] = t3_quant((n0 + r < rows) ? v : 0.0f);
       }
-    } else if (e == plan.next) {
-      f = plan.D;
+    } else if (e < plan.next + 3) {
+      // y digit (e - next) alone in plane 0 of column D + (e - next)
+      const int dig = e - plan.next;
+      f = plan.D + dig;
       const float sc = __uint_as_float(scales[d]);
       const float inv = (y != nullptr && sc > 0.0f) ? 1.0f / sc : 0.0f;
 #pragma unroll
@@ -296,6 +314,16 @@ t3_digits_kernel(rr_plan plan, const float* __restrict__ X, const float* __restr
         const float v = (y != nullptr && n0 + r < rows) ? y[n0 + r] * inv : 0.0f;
         kq[b] = t3_quant(fminf(1.0f, fmaxf(-1.0f, v)));
       }
+      uint4 q0, q1, q2;
+      uint32_t* w0 = reinterpret_cast<uint32_t*>(&q0);
+      uint32_t* w1 = reinterpret_cast<uint32_t*>(&q1);
+      uint32_t* w2 = reinterpret_cast<uint32_t*>(&q2);
+#pragma unroll
+      for (int g = 0; g < 4; ++g)
+        t3_pack4(kq[4 * g], kq[4 * g + 1], kq[4 * g + 2], kq[4 * g + 3], w0[g], w1[g], w2[g]);
+      const uint4 zero = make_uint4(0u, 0u, 0u, 0u);
+      t3_store_planes(img, kb, Fp, f, q, dig == 0 ? q0 : (dig == 1 ? q1 : q2), zero, zero);
+      return;
     } else {
       f = plan.D + (e - plan.next);
       if (f >= Fp) return;
@@ -335,11 +363,13 @@ t3_digits_kernel(rr_plan plan, const float* __restrict__ X, const float* __restr
       const int o = (8 * nt + g) * stride + ks + q;
       const uint32_t bh0 = __float_as_uint(xh[o]), bh1 = __float_as_uint(xh[o + 4]);
       const uint32_t bm0 = __float_as_uint(xm[o]), bm1 = __float_as_uint(xm[o + 4]);
-      const uint32_t bl0 = __float_as_uint(xl[o]), bl1 = __float_as_uint(xl[o + 4]);
-      // x w = (xh + xm + xl)(wh + wm + wl): every product down to 2^-22 |x w|, small first
-      t3_mma_tf32(acc[nt], am, bm0, bm1);
-      t3_mma_tf32(acc[nt], al, bh0, bh1);
-      t3_mma_tf32(acc[nt], ah, bl0, bl1);
+      if (T3_EXACT) {
+        // x w = (xh + xm + xl)(wh + wm + wl): every product down to 2^-22 |x w|, small first
+        const uint32_t bl0 = __float_as_uint(xl[o]), bl1 = __float_as_uint(xl[o + 4]);
+        t3_mma_tf32(acc[nt], am, bm0, bm1);
+        t3_mma_tf32(acc[nt], al, bh0, bh1);
+        t3_mma_tf32(acc[nt], ah, bl0, bl1);
+      }
       t3_mma_tf32(acc[nt], am, bh0, bh1);
       t3_mma_tf32(acc[nt], ah, bm0, bm1);
       t3_mma_tf32(acc[nt], ah, bh0, bh1);
@@ -399,7 +429,7 @@ __device__ __forceinline__ S3Item s3_decode(int item, int ntiles, int NIB, int N
   return it;
 }
 
-// T is (D + 1) x ldT float64, T[fb][fa] for fb >= fa (fa fastest: a warp's 32
+// T is (D + 3) x ldT float64 (rows D .. D+2: the y digit columns), T[fb][fa] for fb >= fa (fa fastest: a warp's 32
 // accumulator lanes are 32 consecutive fa).
 __global__ void __launch_bounds__(S3_THREADS, 1)
 t3_syrk_kernel(const uint8_t* __restrict__ img, int Fp, int nkb_total, int D, int NIB, int NJB,
@@ -536,7 +566,7 @@ t3_syrk_kernel(const uint8_t* __restrict__ img, int Fp, int nkb_total, int D, in
 #pragma unroll
         for (int r = 0; r < 16; ++r) {
           const int fb = fb0 + c0 + r;
-          if (fa < D && fb <= D && fb >= fa) {
+          if (fa < D && fb <= D + 2 && fb >= fa) {
             const long long v = (long long)a0[r] * 65536ll + (long long)a1[r] * 256ll +
                                 (long long)a2[r];
             if (v != 0) atomicAdd(Tcol + (int64_t)fb * ldT, (double)v);
@@ -551,7 +581,8 @@ t3_syrk_kernel(const uint8_t* __restrict__ img, int Fp, int nkb_total, int D, in
   if (warp == 1) tmem_dealloc_2cta(tmem, 512);
 }
 
-// G[i][j] += kappa * camp_i * camp_j * T[max(i,j)][min(i,j)],  p[i] += kappa * camp_i * camp_D * T[D][i].
+// G[i][j] += kappa * camp_i * camp_j * T[max(i,j)][min(i,j)],
+// p[i] += kappa * camp_i * camp_D * (T[D][i] + T[D+1][i] / 256 + T[D+2][i] / 65536).
 __global__ void __launch_bounds__(256)
 t3_finalize_kernel(const double* __restrict__ T, int64_t ldT, const float* __restrict__ camp,
                    double* __restrict__ G, double* __restrict__ p, int D, double kappa) {
@@ -563,7 +594,9 @@ t3_finalize_kernel(const double* __restrict__ T, int64_t ldT, const float* __res
     if (p != nullptr) {
       const int i = bx * 32 + tx;
       if (ty == 0 && i < D)
-        p[i] += kappa * (double)camp[i] * (double)camp[D] * T[(int64_t)D * ldT + i];
+        p[i] += kappa * (double)camp[i] * (double)camp[D] *
+                (T[(int64_t)D * ldT + i] + T[(int64_t)(D + 1) * ldT + i] * (1.0 / 256.0) +
+                 T[(int64_t)(D + 2) * ldT + i] * (1.0 / 65536.0));
     }
     return;
   }
@@ -609,7 +642,7 @@ static S3Shape s3_shape(const rr_plan* pl, int64_t N) {
   S3Shape s;
   s.D = pl->D;
   s.NIB = (s.D + S3_TM - 1) / S3_TM;
-  s.NJB = (s.D + 1 + S3_TN - 1) / S3_TN;
+  s.NJB = (s.D + 3 + S3_TN - 1) / S3_TN;
   const int fa = S3_TM * s.NIB, fb = S3_TN * s.NJB;
   s.Fp = fa > fb ? fa : fb;
   s.ntiles = 0;
@@ -634,7 +667,7 @@ int tc3_suffstats_supported(const rr_plan* pl) {
 
 size_t tc3_suffstats_workspace(const rr_plan* pl, int64_t N) {
   const S3Shape s = s3_shape(pl, N);
-  return align_up((size_t)(s.D + 1) * s.ldT * sizeof(double), 256) +
+  return align_up((size_t)(s.D + 3) * s.ldT * sizeof(double), 256) +
          align_up((size_t)(s.D + 1) * sizeof(float), 256) +
          align_up((size_t)(pl->d + 1) * sizeof(unsigned int), 256) +
          2 * (align_up(s.group_bytes, 1024) + 1024) + 4096;
@@ -672,9 +705,9 @@ static int tc3_groups(const rr_plan* pl, const S3Shape& s, const float* X, const
                       cudaEvent_t ev_mma[2]) {
   const int d = pl->d, D = s.D;
   const int gy_trig = (pl->ktot + T3_FREQS - 1) / T3_FREQS;
-  const int nother = pl->next + 1 + (s.Fp - (D + 1));
+  const int nother = pl->next + 3 + (s.Fp - (D + 3));
   const int gy_other = (nother + T3_OTHER - 1) / T3_OTHER;
-  const size_t dsmem = (size_t)3 * S3_KB * (((d + 7) & ~7) + 4) * sizeof(float);
+  const size_t dsmem = (size_t)T3_PARTS * S3_KB * (((d + 7) & ~7) + 4) * sizeof(float);
   if (dsmem > 48 * 1024)
     RR_CUDA_CHECK(cudaFuncSetAttribute(t3_digits_kernel,
                                        cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dsmem));
@@ -709,7 +742,7 @@ int tc3_suffstats(const rr_plan* pl, const float* X, const float* y, int64_t N, 
   const S3Shape s = s3_shape(pl, N);
   const int D = s.D, d = pl->d;
   Workspace W(ws, ws_bytes);
-  double* T = W.take<double>((size_t)(D + 1) * s.ldT);
+  double* T = W.take<double>((size_t)(D + 3) * s.ldT);
   float* camp = W.take<float>((size_t)D + 1);
   unsigned int* scales = W.take<unsigned int>((size_t)d + 1);
   uint8_t* imgs[2];
@@ -723,7 +756,7 @@ int tc3_suffstats(const rr_plan* pl, const float* X, const float* y, int64_t N, 
   for (int i = 0; i < 2; ++i)
     imgs[i] = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(imgs[i]) + 1023) & ~(uintptr_t)1023);
 
-  RR_CUDA_CHECK(cudaMemsetAsync(T, 0, (size_t)(D + 1) * s.ldT * sizeof(double), st));
+  RR_CUDA_CHECK(cudaMemsetAsync(T, 0, (size_t)(D + 3) * s.ldT * sizeof(double), st));
   RR_CUDA_CHECK(cudaMemsetAsync(scales, 0, (size_t)(d + 1) * sizeof(unsigned int), st));
   RR_CUDA_CHECK(cudaMemsetAsync(camp, 0, (size_t)(D + 1) * sizeof(float), st));
   bool need_x = false;   // any affine column that copies an input column?  (host plan is a
@@ -784,7 +817,7 @@ extern "C" int rr_tcgen05_i8_selftest(int32_t kblocks, int64_t* mismatches) {
   S3Shape s = s3_shape(&pl, N);
   const int D = s.D, Fp = s.Fp;
   const size_t img_bytes = (size_t)3 * kblocks * Fp * 64;
-  const size_t t_bytes = (size_t)(D + 1) * s.ldT * sizeof(double);
+  const size_t t_bytes = (size_t)(D + 3) * s.ldT * sizeof(double);
   int8_t* hd = (int8_t*)malloc((size_t)3 * N * Fp);        // [plane][feature f][row n]
   uint8_t* himg = (uint8_t*)calloc(img_bytes, 1);
   double* hT = (double*)malloc(t_bytes);

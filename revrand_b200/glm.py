@@ -75,6 +75,22 @@ def _qmatrix(m, C):
     return -0.5 * (np.log(2 * np.pi * v) + dm ** 2 / v).sum(axis=0)
 
 
+def _mixture_gradients(m, C, Lam, logNkl, logzk, Edm, EdC, B):
+    """d ELBO / d m, d ELBO / d C for all mixture components at once
+    (glm.py:249-260: likelihood term + prior term + mixture-entropy term),
+    vectorised over the K_mix x K_mix component pairs."""
+    K = m.shape[1]
+    # alpha[j, k] = N_jk / z_k + N_jk / z_j   (rows j: the other component)
+    alpha = np.exp(logNkl - logzk[None, :]) + np.exp(logNkl - logzk[:, None])
+    mkmj = m[:, :, None] - m[:, None, :]            # [:, k, j] = m_k - m_j
+    iCkCj = 1. / (C[:, :, None] + C[:, None, :])    # [:, k, j]
+    aT = alpha.T[None, :, :]                        # [1, k, j] = alpha[j, k]
+    dm = (B * Edm - m / Lam[:, None] + (iCkCj * mkmj * aT).sum(axis=2)) / K
+    dC = (B * EdC - 1. / Lam[:, None]
+          + ((iCkCj - (mkmj * iCkCj) ** 2) * aT).sum(axis=2)) / (2 * K)
+    return dm, dC
+
+
 def _reshape_likelihood_args(likelihood_args, N):
     out = []
     for arg in likelihood_args:
@@ -271,18 +287,7 @@ class GeneralizedLinearModel(BaseEstimator, RegressorMixin):
         iL = 1. / Lam[:, None]
         logNkl = _qmatrix(m, C)
         logzk = logsumexp(logNkl, axis=0)
-        dm = np.empty_like(m)
-        dC = np.empty_like(C)
-        for k in range(K):
-            Nkl_zk = np.exp(logNkl[:, k] - logzk[k])
-            Nkl_zl = np.exp(logNkl[:, k] - logzk)
-            alpha = Nkl_zk + Nkl_zl
-            mkmj = m[:, k][:, None] - m
-            iCkCj = 1. / (C[:, k][:, None] + C)
-            dm[:, k] = (self.B_ * Edm_h[:, k] - m[:, k] / Lam
-                        + (iCkCj * mkmj).dot(alpha)) / K
-            dC[:, k] = (self.B_ * EdC_h[:, k] - 1. / Lam
-                        + (iCkCj - (mkmj * iCkCj) ** 2).dot(alpha)) / (2 * K)
+        dm, dC = _mixture_gradients(m, C, Lam, logNkl, logzk, Edm_h, EdC_h, self.B_)
 
         def dreg(s):
             return -0.5 * (((m[s] ** 2 + C[s]) * iL[s] ** 2).sum() / K

@@ -386,3 +386,28 @@ def test_device_data_cache_key_sees_in_place_edits():
     X[0, 0] -= 1.0
     y[-1] = 7.0
     assert k0 != StandardLinearModel._fingerprint(X, y)
+
+
+def test_glm_mixture_gradients_match_the_component_loop():
+    """The vectorised mixture terms of the GLM step against the reference's loop
+    over components (glm.py:249-260)."""
+    from revrand_b200 import glm
+    from revrand_b200.mathfun.special import logsumexp
+    rs = np.random.RandomState(0)
+    D, K, B = 12, 4, 7.5
+    m, C = rs.randn(D, K), 0.1 + rs.rand(D, K)
+    Lam = 0.5 + rs.rand(D)
+    Edm, EdC = rs.randn(D, K), rs.randn(D, K)
+    logNkl = glm._qmatrix(m, C)
+    logzk = logsumexp(logNkl, axis=0)
+    dm, dC = glm._mixture_gradients(m, C, Lam, logNkl, logzk, Edm, EdC, B)
+    for k in range(K):
+        Nkl_zk = np.exp(logNkl[:, k] - logzk[k])
+        Nkl_zl = np.exp(logNkl[:, k] - logzk)
+        alpha = Nkl_zk + Nkl_zl
+        mkmj = m[:, k][:, None] - m
+        iCkCj = 1. / (C[:, k][:, None] + C)
+        rm = (B * Edm[:, k] - m[:, k] / Lam + (iCkCj * mkmj).dot(alpha)) / K
+        rC = (B * EdC[:, k] - 1. / Lam + (iCkCj - (mkmj * iCkCj) ** 2).dot(alpha)) / (2 * K)
+        np.testing.assert_allclose(dm[:, k], rm, rtol=1e-12, atol=1e-14)
+        np.testing.assert_allclose(dC[:, k], rC, rtol=1e-12, atol=1e-14)
