@@ -82,6 +82,12 @@ typedef struct rr_plan {
   /* Optional (NULL = all 1): integer power of extra column j, i.e. the column is
    * X[n, ext_src[j]] ^ ext_pow[j] -- PolynomialBasis (basis_functions.py:537-566). */
   const int32_t* ext_pow; /* (next) or NULL                                   */
+  /* Optional (NULL = taken from the rows of the call): the fixed-point scales of the
+   * int8 value pass, col_scale[i] >= max |X[:, i]| (i < d) and col_scale[d] >= max |y|
+   * over ALL rows of the job.  A row-sharded caller passes the job-wide maxima so
+   * that every rank quantises alike (the ranks' statistics then add up to the
+   * one-process result bit for bit); it also saves the pass over X that finds them. */
+  const float* col_scale; /* (d + 1) or NULL                                  */
 } rr_plan;
 
 /* Likelihood ids for rr_glm_step; revrand/likelihoods.py:18-545. */

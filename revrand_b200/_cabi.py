@@ -33,6 +33,7 @@ class RRPlan(C.Structure):
         ("ext_col", C.c_void_p),
         ("kind", C.c_void_p),
         ("ext_pow", C.c_void_p),
+        ("col_scale", C.c_void_p),
     ]
 
 

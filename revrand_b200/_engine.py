@@ -196,6 +196,7 @@ class FeaturePlan(object):
                            device=device())
         self.struct = RRPlan()
         self.struct_tc = None      # extended plan (affine columns as slots), see below
+        self._col_scale = None     # job-wide fixed-point scales (set_col_scale)
         self._ext_host = (cat(ext_src, np.int32), cat(ext_val, np.float32),
                           cat(ext_col, np.int32))
         self.refresh()
@@ -243,6 +244,13 @@ class FeaturePlan(object):
         self.struct_tc = s
         self.refresh()
 
+    def set_col_scale(self, scale):
+        """Fixed-point scales of the int8 value pass (rr_plan.col_scale): a (d+1,)
+        float32 device tensor, max |X[:, i]| and max |y| over ALL rows of the job,
+        or None (each call then finds the maxima of its own rows)."""
+        self._col_scale = scale
+        self.struct.col_scale = None if scale is None else scale.data_ptr()
+
     def set_lenscales(self, lenscales):
         """New lengthscale per trig block (scalar or (d_eff,) each)."""
         assert len(lenscales) == len(self.trig)
@@ -260,15 +268,32 @@ class FeaturePlan(object):
             inv[rows, ko:ko + b.K] = (1.0 / ls)[:, None]
         return inv[:, :self.ktot]
 
+    def Wt_host(self, lenscales=None):
+        """Wt = W / lenscale / 2pi as a float32 host array (float64 arithmetic); for
+        the blocks' current lengthscales, or for ``lenscales`` without changing them."""
+        if lenscales is not None:
+            keep = [b.lenscale for b in self.trig]
+            for b, ls in zip(self.trig, lenscales):
+                b.lenscale = np.atleast_1d(np.asarray(ls, dtype=np.float64))
+        # (a random start may draw a lengthscale so small that W / l leaves the
+        # fp32 range: keep it finite, the phase is meaningless there anyway)
+        Wt = np.clip(self.Wfull * self.inv_lenscale_full() / TWO_PI, -3e38, 3e38)
+        if lenscales is not None:
+            for b, ls in zip(self.trig, keep):
+                b.lenscale = ls
+        return np.ascontiguousarray(Wt.astype(np.float32))
+
+    def point_Wt_at(self, tensor=None):
+        """Let the plan read its projection from ``tensor`` ((d, ktot) float32 on the
+        device, e.g. one of a stack uploaded ahead of a pipelined batch of
+        evaluations) instead of its own buffer; None restores the own buffer."""
+        self.struct.Wt = (self._Wt if tensor is None else tensor).data_ptr()
+
     def refresh(self):
         """Recompute Wt = W / lenscale / 2pi (float64 on host) and upload."""
         t = torch()
         if self.ktot:
-            # (a random start may draw a lengthscale so small that W / l leaves the
-            # fp32 range: keep it finite, the phase is meaningless there anyway)
-            Wt = np.clip(self.Wfull * self.inv_lenscale_full() / TWO_PI, -3e38, 3e38)
-            self._Wt.copy_(t.from_numpy(np.ascontiguousarray(
-                Wt.astype(np.float32))), non_blocking=False)
+            self._Wt.copy_(t.from_numpy(self.Wt_host()), non_blocking=False)
         s = self.struct
         s.d, s.ktot, s.next, s.D = self.d, self.ktot, self.next, self.D
         s.Wt = self._Wt.data_ptr()
@@ -280,6 +305,7 @@ class FeaturePlan(object):
         s.ext_col = self._ext_col.data_ptr()
         s.kind = None
         s.ext_pow = None if self._ext_pow is None else self._ext_pow.data_ptr()
+        s.col_scale = None if self._col_scale is None else self._col_scale.data_ptr()
         if self.struct_tc is not None:
             self._Wt_x[:, :self.ktot].copy_(self._Wt)
 
@@ -565,9 +591,9 @@ class Posterior(object):
     an evaluation only needs diag(C), m, logdet and -- for the gradient pass --
     a float32 image of C."""
 
-    def __init__(self, m, diagC, logdet, trgc, Linv=None, C=None, dg=None):
+    def __init__(self, m, diagC, logdet, trgc, Linv=None, C=None, dg=None, C32=None):
         self.m, self.diagC, self.logdet, self.trgc = m, diagC, logdet, trgc
-        self._Linv, self._C = Linv, C
+        self._Linv, self._C, self._C32 = Linv, C, C32
         # (max / min of the Cholesky diagonal)^2: a cheap lower bound on cond(iC)
         self.cond_est = None if dg is None else (dg.max() / dg.min()) ** 2
 
@@ -579,12 +605,15 @@ class Posterior(object):
 
     def C32(self):
         """float32 image of C for the gradient pass."""
-        return self.C.float().contiguous()
+        if self._C32 is None:
+            self._C32 = self.C.float().contiguous()
+        return self._C32
 
 
 _BLOCK_INV_MIN = 1024   # below this potri is as fast
 _BLOCK_INV_LEAF = 512
 _BLOCK_INV_CUDA_ONLY = True   # tests flip this to exercise the blocked paths on CPU
+_BLOCK_INV_BATCHED = True     # level-by-level batched triangular inverse (False: recursion)
 
 
 def _use_blocked(L):
@@ -598,12 +627,56 @@ def _split(n):
     return h if 0 < h < n else n // 2
 
 
+def _diag_blocks(M, nblk, c, bi, bj):
+    """(nblk, c, c) strided view of sub-block (bi, bj) of every 2c x 2c diagonal
+    block of M (M is (2 c nblk)^2, contiguous)."""
+    V = M.view(nblk, 2, c, nblk, 2, c)[:, bi, :, :, bj, :]      # (nblk, c, nblk, c)
+    return V.diagonal(dim1=0, dim2=2).permute(2, 0, 1)
+
+
 def _tri_inv_lower(L, out):
-    """out = L^-1 for lower-triangular L, recursively: with L = [[L11, 0], [L21, L22]],
-    L^-1 = [[L11^-1, 0], [-L22^-1 L21 L11^-1, L22^-1]].  All the O(n^3) work is in
-    float64 GEMMs (tensor cores) instead of cuSOLVER's triangular kernels."""
+    """out = L^-1 for lower-triangular L.  With L = [[L11, 0], [L21, L22]],
+    L^-1 = [[L11^-1, 0], [-L22^-1 L21 L11^-1, L22^-1]]: applied bottom-up over a
+    power-of-two number of diagonal blocks, every level is ONE batched triangular
+    solve (the leaves) or two batched float64 GEMMs over all block pairs of that
+    level -- log2(n / leaf) + 1 launches' worth of well-filled library calls instead
+    of a recursion whose leaves run one small trsm at a time (3.8 ms -> see
+    DESIGN.md section 3.5 at D = 4096).  Matrices whose size is not leaf * 2^k are padded
+    with an identity block."""
     t = torch()
     n = L.shape[0]
+    if n > _BLOCK_INV_LEAF and _BLOCK_INV_BATCHED:
+        nb = 1
+        while n > nb * _BLOCK_INV_LEAF:
+            nb *= 2
+        b = -(-n // nb)
+        Dp = nb * b
+        if Dp != n:
+            Lp = t.zeros((Dp, Dp), dtype=L.dtype, device=L.device)
+            Lp[:n, :n] = L
+            Lp.diagonal()[n:] = 1.0
+            Op = t.zeros_like(Lp)
+        else:
+            Lp = L if L.is_contiguous() else L.contiguous()
+            Op = out if (out.is_contiguous() and out.shape == Lp.shape) else t.empty_like(Lp)
+            Op.zero_()
+        # leaves: all nb diagonal b x b blocks in one batched triangular solve
+        Vd = Lp.view(nb, b, nb, b).diagonal(dim1=0, dim2=2).permute(2, 0, 1)
+        eye = t.eye(b, dtype=L.dtype, device=L.device).expand(nb, b, b)
+        inv = t.linalg.solve_triangular(Vd.contiguous(), eye, upper=False)
+        Op.view(nb, b, nb, b).diagonal(dim1=0, dim2=2).permute(2, 0, 1).copy_(inv)
+        c = b
+        while c < Dp:
+            P = Dp // (2 * c)
+            L21 = _diag_blocks(Lp, P, c, 1, 0)
+            A = _diag_blocks(Op, P, c, 0, 0)
+            B = _diag_blocks(Op, P, c, 1, 1)
+            X = t.bmm(B, t.bmm(L21, A))
+            _diag_blocks(Op, P, c, 1, 0).copy_(X.neg_())
+            c *= 2
+        if Op is not out:
+            out.copy_(Op[:n, :n])
+        return
     if n <= _BLOCK_INV_LEAF:
         out.copy_(t.linalg.solve_triangular(
             L, t.eye(n, dtype=L.dtype, device=L.device), upper=False))
@@ -642,6 +715,33 @@ def blocked_spd_inverse(L):
     C = t.empty_like(L)
     _gram_of_lower(Li, C)
     return C
+
+
+def _posterior_sharded(L, dg, p, var, lam):
+    """Row-sharded job, large D: every rank holds the same factor L.  L^-1 is formed
+    on every rank (batched GEMM form), from it m and diag C in float64; the O(D^3)
+    product C = L^-T L^-1 is split by rows over the ranks and all-gathered as the
+    float32 image the gradient pass reads (half the bytes of a float64 gather; the
+    float64 C itself is only formed if somebody asks for it, from the replicated
+    L^-1)."""
+    t = torch()
+    rank, ws = world()
+    D = L.shape[0]
+    per = (D + ws - 1) // ws
+    lo = min(rank * per, D)
+    hi = min(lo + per, D)
+    Li = t.empty_like(L)
+    _tri_inv_lower(L, Li)
+    diagC = (Li * Li).sum(dim=0)
+    m = (Li.T @ (Li @ p)) / var
+    rows = t.zeros((per, D), dtype=t.float32, device=L.device)
+    if hi > lo:
+        rows[:hi - lo] = (Li[:, lo:hi].T @ Li).float()
+    full = t.empty((ws * per, D), dtype=t.float32, device=L.device)
+    t.distributed.all_gather_into_tensor(full, rows)
+    logdet = 2.0 * t.log(dg).sum()
+    trgc = var * (D - (diagC / lam).sum())
+    return Posterior(m, diagC, logdet, trgc, Linv=Li, dg=dg, C32=full[:D].contiguous())
 
 
 def _inverse_from_factor(L):
@@ -703,6 +803,8 @@ def solve_posterior(G, p, var, lam, need_C=True):
     L, info = t.linalg.cholesky_ex(iC)
     dg = L.diagonal()
     ok = bool(((info == 0) & (dg >= CHOLTHRESH).all()).item())
+    if ok and need_C and world()[1] > 1 and _use_blocked(L) and D >= 2 * world()[1]:
+        return _posterior_sharded(L, dg, p, var, lam)
     if ok and need_C:
         Cm = _inverse_from_factor(L)
         diagC = Cm.diagonal().clone()
@@ -722,12 +824,51 @@ def solve_posterior(G, p, var, lam, need_C=True):
         logdet = 2.0 * t.log(dg).sum()
         trgc = var * (D - (diagC / lam).sum())
         return Posterior(m, diagC, logdet, trgc, Linv=Linv, dg=dg)
-    U, s, Vh = t.linalg.svd(iC)
-    sc = t.clamp(s, min=SVD_FLOOR)
-    Cm = (U / sc) @ Vh
-    logdet = t.log(s).sum()
+    # Clamped-spectrum fallback (svd_solve, linalg.py:128-179).  iC is symmetric, so
+    # its SVD is its eigendecomposition with s = |w|, U = V sign(w), Vh = V^T; syevd
+    # is the robust dense routine on the device (gesvd returns NaN / exact zeros on
+    # the numerically rank-one matrices a wild line-search step produces).  The
+    # log-determinant uses the same clamped spectrum as the solve, so it stays
+    # finite where the reference's sum(log s) relies on rounding noise in s.
+    w, V = t.linalg.eigh(iC)
+    w = t.nan_to_num(w, nan=0.0, posinf=1e300, neginf=-1e300)
+    sc = t.clamp(w.abs(), min=SVD_FLOOR)
+    sgn = t.where(w < 0, -t.ones_like(w), t.ones_like(w))
+    Cm = (V * (sgn / sc)) @ V.T
+    logdet = t.log(sc).sum()
     m = (Cm @ p) / var
     return Posterior(m, Cm.diagonal().clone(), logdet, (G * Cm).sum(), C=Cm)
+
+
+def solve_value_scalars(G, p, var, lam, yy, slices):
+    """The value-only branch of ``solve_posterior`` without any host decision, for
+    pipelined batches of evaluations (random starts, sweeps): returns ONE float64
+    device vector  [ok, logdet, trgc, sqerr, q_0 .. q_{S-1}]  where ``ok`` is 0 if
+    the Cholesky factorisation failed or was unstable (the caller then re-runs
+    that point through ``solve_posterior`` and its clamped-spectrum fallback),
+    sqerr = y'y - 2 p'm + m'G m and q_s = sum over slice s of m^2 + diag C."""
+    t = torch()
+    D = G.shape[0]
+    iC = G / var
+    iC.diagonal().add_(1.0 / lam)
+    L, info = t.linalg.cholesky_ex(iC)
+    dg = L.diagonal()
+    ok = (info == 0) & (dg >= CHOLTHRESH).all()
+    if _use_blocked(L):
+        Linv = t.empty_like(L)
+        _tri_inv_lower(L, Linv)
+    else:
+        Linv = t.linalg.solve_triangular(
+            L, t.eye(D, dtype=G.dtype, device=G.device), upper=False)
+    diagC = (Linv * Linv).sum(dim=0)
+    m = (Linv.T @ (Linv @ p)) / var
+    logdet = 2.0 * t.log(dg).sum()
+    trgc = var * (D - (diagC / lam).sum())
+    sqerr = yy - 2.0 * p.dot(m) + m.dot(G @ m)
+    mc = m * m + diagC
+    q = t.stack([mc[sl].sum() for sl in slices])
+    head = t.stack([ok.to(G.dtype).reshape(()), logdet, trgc, sqerr])
+    return t.cat([head, q])
 
 
 # ---------------------------------------------------------------------------

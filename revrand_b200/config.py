@@ -40,3 +40,14 @@ POLISH_COND = float(os.environ.get("REVRAND_B200_POLISH_COND", "1e3"))
 # the device between calls while the same host arrays are passed (identity plus
 # a content fingerprint).  False: upload the rows on every call.
 CACHE_DEVICE_DATA = os.environ.get("REVRAND_B200_CACHE_DATA", "1") != "0"
+
+# Value-only evaluations take sum Err^2 = y'y - 2 p'm + m'G m from the float64
+# sufficient statistics when it is at least this fraction of y'y (the quadratic
+# form loses y'y / sum Err^2 digits of the statistics' ~1e-7 relative accuracy to
+# cancellation); nearer to interpolation they run the residual pass over the rows.
+SQERR_FROM_STATS_MIN = float(os.environ.get("REVRAND_B200_SQERR_STATS_MIN", "1e-3"))
+
+# ``fit`` evaluates its random starts (independent points) as one pipelined batch:
+# the float64 solve of one start overlaps the value pass of the next, with no host
+# synchronisation inside the loop.  False: one blocking evaluation per start.
+PIPELINE_STARTS = os.environ.get("REVRAND_B200_PIPELINE_STARTS", "1") != "0"

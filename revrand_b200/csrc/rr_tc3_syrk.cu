@@ -102,16 +102,11 @@ t3_scales_kernel(const float* __restrict__ X, const float* __restrict__ y, int64
     }
   }
   __syncthreads();
-  // The scale is the next power of two >= the maximum: row shards of one data set
-  // (ranks of a sharded job) then almost always agree on it although their maxima
-  // differ, which makes their quantised statistics add up to the one-process result
-  // bit for bit; the price is at most one of the 23 bits.
+  // (Row shards of one data set see different maxima: a sharded caller passes the
+  // job-wide maxima in rr_plan.col_scale instead, which makes the ranks' quantised
+  // statistics add up to the one-process result bit for bit.)
   for (int i = threadIdx.x; i <= d; i += blockDim.x)
-    if (smax[i]) {
-      const uint32_t b = smax[i];
-      const uint32_t up = (b & 0x007FFFFFu) ? ((b & 0x7F800000u) + 0x00800000u) : b;
-      atomicMax(&scales[i], up < 0x7F800000u ? up : b);
-    }
+    if (smax[i]) atomicMax(&scales[i], smax[i]);
 }
 
 // camp[f] = real amplitude of integer feature f (f <= D; f == D is the y column).
@@ -763,10 +758,16 @@ int tc3_suffstats(const rr_plan* pl, const float* X, const float* y, int64_t N, 
                          // device image: decide from `next` alone)
   need_x = pl->next > 0;
   {
-    const int blocks = sm_count() * 4;
-    t3_scales_kernel<<<blocks, 256, (size_t)(d + 1) * sizeof(unsigned int), st>>>(
-        X, (p != nullptr) ? y : nullptr, N, d, need_x ? 1 : 0, scales);
-    RR_LAUNCH_CHECK("t3_scales_kernel");
+    if (pl->col_scale != nullptr) {
+      // caller-provided (job-wide) scales: float bit patterns, as the kernel would write
+      RR_CUDA_CHECK(cudaMemcpyAsync(scales, pl->col_scale, (size_t)(d + 1) * sizeof(float),
+                                    cudaMemcpyDeviceToDevice, st));
+    } else {
+      const int blocks = sm_count() * 4;
+      t3_scales_kernel<<<blocks, 256, (size_t)(d + 1) * sizeof(unsigned int), st>>>(
+          X, (p != nullptr) ? y : nullptr, N, d, need_x ? 1 : 0, scales);
+      RR_LAUNCH_CHECK("t3_scales_kernel");
+    }
     const int nth = pl->ktot > pl->next ? pl->ktot : pl->next;
     t3_colamp_kernel<<<(nth + 256) / 256, 256, 0, st>>>(*pl, scales, camp);
     RR_LAUNCH_CHECK("t3_colamp_kernel");

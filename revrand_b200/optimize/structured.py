@@ -114,6 +114,19 @@ def _random_starts(fun, parameters, jac, args, nstarts, random_state,
     log.info("Evaluating random starts...")
     best_obj, best = None, None
     value_only = getattr(fun, "value_only", None) if data_gen is None else None
+    value_batch = getattr(fun, "value_only_batch", None) if data_gen is None else None
+    if value_batch is not None:
+        # the draws do not depend on the objective: take them all first (same
+        # generator order as the loop below), then let the objective pipeline the
+        # independent evaluations
+        cands = [_map_params(lambda p: p.rvs(random_state), parameters)
+                 for _ in range(nstarts)]
+        objs = value_batch([tuple(chain(c, args)) for c in cands])
+        for cand, obj in zip(cands, objs):
+            if best_obj is None or obj < best_obj:
+                best_obj, best = obj, cand
+        log.info("Best start found with objective = {}".format(best_obj))
+        return flatten_values(best)
     for _ in range(nstarts):
         batch = next(data_gen) if data_gen else ()
         cand = _map_params(lambda p: p.rvs(random_state), parameters)

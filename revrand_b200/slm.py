@@ -74,6 +74,20 @@ class _SLMProblem(object):
         self.R = self.rflat[:nfl - 1].view(self.plan.d, max(self.plan.ktot, 1))
         self.sqerr = self.rflat[nfl - 1:]
         self.yy = None
+        self._refresh_col_scale()
+
+    def _refresh_col_scale(self):
+        """max |X[:, i]|, max |y| over all rows of all ranks: the fixed-point scales
+        of the int8 value pass, found once per data set instead of once per
+        evaluation, and identical on every rank (rr_plan.col_scale)."""
+        t = eng.torch()
+        if self.Xd.shape[0]:
+            amax = t.cat([self.Xd.abs().amax(dim=0), self.yd.abs().max().reshape(1)]).float()
+        else:
+            amax = t.zeros(self.d + 1, dtype=t.float32, device=self.Xd.device)
+        if self.world > 1:
+            t.distributed.all_reduce(amax, op=t.distributed.ReduceOp.MAX)
+        self.plan.set_col_scale(amax.contiguous())
 
     def upload(self, X, y):
         """Replace the device-resident rows by new host data of the same shape
@@ -92,6 +106,7 @@ class _SLMProblem(object):
         self.yd.copy_(host(y), non_blocking=True)
         self.yy = None
         self.Xhost_probe = np.asarray(X[:1], dtype=float).reshape(1, -1)
+        self._refresh_col_scale()
 
     def uses_tcgen05(self):
         """True when this problem's value pass runs on the tensor cores
@@ -151,12 +166,19 @@ class _SLMProblem(object):
         m32 = m.float().contiguous()
         self.rflat.zero_()
         g = None
+        from_stats = False
         if want_grad and plan.ktot:
             eng.slm_gradpass(plan, self.Xd, self.yd, m32, post.C32(), self.R,
                              self.sqerr, engine=self.engine)
+            eng.allreduce_sum_(self.rflat)
         else:
-            eng.slm_residual(plan, self.Xd, self.yd, m32, sqerr=self.sqerr)
-        eng.allreduce_sum_(self.rflat)
+            # value-only evaluation: sum Err^2 = y'y - 2 p'm + m'G m from the (already
+            # all-reduced, float64) statistics -- no second pass over the rows.  The
+            # quadratic form cancels y'y / sum Err^2 digits of the statistics' ~1e-7
+            # relative accuracy, so a nearly interpolating fit takes the residual pass
+            # after all (decided below, once the scalars are on the host).
+            from_stats = True
+            self.sqerr.copy_((self.yy - 2.0 * st.p.dot(m) + m.dot(st.G @ m)).reshape(1))
         cond = post.cond_est if post.cond_est is not None else logdet.new_zeros(())
         parts = [logdet.reshape(1), trgc.reshape(1), self.sqerr, cond.reshape(1), q]
         if want_grad and plan.ktot:
@@ -165,12 +187,90 @@ class _SLMProblem(object):
                          for b, ko in zip(plan.trig, plan.freq_offsets)])
             parts.append(g.reshape(-1))
         host = t.cat(parts).cpu().numpy()
+        if from_stats and not host[2] > config.SQERR_FROM_STATS_MIN * self.yy:
+            self.rflat.zero_()
+            eng.slm_residual(plan, self.Xd, self.yd, m32, sqerr=self.sqerr)
+            eng.allreduce_sum_(self.rflat)
+            host[2] = float(self.sqerr.item())
         out["logdet"], out["trgc"], out["sqerr"] = host[0], host[1], host[2]
         out["cond_est"] = host[3]
         out["q"] = host[4:4 + len(slices)]
         if g is not None:
             out["g"] = host[4 + len(slices):].reshape(len(plan.trig), plan.d)
         return out
+
+
+    def evaluate_values(self, cands):
+        """Value-only evaluations of INDEPENDENT hyper-parameter points (the
+        random starts of ``fit``, decorators.py:570-579; sweep points), pipelined:
+        the float64 solve of point i runs on a second stream while the value pass
+        of point i+1 runs on the tensor cores, and nothing in the loop waits for
+        the device -- all projections and regulariser diagonals go down in two
+        uploads before it, all results come back in one read after it.
+
+        ``cands``: list of (var, regs, hypers).  Returns a list of dicts with
+        ``logdet, trgc, sqerr, q, lam`` (as ``evaluate``), or None where the
+        Cholesky factorisation was unstable / the statistics-based residual sum
+        cancels too much (the caller re-runs those through ``evaluate``)."""
+        t = eng.torch()
+        plan = self.plan
+        n = len(cands)
+        if n == 0:
+            return []
+        dev = self.Xd.device
+        lams, slices = [], None
+        for var, regs, hyps in cands:
+            lam_np, sl = self.basis.regularizer_diagonal(self.Xhost_probe, *regs)
+            slices = sl if isinstance(sl, list) else [slice(0, self.D)]
+            lams.append(lam_np)
+        lam_dev = eng.to_device(np.stack(lams), t.float64)
+        Wts = None
+        if plan.trig:
+            Wts = eng.to_device(np.stack([plan.Wt_host([h for h in hyps])
+                                          for _, _, hyps in cands]))
+        if self.yy is None:            # y'y: once per data set (one tiny pass, one sync)
+            yy = (self.yd.double() ** 2).sum().reshape(1)
+            eng.allreduce_sum_(yy)
+            self.yy = float(yy.item())
+        if getattr(self, "_stats2", None) is None:
+            self._stats2 = eng.SuffStats(self.D)
+            self._side = t.cuda.Stream()
+        ring = [self.stats, self._stats2]
+        main, side = t.cuda.current_stream(), self._side
+        out = t.zeros((n, 4 + len(slices)), dtype=t.float64, device=dev)
+        done = [None, None]
+        try:
+            for i, (var, regs, hyps) in enumerate(cands):
+                st = ring[i & 1]
+                if done[i & 1] is not None:
+                    main.wait_event(done[i & 1])       # its previous solve has read it
+                st.zero_()
+                if Wts is not None:
+                    plan.point_Wt_at(Wts[i])
+                eng.slm_suffstats(plan, self.Xd, self.yd, st, engine=self.engine,
+                                  want_yy=False)
+                eng.allreduce_sum_(st.flat)
+                ready = t.cuda.Event()
+                ready.record(main)
+                side.wait_event(ready)
+                with t.cuda.stream(side):
+                    out[i] = eng.solve_value_scalars(st.G, st.p, float(var), lam_dev[i],
+                                                     self.yy, slices)
+                    ev = t.cuda.Event()
+                    ev.record(side)
+                done[i & 1] = ev
+        finally:
+            plan.point_Wt_at(None)
+            main.wait_stream(side)
+        host = out.cpu().numpy()
+        res = []
+        for i in range(n):
+            h = host[i]
+            good = (h[0] == 1.0 and np.all(np.isfinite(h))
+                    and h[3] > config.SQERR_FROM_STATS_MIN * self.yy)
+            res.append(dict(logdet=h[1], trgc=h[2], sqerr=h[3], q=h[4:], lam=lams[i],
+                            slices=slices) if good else None)
+        return res
 
 
 class StandardLinearModel(BaseEstimator, RegressorMixin):
@@ -223,10 +323,14 @@ class StandardLinearModel(BaseEstimator, RegressorMixin):
         elbo.value_only = lambda var, reg, hypers: self._elbo(
             X, y, var, reg, hypers, want_grad=False)[0]
 
+        if config.PIPELINE_STARTS:
+            elbo.value_only_batch = lambda pts: self._elbo_values(X, y, pts)
+
         res = nmin(elbo, params, method='L-BFGS-B', jac=True, tol=self.tol,
                    options={'maxiter': self.maxiter, 'maxcor': 100},
                    random_state=self.random_, nstarts=self.nstarts)
         self.var_, self.regularizer_, self.hypers_ = res.x
+        self.opt_message_ = res.get("message", "")
         self._sync_posterior(self._problem)
         log.info("Done! ELBO = {}, var = {}, reg = {}, hypers = {}, "
                  "message = {}.".format(-res['fun'], self.var_,
@@ -313,7 +417,7 @@ class StandardLinearModel(BaseEstimator, RegressorMixin):
         ELBO = -0.5 * (N * np.log(2 * np.pi * var) + r["sqerr"] / var
                        + r["trgc"] / var + (r["q"] / lam_s).sum() + r["logdet"]
                        + np.log(lam).sum() - D)
-        if ELBO > self.obj_:
+        if np.isfinite(ELBO) and ELBO > self.obj_:
             self._m_dev, self._post = r["m"], r["post"]
             self._best_point = (var, regs, hyps, float(r["cond_est"]))
             self.obj_ = ELBO
@@ -322,6 +426,19 @@ class StandardLinearModel(BaseEstimator, RegressorMixin):
         if log.isEnabledFor(logging.INFO):
             log.info("ELBO = {}, var = {}, reg = {}, hypers = {}."
                      .format(ELBO, var, reg, hypers))
+        if not np.isfinite(ELBO):
+            # a wild line-search step (var -> 0, lenscale -> 1e36 ...) can overflow the
+            # float32 posterior image; report a finite, very bad objective with a null
+            # gradient so that L-BFGS-B backs off instead of aborting on NaN
+            bad = np.finfo(float).max / 1e8
+            if not want_grad:
+                return bad, None
+            zl = [np.zeros_like(np.asarray(v, dtype=float)) if np.ndim(v) else 0.0
+                  for v in _aslist(reg)]
+            zh = [np.zeros_like(np.asarray(h, dtype=float)) if np.ndim(h) else 0.0
+                  for h in _aslist(hypers)]
+            return bad, [0.0, zl if isinstance(reg, list) else zl[0],
+                         zh if isinstance(hypers, list) else zh[0]]
         if not want_grad:
             return -ELBO, None
         dvar = 0.5 * (-N + (r["sqerr"] + r["trgc"]) / var) / var
@@ -340,8 +457,58 @@ class StandardLinearModel(BaseEstimator, RegressorMixin):
                 dh.append(float(gi[0] / (var * ls[0] ** 2)))
             else:
                 dh.append(float(gi.sum() / (var * ls[0] ** 2)))
+        dh = [np.nan_to_num(g) if np.ndim(g) else (g if np.isfinite(g) else 0.0) for g in dh]
         dhypers = dh if len(dh) != 1 else dh[0]
         return -ELBO, [-dvar, dL, dhypers]
+
+    def _elbo_values(self, X, y, points):
+        """-ELBO at each of ``points`` = [(var, reg, hypers), ...], independent
+        evaluations pipelined on the device (``_SLMProblem.evaluate_values``).
+        Points the pipelined solve cannot vouch for (unstable Cholesky factor,
+        near-interpolating fit) go through ``_elbo`` one by one."""
+        prob = self._get_problem(X, y)
+        t = eng.torch()
+        if prob.world > 1:  # every rank evaluates rank 0's points
+            flat = np.concatenate([np.ravel(np.asarray(v, dtype=float))
+                                   for pt in points for part in pt
+                                   for v in _aslist(part) if np.size(v)])
+            buf = eng.to_device(flat, t.float64)
+            t.distributed.broadcast(buf, src=0)
+            flat, pos, new = buf.cpu().numpy(), 0, []
+
+            def take(v):
+                nonlocal pos
+                n = int(np.size(v))
+                out = flat[pos:pos + n].reshape(np.shape(v))
+                pos += n
+                return float(out) if np.shape(v) == () else out
+            for var, reg, hyp in points:
+                var = take(var)
+                reg = [take(r) for r in reg] if isinstance(reg, list) else take(reg)
+                hyp = ([take(h) for h in hyp] if isinstance(hyp, list)
+                       else (take(hyp) if np.size(hyp) else hyp))
+                new.append((var, reg, hyp))
+            points = new
+        cands = []
+        for var, reg, hyp in points:
+            hyps = [h for h in _aslist(hyp)]
+            if len(hyps) == 1 and np.size(hyps[0]) == 0:
+                hyps = []
+            cands.append((var, _aslist(reg), hyps))
+        res = prob.evaluate_values(cands)
+        N, D = prob.N_total, prob.D
+        out = []
+        for (var, reg, hyp), r in zip(points, res):
+            if r is None:
+                out.append(self._elbo(X, y, var, reg, hyp, want_grad=False)[0])
+                continue
+            lam, slices = r["lam"], r["slices"]
+            lam_s = np.array([lam[s][0] for s in slices])
+            ELBO = -0.5 * (N * np.log(2 * np.pi * var) + r["sqerr"] / var
+                           + r["trgc"] / var + (r["q"] / lam_s).sum() + r["logdet"]
+                           + np.log(lam).sum() - D)
+            out.append(-ELBO if np.isfinite(ELBO) else np.finfo(float).max / 1e8)
+        return out
 
     def _sync_posterior(self, prob=None):
         """Materialise the cached best posterior as numpy attributes.  (If it came

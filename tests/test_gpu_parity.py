@@ -719,3 +719,68 @@ def test_glm_predict_moments_cdf_interval_vs_reference(name):
         ok = ~np.isnan(ref)
         # continuous (Gaussian): the root itself; discrete: the jump both methods sit on
         np.testing.assert_allclose(got[ok], ref[ok], rtol=1e-4, atol=1e-4)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("engine,N,d,K", [("simt", 1500, 3, 40), ("tcgen05", 30011, 6, 96)])
+def test_pipelined_value_evaluations_equal_the_blocking_ones(engine, N, d, K):
+    """_SLMProblem.evaluate_values (random starts of fit: solve of point i on a
+    second stream behind the value pass of point i+1, sum Err^2 from the float64
+    statistics) against one blocking evaluate() per point, and against the oracle."""
+    from revrand_b200.slm import _SLMProblem
+    X, y = _synthetic(N, d, seed=31)
+    basis = bf.RandomRBF(nbases=K, Xdim=d, random_state=4,
+                         lenscale=Parameter(np.full(d, 1.5), Positive()))
+    rs = np.random.RandomState(8)
+    cands = [(float(rs.gamma(1.0) + 0.01), [float(rs.gamma(1.0) + 0.05)],
+              [1.5 * (0.5 + rs.rand(d))]) for _ in range(7)]
+    old = config.ENGINE
+    config.ENGINE = engine
+    try:
+        prob = _SLMProblem(basis, X, y)
+        batch = prob.evaluate_values(cands)
+        for (var, regs, hyps), b in zip(cands, batch):
+            assert b is not None
+            r = prob.evaluate(var, regs, hyps, want_grad=False)
+            np.testing.assert_allclose(b["logdet"], r["logdet"], rtol=1e-10)
+            np.testing.assert_allclose(b["trgc"], r["trgc"], rtol=1e-8)
+            np.testing.assert_allclose(b["q"], r["q"], rtol=1e-9)
+            np.testing.assert_allclose(b["sqerr"], r["sqerr"], rtol=1e-9)
+            # ... and the residual pass over the rows agrees with the statistics
+            m32 = r["m"].float().contiguous()
+            sq = _engine.slm_residual(prob.plan, prob.Xd, prob.yd, m32)
+            np.testing.assert_allclose(float(sq.item()), b["sqerr"], rtol=2e-5)
+        var, regs, hyps = cands[0]
+        ref = orc.slm_elbo(X, y, var, regs, [dict(kind="trig", W=basis.W, lenscale=hyps[0],
+                                                   cols=None)])
+        err = y - orc.trig_features(X, basis.W, hyps[0]).dot(ref["m"])
+        np.testing.assert_allclose(batch[0]["sqerr"], err.dot(err), rtol=1e-5)
+    finally:
+        config.ENGINE = old
+
+
+@pytest.mark.gpu
+def test_fit_with_pipelined_starts_equals_sequential_starts():
+    """The random-start phase as one pipelined batch picks the same start (and the
+    fit ends at the same optimum) as one blocking evaluation per start."""
+    rs = np.random.RandomState(0)
+    X = np.sort(rs.uniform(-5, 5, size=(1000, 1)), axis=0)
+    y = np.sin(X[:, 0]) + 0.1 * rs.randn(1000)
+    out = []
+    for pipe in (True, False):
+        old = config.PIPELINE_STARTS
+        config.PIPELINE_STARTS = pipe
+        try:
+            slm = rr.StandardLinearModel(basis=bf.RandomRBF(nbases=256, Xdim=1, random_state=1),
+                                         nstarts=100, maxiter=200, random_state=2)
+            slm.fit(X, y)
+        finally:
+            config.PIPELINE_STARTS = old
+        out.append((slm.obj_, slm.var_, slm.regularizer_, slm.hypers_))
+    # the unmodified reference with the same seeds: ELBO 884.1130585887014,
+    # var 0.009382774997534381, reg 2.604544348753961, lenscale 2.3147175684812105
+    for obj, var, reg, hyp in out:
+        np.testing.assert_allclose(obj, 884.1130585887014, rtol=1e-6)
+        np.testing.assert_allclose(var, 0.009382774997534381, rtol=1e-3)
+        np.testing.assert_allclose(reg, 2.604544348753961, rtol=1e-2)
+        np.testing.assert_allclose(hyp, 2.3147175684812105, rtol=1e-3)

@@ -35,7 +35,7 @@ def test_library_exports_every_declared_symbol():
     for name in declared:
         assert getattr(lib, name) is not None
     assert lib.rr_version() >= 100
-    assert ctypes.sizeof(_cabi.RRPlan) == 16 + 9 * ctypes.sizeof(ctypes.c_void_p)
+    assert ctypes.sizeof(_cabi.RRPlan) == 16 + 10 * ctypes.sizeof(ctypes.c_void_p)
     # shape queries need no GPU
     assert lib.rr_tcgen05_supported(21, 2048, 0, 4096) == 1
     assert lib.rr_tcgen05_supported(21, 2048, 22, 4118) == 1   # affine columns ride along
@@ -312,6 +312,33 @@ def test_blocked_spd_inverse_matches_numpy():
     ref = np.linalg.inv(S)
     assert np.max(np.abs(C - ref)) < 1e-10 * np.max(np.abs(ref))
     assert np.max(np.abs(C - C.T)) < 1e-12
+
+
+def test_batched_triangular_inverse_levels_and_padding():
+    """_engine._tri_inv_lower, level-by-level batched form: exact power-of-two
+    blocking, identity padding, and the recursion it replaces give the same L^-1."""
+    import torch
+    rs = np.random.RandomState(5)
+    old = _engine._BLOCK_INV_LEAF
+    try:
+        for n, leaf in ((512, 64), (700, 128), (130, 64), (37, 8)):
+            A = rs.randn(n, 2 * n)
+            L = torch.linalg.cholesky(torch.from_numpy(A.dot(A.T) / n + 0.5 * np.eye(n)))
+            _engine._BLOCK_INV_LEAF = leaf
+            out = torch.empty_like(L)
+            _engine._tri_inv_lower(L, out)
+            ref = np.linalg.inv(L.numpy())
+            assert np.max(np.abs(out.numpy() - ref)) < 1e-11 * np.max(np.abs(ref)), (n, leaf)
+            assert np.max(np.abs(np.triu(out.numpy(), 1))) == 0.0
+            _engine._BLOCK_INV_BATCHED = False
+            try:
+                out2 = torch.empty_like(L)
+                _engine._tri_inv_lower(L, out2)
+            finally:
+                _engine._BLOCK_INV_BATCHED = True
+            assert np.max(np.abs(out2.numpy() - ref)) < 1e-11 * np.max(np.abs(ref))
+    finally:
+        _engine._BLOCK_INV_LEAF = old
 
 
 def test_bench_reference_arm_prints_the_contract_line():
