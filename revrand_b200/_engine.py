@@ -18,6 +18,7 @@ from ._cabi import RRPlan, RevrandB200Error, check
 CHOLTHRESH = 1e-5   # revrand/mathfun/linalg.py:31
 SVD_FLOOR = 1e-15   # revrand/mathfun/linalg.py:128 (s_tol)
 TWO_PI = 2.0 * math.pi
+WT_CLIP = 1e30      # bound on |W / lenscale / 2pi| sent to the device (see Wt_host)
 
 _torch = None
 
@@ -275,9 +276,12 @@ class FeaturePlan(object):
             keep = [b.lenscale for b in self.trig]
             for b, ls in zip(self.trig, lenscales):
                 b.lenscale = np.atleast_1d(np.asarray(ls, dtype=np.float64))
-        # (a random start may draw a lengthscale so small that W / l leaves the
-        # fp32 range: keep it finite, the phase is meaningless there anyway)
-        Wt = np.clip(self.Wfull * self.inv_lenscale_full() / TWO_PI, -3e38, 3e38)
+        # (a random start or a line-search step to the edge of the log-warp box may
+        # ask for a lengthscale so small that W / l leaves the fp32 range: keep the
+        # projection u = x . Wt finite -- WT_CLIP * d * max|x| < 3.4e38 -- so that the
+        # exact range reduction returns phase 0 instead of NaN; the phase is
+        # meaningless there anyway, as is cos(1e100 x) in float64)
+        Wt = np.clip(self.Wfull * self.inv_lenscale_full() / TWO_PI, -WT_CLIP, WT_CLIP)
         if lenscales is not None:
             for b, ls in zip(self.trig, keep):
                 b.lenscale = ls
@@ -611,7 +615,10 @@ class Posterior(object):
 
 
 _BLOCK_INV_MIN = 1024   # below this potri is as fast
-_BLOCK_INV_LEAF = 512
+_BLOCK_INV_LEAF = 128         # diagonal blocks inverted by ONE batched trsm (cuBLAS's
+                              # batched trsm is fast up to 256: 0.11 ms for 32 x 128^2,
+                              # 2.0 ms for 8 x 512^2 at D = 4096)
+_GRAM_LEAF = 512              # recursion leaf of L^-T L^-1
 _BLOCK_INV_CUDA_ONLY = True   # tests flip this to exercise the blocked paths on CPU
 _BLOCK_INV_BATCHED = True     # level-by-level batched triangular inverse (False: recursion)
 
@@ -677,7 +684,7 @@ def _tri_inv_lower(L, out):
         if Op is not out:
             out.copy_(Op[:n, :n])
         return
-    if n <= _BLOCK_INV_LEAF:
+    if n <= max(_BLOCK_INV_LEAF, 256):
         out.copy_(t.linalg.solve_triangular(
             L, t.eye(n, dtype=L.dtype, device=L.device), upper=False))
         return
@@ -694,7 +701,7 @@ def _gram_of_lower(Li, out):
     (only half-size GEMMs; the zero block of Li is never multiplied)."""
     t = torch()
     n = Li.shape[0]
-    if n <= _BLOCK_INV_LEAF:
+    if n <= _GRAM_LEAF:
         t.matmul(Li.T, Li, out=out)
         return
     h = _split(n)

@@ -51,3 +51,11 @@ SQERR_FROM_STATS_MIN = float(os.environ.get("REVRAND_B200_SQERR_STATS_MIN", "1e-
 # the float64 solve of one start overlaps the value pass of the next, with no host
 # synchronisation inside the loop.  False: one blocking evaluation per start.
 PIPELINE_STARTS = os.environ.get("REVRAND_B200_PIPELINE_STARTS", "1") != "0"
+
+# GeneralizedLinearModel.fit keeps the SVI loop on the device (parameters, update
+# rule, mixture-entropy terms, minibatch gather; replayed as a CUDA graph) when the
+# likelihood has no learnable parameter.  False: the host loop of the reference's
+# structured_sgd(logtrick_sgd(sgd)) composition around the device step.
+GLM_DEVICE_LOOP = os.environ.get("REVRAND_B200_GLM_DEVICE_LOOP", "1") != "0"
+# ... replayed as a CUDA graph from its third step on (False: eager launches).
+GLM_DEVICE_GRAPH = os.environ.get("REVRAND_B200_GLM_DEVICE_GRAPH", "1") != "0"

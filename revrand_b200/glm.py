@@ -158,11 +158,15 @@ class GeneralizedLinearModel(BaseEstimator, RegressorMixin):
         log.info("Optimising parameters...")
         self._it = -self.nstarts
         self._plan_cache = None
-        nsgd = structured_sgd(logtrick_sgd(sgd))
-        res = nsgd(self._elbo, params, data, eval_obj=True,
-                   maxiter=self.maxiter, updater=self.updater,
-                   batch_size=self.batch_size, random_state=self.random_,
-                   nstarts=self.nstarts)
+        from . import _svi
+        if _svi.supported(self, likelihood_args):
+            res = self._fit_on_device(params, data)
+        else:
+            nsgd = structured_sgd(logtrick_sgd(sgd))
+            res = nsgd(self._elbo, params, data, eval_obj=True,
+                       maxiter=self.maxiter, updater=self.updater,
+                       batch_size=self.batch_size, random_state=self.random_,
+                       nstarts=self.nstarts)
         (self.weights_, self.covariance_, self.regularizer_,
          self.like_hypers_, self.basis_hypers_) = res.x
         log.info("Finished! reg = {}, likelihood_hypers = {}, "
@@ -171,6 +175,22 @@ class GeneralizedLinearModel(BaseEstimator, RegressorMixin):
                          self.basis_hypers_, res.message))
         self._plan_cache = None
         return self
+
+    def _fit_on_device(self, params, data):
+        """The optimisation of ``fit`` with the SGD loop resident on the device
+        (``_svi.DeviceSVI``): same composition as structured_sgd(logtrick_sgd(sgd)) --
+        an initial draw, the random starts (each on the next minibatch, objective
+        through ``_elbo``), then ``maxiter`` steps."""
+        from . import _svi
+        from .optimize.sgd import gen_batch
+        from .optimize.structured import _map_params, _random_starts, flatten_values
+        x0 = flatten_values(_map_params(lambda p: p.rvs(None), params))
+        if self.nstarts > 0:
+            data_gen = gen_batch(data, self.batch_size, random_state=self.random_)
+            x0 = flatten_values(_random_starts(self._elbo, params, True, (), self.nstarts,
+                                               self.random_, data_gen))
+        run = _svi.DeviceSVI(self, params, data, self.maxiter, self.random_, x0=x0)
+        return run.run().result()
 
     def svi_stepper(self, X, y, likelihood_args=(), maxiter=10 ** 9):
         """The loop body of ``fit`` as an object: ``step()`` runs ONE SVI
@@ -193,6 +213,10 @@ class GeneralizedLinearModel(BaseEstimator, RegressorMixin):
                   self.basis.params]
         self._it = 1            # > 0: no ELBO logging evaluation on benchmark steps
         self._plan_cache = None
+        from . import _svi
+        if _svi.supported(self, likelihood_args):
+            return _DeviceStepper(_svi.DeviceSVI(self, params, data, maxiter, self.random_),
+                                  self, X.shape[1])
         holder = {}
 
         def capture(fun, x0, data, **kw):
@@ -441,6 +465,30 @@ class GeneralizedLinearModel(BaseEstimator, RegressorMixin):
                 type(self).__name__, self.likelihood, self.basis, self.K,
                 self.maxiter, self.batch_size, self.updater, self.nsamples,
                 self.nstarts, self.random_state)
+
+
+class _DeviceStepper(object):
+    """``svi_stepper`` on the device-resident loop: nothing crosses the host
+    boundary in a step except, amortised, the next chunk of minibatch indices."""
+
+    def __init__(self, run, glm, d):
+        self.run, self.glm, self.d = run, glm, d
+        self.d2h_bytes = 0
+
+    @property
+    def h2d_bytes(self):
+        return int(self.run.B * 8)      # this step's minibatch indices (uploaded in chunks)
+
+    def step(self):
+        return self.run.step()
+
+    def objective(self):
+        """-ELBO estimate of the last step (one 8-byte read, synchronises)."""
+        r = self.run
+        return float(r.objs[(r.it - 1) % r.ntrace].item())
+
+    def device_ms(self, reps=5):
+        return _SVIStepper.device_ms(self, reps)
 
 
 class _SVIStepper(object):

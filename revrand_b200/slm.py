@@ -524,8 +524,41 @@ class StandardLinearModel(BaseEstimator, RegressorMixin):
             self._m_dev, self._post = post.m, post
             self._best_point = best[:3] + (0.0,)
         if getattr(self, "_m_dev", None) is not None:
-            self.weights_ = self._m_dev.cpu().numpy()
-            self.covariance_ = self._post.C.cpu().numpy()
+            # the host copies are made when somebody reads weights_ / covariance_
+            # (D^2 float64: 134 MB at config 2 -- not on the path of an evaluation)
+            self._host_posterior = None
+            self._have_posterior = True
+
+    def _materialise_posterior(self):
+        hp = self.__dict__.get("_host_posterior")
+        if hp is None:
+            if not self.__dict__.get("_have_posterior", False):
+                raise AttributeError("posterior not available: call fit() first")
+            hp = (self._m_dev.cpu().numpy(), self._post.C.cpu().numpy())
+            self._host_posterior = hp
+        return hp
+
+    @property
+    def weights_(self):
+        """Posterior mean (slm.py:174), read back from the device on first use."""
+        return self._materialise_posterior()[0]
+
+    @weights_.setter
+    def weights_(self, value):
+        hp = self.__dict__.get("_host_posterior") or (None, None)
+        self._host_posterior = (np.asarray(value), hp[1])
+        self._have_posterior = True
+
+    @property
+    def covariance_(self):
+        """Posterior covariance (slm.py:175), read back from the device on first use."""
+        return self._materialise_posterior()[1]
+
+    @covariance_.setter
+    def covariance_(self, value):
+        hp = self.__dict__.get("_host_posterior") or (None, None)
+        self._host_posterior = (hp[0], np.asarray(value))
+        self._have_posterior = True
 
     # -- prediction ------------------------------------------------------------------
     def predict(self, X):
@@ -543,13 +576,20 @@ class StandardLinearModel(BaseEstimator, RegressorMixin):
         if len(hyps) == 1 and np.size(hyps[0]) == 0:
             hyps = []
         plan = self.basis._plan(X.shape[1], hyps)
-        m32 = eng.to_device(self.weights_)
-        C32 = eng.to_device(self.covariance_)
+        if self.__dict__.get("_host_posterior") is None and \
+                self.__dict__.get("_m_dev") is not None:
+            # posterior still resident from fit: no host round trip
+            m32, C32 = self._m_dev.float().contiguous(), self._post.C32()
+        else:
+            m32 = eng.to_device(self.weights_)
+            C32 = eng.to_device(self.covariance_)
         Ey, Vf = eng.slm_predict(plan, eng.to_device(X), m32, C32)
         return (Ey.double().cpu().numpy(),
                 Vf.double().cpu().numpy() + self.var_)
 
     def __getstate__(self):
+        if self.__dict__.get("_have_posterior", False):
+            self._materialise_posterior()
         state = dict(self.__dict__)
         for k in ("_problem", "_cached_problem", "_problem_key", "_m_dev",
                   "_post", "_best_point"):

@@ -61,6 +61,25 @@ print("cholesky_inverse (potri): %.2f ms" % timed(lambda: torch.cholesky_inverse
 print("cholesky_solve(I): %.2f ms" % timed(lambda: torch.cholesky_solve(I, L)))
 Li = torch.empty_like(L)
 print("tri_inv_lower (replicated part): %.2f ms" % timed(lambda: eng._tri_inv_lower(L, Li)))
+ref_inv = Li.clone()
+for leaf in (32, 64, 128, 256, 512, 1024):
+    eng._BLOCK_INV_LEAF = leaf
+    tm = timed(lambda: eng._tri_inv_lower(L, Li))
+    print("   batched, leaf %4d: %.2f ms (dev %.1e)" % (leaf, tm, float((Li - ref_inv).abs().max() / ref_inv.abs().max())))
+    nb = D // leaf
+    Vd = L.view(nb, leaf, nb, leaf).diagonal(dim1=0, dim2=2).permute(2, 0, 1).contiguous()
+    eye = torch.eye(leaf, dtype=L.dtype, device=L.device).expand(nb, leaf, leaf)
+    print("        leaves alone (batched trsm): %.2f ms" % timed(lambda: torch.linalg.solve_triangular(Vd, eye, upper=False)))
+eng._BLOCK_INV_BATCHED = False
+eng._BLOCK_INV_LEAF = 512
+print("recursive, leaf 512: %.2f ms" % timed(lambda: eng._tri_inv_lower(L, Li)))
+eng._BLOCK_INV_BATCHED = True
+A2 = torch.randn(4, 1024, 1024, dtype=torch.float64, device="cuda")
+print("bmm 4 x 1024^3 fp64: %.2f ms" % timed(lambda: torch.bmm(A2, A2)))
+A3 = torch.randn(8, 512, 512, dtype=torch.float64, device="cuda")
+print("bmm 8 x 512^3 fp64: %.2f ms" % timed(lambda: torch.bmm(A3, A3)))
+A4 = torch.randn(2048, 2048, dtype=torch.float64, device="cuda")
+print("mm 2048^3 fp64: %.2f ms" % timed(lambda: A4 @ A4))
 ws = 8
 per = D // ws
 for r in (0, 3, 7):

@@ -784,3 +784,42 @@ def test_fit_with_pipelined_starts_equals_sequential_starts():
         np.testing.assert_allclose(var, 0.009382774997534381, rtol=1e-3)
         np.testing.assert_allclose(reg, 2.604544348753961, rtol=1e-2)
         np.testing.assert_allclose(hyp, 2.3147175684812105, rtol=1e-3)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("updater", ["adam", "adadelta", "momentum"])
+def test_glm_device_resident_loop_equals_host_loop(updater):
+    """The device-resident SVI loop (_svi.DeviceSVI: parameters, mixture-entropy
+    terms, log warp and update rule as device tensors, replayed as a CUDA graph from
+    its third step) against the host composition structured_sgd(logtrick_sgd(sgd))
+    around ``_elbo``, same seeds: identical minibatches and noise, so the two
+    parameter trajectories agree to rounding."""
+    from revrand_b200.optimize import sgd as sgdmod
+    rs = np.random.RandomState(5)
+    N, d = 3000, 3
+    X = rs.uniform(-2, 2, size=(N, d))
+    y = rs.poisson(np.exp(np.sin(X[:, 0]) + 0.3 * X[:, 1])).astype(float)
+    mk = {"adam": lambda: sgdmod.Adam(alpha=0.02), "adadelta": lambda: sgdmod.AdaDelta(),
+          "momentum": lambda: sgdmod.Momentum(rho=0.5, eta=1e-4)}[updater]
+    out = []
+    for dev_loop, graph in ((True, True), (False, False), (True, False)):
+        old = config.GLM_DEVICE_LOOP, config.GLM_DEVICE_GRAPH
+        config.GLM_DEVICE_LOOP, config.GLM_DEVICE_GRAPH = dev_loop, graph
+        try:
+            basis = (bf.RandomRBF(nbases=24, Xdim=d, random_state=0,
+                                  lenscale=Parameter(np.array([1.0, 1.5, 2.0]), Positive()))
+                     + bf.LinearBasis(onescol=True))
+            glm = rr.GeneralizedLinearModel(likelihood=lk.Poisson('exp'), basis=basis, K=3,
+                                            maxiter=7, batch_size=256, nsamples=8, nstarts=3,
+                                            updater=mk(), random_state=11)
+            np.random.seed(123)          # the initial p.rvs(None) draw
+            glm.fit(X, y)
+        finally:
+            config.GLM_DEVICE_LOOP, config.GLM_DEVICE_GRAPH = old
+        out.append((glm.weights_, glm.covariance_, glm.regularizer_, glm.basis_hypers_))
+    m2, C2, r2, h2 = out[1]                       # the host loop
+    for m1, C1, r1, h1 in (out[2], out[0]):       # eager device loop, then graph replay
+        np.testing.assert_allclose(m1, m2, rtol=1e-6, atol=1e-8)
+        np.testing.assert_allclose(C1, C2, rtol=1e-6)
+        np.testing.assert_allclose(np.ravel(r1), np.ravel(r2), rtol=1e-6)
+        np.testing.assert_allclose(np.ravel(h1), np.ravel(h2), rtol=1e-6)
