@@ -313,6 +313,20 @@ int rr_tcgen05_selftest(double* max_abs_err);
 int rr_tcgen05_i8_selftest(int32_t kblocks, int64_t* mismatches);
 
 /*
+ * The fp32-grade tensor-core GEMM behind the GLM step and predictive sampler,
+ * callable on its own (tests, diagnostics): C (+)= alpha * A B^T for row-major fp32
+ * DEVICE matrices A (M x K, leading dimension lda), B (N x K, ldb), C (M x N, ldc);
+ * transa / transb != 0: the operand is stored K x M / K x N instead.  Operands are
+ * split into two tf32 parts, three tcgen05.mma.kind::tf32 products per k-step
+ * (every product to ~2^-21), fp32 accumulation in TMEM.  Workspace: at least
+ * 65536 * (ceil(M/256) + ceil(N/256)) * ceil(K/32) + 4096 bytes.
+ */
+int rr_tcgen05_gemm3(int32_t M, int32_t N, int32_t K, float alpha, const float* A,
+                     int64_t lda, int32_t transa, const float* B, int64_t ldb,
+                     int32_t transb, float* C, int64_t ldc, int32_t accumulate,
+                     void* workspace, size_t workspace_bytes, void* stream);
+
+/*
  * Diagnostic: repeat D += A B^T over one 128 x 256 x 64 fp16 tile `reps`
  * times in TMEM and return the fp32 accumulator (HOST pointers; A* are
  * (128,64), B* (256,64) fp16 bit patterns, D and Aux (128,256) float).

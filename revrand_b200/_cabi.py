@@ -73,6 +73,8 @@ SIGNATURES = {
     "rr_tcgen05_supported": (C.c_int, [_I32, _I32, _I32, _I32]),
     "rr_tcgen05_selftest": (C.c_int, [C.POINTER(C.c_double)]),
     "rr_tcgen05_i8_selftest": (C.c_int, [_I32, C.POINTER(_I64)]),
+    "rr_tcgen05_gemm3": (C.c_int, [_I32, _I32, _I32, _F32, _P, _I64, _I32, _P, _I64, _I32, _P,
+                                   _I64, _I32, _P, _SZ, _P]),
     "rr_tcgen05_accum_probe": (C.c_int, [_P, _P, _P, _P, _I32, _I32, _P, _P]),
 }
 

@@ -569,6 +569,24 @@ def glm_quantiles(Fd, lik, lik_param, lo_p, hi_p, largd=None):
     return ql, qu
 
 
+def tcgen05_gemm3(A, B, transa=False, transb=False, alpha=1.0, C=None, accumulate=False):
+    """C (+)= alpha * op(A) op(B)^T on the tcgen05 tf32x3 kernel.  ``A``: (M, K) float32
+    device tensor, or (K, M) with ``transa``; ``B``: (N, K), or (K, N) with ``transb``."""
+    t = require_cuda()
+    lib = _cabi.load()
+    A, B = A.contiguous(), B.contiguous()
+    M, K = (A.shape[1], A.shape[0]) if transa else A.shape
+    N = B.shape[1] if transb else B.shape[0]
+    if C is None:
+        C = t.zeros((M, N), dtype=t.float32, device=A.device)
+    nb = 65536 * (-(-M // 256) + -(-N // 256)) * -(-K // 32) + 8192
+    ws = workspace(nb)
+    check(lib.rr_tcgen05_gemm3(M, N, K, float(alpha), _ptr(A), A.shape[1], int(transa), _ptr(B),
+                               B.shape[1], int(transb), _ptr(C), C.stride(0), int(accumulate),
+                               _ptr(ws), ws.numel(), _stream_ptr()), "rr_tcgen05_gemm3")
+    return C
+
+
 def tcgen05_selftest():
     require_cuda()
     err = C.c_double(0.0)

@@ -29,7 +29,7 @@ import numpy as np
 from . import _engine as eng
 from . import config
 from .btypes import Positive
-from .optimize import sgd as _sgd
+from . import optimize as _sgd      # (its names: Adam, SGDUpdater, Momentum, AdaGrad, AdaDelta)
 from .optimize.structured import (EXPMAX, LOGMINPOS, Layout, _flat_bounds,
                                   _map_params, flatten_values)
 

@@ -109,6 +109,15 @@ int sgemm(int M, int N, int K, float alpha, const float* A, int64_t sAm,
           int64_t sAk, const float* B, int64_t sBk, int64_t sBn, float* Cf,
           double* Cd, int64_t ldc, int accumulate, cudaStream_t st);
 
+// The same product (fp32 output) on the tcgen05 tensor cores, operands split into two
+// tf32 parts, three products (rr_tc_gemm3.cu).  imgA / imgB: scratch of
+// gemm3_image_bytes(M, K) / gemm3_image_bytes(N, K) bytes.
+size_t gemm3_image_bytes(int64_t R, int64_t K);
+bool gemm3_worthwhile(int M, int N, int K);
+int gemm3(int M, int N, int K, float alpha, const float* A, int64_t sAm, int64_t sAk,
+          const float* B, int64_t sBk, int64_t sBn, float* C, int64_t ldc, int accumulate,
+          uint8_t* imgA, uint8_t* imgB, cudaStream_t st);
+
 // R (d x kt, float64) += X^T Q for row-major fp32 X (rows x d), Q (rows x kt).
 int xtq(const float* X, const float* Q, int rows, int d, int kt, double* R, cudaStream_t st);
 

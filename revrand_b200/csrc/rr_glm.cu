@@ -336,6 +336,36 @@ glm_quantile_kernel(const float* __restrict__ F, int rows, int S, int lik, float
   }
 }
 
+// scratch for the tile-major tf32 operand images of the tensor-core GEMMs
+// (rr_tc_gemm3.cu): the largest A-side and B-side operand of the pass
+static size_t glm_img_a(int op, int64_t R, int D, int S) {
+  size_t a = gemm3_image_bytes(R, D);                       // F = Phi Ws^T
+  if (op == RR_OP_GLM_STEP) {
+    const size_t b = gemm3_image_bytes(S, R), c = gemm3_image_bytes(R, S);
+    a = a > b ? a : b;                                      // Edws = dF^T Phi
+    a = a > c ? a : c;                                      // EdPhi = dF Ws
+  }
+  return align_up(a, 1024);
+}
+static size_t glm_img_b(int op, int64_t R, int D, int S) {
+  size_t a = gemm3_image_bytes(S, D);
+  if (op == RR_OP_GLM_STEP) {
+    const size_t b = gemm3_image_bytes(D, R), c = gemm3_image_bytes(D, S);
+    a = a > b ? a : b;
+    a = a > c ? a : c;
+  }
+  return align_up(a, 1024);
+}
+// fp32-output product: tensor cores when the product is large enough to pay for
+// packing its operands, CUDA cores otherwise
+static int glm_gemm(int M, int N, int K, float alpha, const float* A, int64_t sAm, int64_t sAk,
+                    const float* B, int64_t sBk, int64_t sBn, float* C, int64_t ldc,
+                    int accumulate, uint8_t* imgA, uint8_t* imgB, cudaStream_t st) {
+  if (imgA && imgB && gemm3_worthwhile(M, N, K))
+    return gemm3(M, N, K, alpha, A, sAm, sAk, B, sBk, sBn, C, ldc, accumulate, imgA, imgB, st);
+  return sgemm(M, N, K, alpha, A, sAm, sAk, B, sBk, sBn, C, nullptr, ldc, accumulate, st);
+}
+
 size_t glm_workspace_bytes(int op, int64_t M, const rr_plan* pl, int S) {
   int64_t R = M < GLM_CHUNK ? M : GLM_CHUNK;
   if (R < 1) R = 1;
@@ -343,8 +373,11 @@ size_t glm_workspace_bytes(int op, int64_t M, const rr_plan* pl, int S) {
   size_t f = align_up((size_t)R * S * 4, 256);
   size_t ws = align_up((size_t)S * pl->D * 4, 256);
   size_t q = align_up((size_t)R * (pl->ktot > 0 ? pl->ktot : 1) * 4, 256);
-  if (op == RR_OP_GLM_STEP) return 2 * phi + f + 2 * ws + q + 2048;
-  return phi + f + 1024;
+  size_t img = 0;
+  if (gemm3_worthwhile((int)R, S, pl->D))
+    img = glm_img_a(op, R, pl->D, S) + glm_img_b(op, R, pl->D, S) + 2048;
+  if (op == RR_OP_GLM_STEP) return 2 * phi + f + 2 * ws + q + img + 2048;
+  return phi + f + img + 1024;
 }
 
 }  // namespace rr
@@ -376,6 +409,14 @@ extern "C" int rr_glm_step(const rr_plan* plan, const float* X, const float* y,
     set_error("glm_step workspace too small");
     return RR_ERR_WORKSPACE;
   }
+  // operand images of the tensor-core GEMMs (absent in a caller's smaller, older
+  // workspace: the CUDA-core kernel then does the products)
+  uint8_t* imgA = nullptr;
+  uint8_t* imgB = nullptr;
+  if (gemm3_worthwhile((int)R, S, D)) {
+    imgA = W.take<uint8_t>(glm_img_a(RR_OP_GLM_STEP, R, D, S));
+    imgB = W.take<uint8_t>(glm_img_b(RR_OP_GLM_STEP, R, D, S));
+  }
   {
     int64_t total = (int64_t)S * D;
     draw_weights_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(
@@ -387,19 +428,19 @@ extern "C" int rr_glm_step(const rr_plan* plan, const float* X, const float* y,
     int rc = launch_features(plan, X + s * d, rows, Phi, D, st);
     if (rc) return rc;
     // F = Phi Ws^T  (glm.py:303)
-    rc = sgemm(rows, S, D, 1.0f, Phi, D, 1, Ws, 1, D, F, nullptr, S, 0, st);
+    rc = glm_gemm(rows, S, D, 1.0f, Phi, D, 1, Ws, 1, D, F, S, 0, imgA, imgB, st);
     if (rc) return rc;
     dim3 lg(Kmix, (rows + LIK_ROWS - 1) / LIK_ROWS);
     lik_kernel<<<lg, 256, 0, st>>>(F, rows, S, L, y + s, larg ? larg + s : nullptr,
                                    lik, lik_param, Ell, dlpar);
     RR_LAUNCH_CHECK("lik_kernel");
     // Edws (+)= dF^T Phi  (glm.py:307)
-    rc = sgemm(S, D, rows, 1.0f, F, 1, S, Phi, D, 1, Edws, nullptr, D, s > 0, st);
+    rc = glm_gemm(S, D, rows, 1.0f, F, 1, S, Phi, D, 1, Edws, D, s > 0, imgA, imgB, st);
     if (rc) return rc;
     if (Rout && kt > 0) {
       // EdPhi = dF Ws / (L Kmix)  (glm.py:310, :246)
-      rc = sgemm(rows, D, S, 1.0f / (float)(L * Kmix), F, S, 1, Ws, D, 1, T,
-                 nullptr, D, 0, st);
+      rc = glm_gemm(rows, D, S, 1.0f / (float)(L * Kmix), F, S, 1, Ws, D, 1, T, D, 0, imgA,
+                    imgB, st);
       if (rc) return rc;
       dim3 qg((kt + 255) / 256, rows);
       q_plain_kernel<<<qg, 256, 0, st>>>(*plan, Phi, T, D, rows, Q);
@@ -430,11 +471,17 @@ extern "C" int rr_glm_predict(const rr_plan* plan, const float* X, int64_t N,
   float* Phi = W.take<float>((size_t)R * D);
   float* F = W.take<float>((size_t)R * S);
   if (!Phi || !F) { set_error("glm_predict workspace too small"); return RR_ERR_WORKSPACE; }
+  uint8_t* imgA = nullptr;
+  uint8_t* imgB = nullptr;
+  if (gemm3_worthwhile((int)R, S, D)) {
+    imgA = W.take<uint8_t>(glm_img_a(RR_OP_GLM_PREDICT, R, D, S));
+    imgB = W.take<uint8_t>(glm_img_b(RR_OP_GLM_PREDICT, R, D, S));
+  }
   for (int64_t s = 0; s < N; s += R) {
     int rows = (int)((N - s) < R ? (N - s) : R);
     int rc = launch_features(plan, X + s * plan->d, rows, Phi, D, st);
     if (rc) return rc;
-    rc = sgemm(rows, S, D, 1.0f, Phi, D, 1, ws, 1, D, F, nullptr, S, 0, st);
+    rc = glm_gemm(rows, S, D, 1.0f, Phi, D, 1, ws, 1, D, F, S, 0, imgA, imgB, st);
     if (rc) return rc;
     predict_reduce_kernel<<<(rows + 7) / 8, 256, 0, st>>>(
         F, rows, S, lik, larg ? larg + s : nullptr, Ey + s, Ey2 ? Ey2 + s : nullptr);

@@ -104,7 +104,14 @@ static size_t simt_ws(int op, int64_t N, const rr_plan* pl) {
   switch (op) {
     case RR_OP_SUFFSTATS: return phi + 256;
     case RR_OP_GRADPASS: return 2 * phi + q + align_up((size_t)(N > 0 ? N : 1) * 4, 256) + 1024;
-    case RR_OP_PREDICT: return 2 * phi + 1024;
+    case RR_OP_PREDICT: {
+      // + the tf32 operand images of Phi (chunk) and C for the tensor-core product
+      size_t img = 0;
+      if (gemm3_worthwhile((int)R, pl->D, pl->D))
+        img = align_up(gemm3_image_bytes(R, pl->D), 1024) +
+              align_up(gemm3_image_bytes(pl->D, pl->D), 1024) + 2048;
+      return 2 * phi + img + 1024;
+    }
     case RR_OP_RESIDUAL: return align_up((size_t)(N > 0 ? N : 1) * 4, 256) + 512;
     default: return 0;
   }
@@ -251,12 +258,23 @@ extern "C" int rr_slm_predict(const rr_plan* plan, const float* X, int64_t N,
   float* Phi = W.take<float>((size_t)R * D);
   float* T = Vf ? W.take<float>((size_t)R * D) : nullptr;
   if (!Phi || (Vf && !T)) { set_error("predict workspace too small"); return RR_ERR_WORKSPACE; }
+  // Phi C on the tcgen05 tensor cores (tf32, three-product split: fp32 grade) when the
+  // product is large enough to pay for packing its operands
+  uint8_t* imgA = nullptr;
+  uint8_t* imgB = nullptr;
+  if (Vf && gemm3_worthwhile((int)R, D, D)) {
+    imgA = W.take<uint8_t>(align_up(gemm3_image_bytes(R, D), 1024));
+    imgB = W.take<uint8_t>(align_up(gemm3_image_bytes(D, D), 1024));
+  }
   for (int64_t s = 0; s < N; s += R) {
     int rows = (int)((N - s) < R ? (N - s) : R);
     int rc = launch_features(plan, X + s * plan->d, rows, Phi, D, st);
     if (rc) return rc;
     if (Vf) {
-      rc = sgemm(rows, D, D, 1.0f, Phi, D, 1, C, D, 1, T, nullptr, D, 0, st);
+      if (imgA && imgB)
+        rc = gemm3(rows, D, D, 1.0f, Phi, D, 1, C, D, 1, T, D, 0, imgA, imgB, st);
+      else
+        rc = sgemm(rows, D, D, 1.0f, Phi, D, 1, C, D, 1, T, nullptr, D, 0, st);
       if (rc) return rc;
     }
     rowdot_kernel<<<(rows + 7) / 8, 256, 0, st>>>(Phi, T, D, rows, D, m,

@@ -794,7 +794,7 @@ def test_glm_device_resident_loop_equals_host_loop(updater):
     its third step) against the host composition structured_sgd(logtrick_sgd(sgd))
     around ``_elbo``, same seeds: identical minibatches and noise, so the two
     parameter trajectories agree to rounding."""
-    from revrand_b200.optimize import sgd as sgdmod
+    from revrand_b200 import optimize as sgdmod
     rs = np.random.RandomState(5)
     N, d = 3000, 3
     X = rs.uniform(-2, 2, size=(N, d))
@@ -823,3 +823,65 @@ def test_glm_device_resident_loop_equals_host_loop(updater):
         np.testing.assert_allclose(C1, C2, rtol=1e-6)
         np.testing.assert_allclose(np.ravel(r1), np.ravel(r2), rtol=1e-6)
         np.testing.assert_allclose(np.ravel(h1), np.ravel(h2), rtol=1e-6)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("M,N,K,ta,tb", [(8192, 500, 2048, False, False),   # F = Phi Ws^T
+                                         (500, 2048, 8192, True, True),     # Edws = dF^T Phi
+                                         (4096, 2048, 500, False, True),    # EdPhi = dF Ws
+                                         (300, 77, 130, False, False),
+                                         (257, 513, 33, True, False)])
+def test_tcgen05_tf32x3_gemm_vs_float64(M, N, K, ta, tb):
+    """The tensor-core GEMM of the GLM step (two tf32 parts per operand, three
+    products, fp32 accumulation in TMEM; split-K for short-and-wide outputs)
+    against float64, all operand layouts, ragged sizes, accumulation."""
+    import torch
+    g = torch.Generator(device="cuda").manual_seed(M + N + K)
+    A = torch.randn((K, M) if ta else (M, K), generator=g, device="cuda")
+    B = torch.randn((K, N) if tb else (N, K), generator=g, device="cuda") * 3.0
+    A[0, 0] = 1000.0                       # a wide dynamic range inside one operand
+    ref = (A.double().T if ta else A.double()) @ (B.double() if tb else B.double().T)
+    C = _engine.tcgen05_gemm3(A, B, transa=ta, transb=tb, alpha=0.5)
+    torch.cuda.synchronize()
+    err = float((C.double() - 0.5 * ref).norm() / (0.5 * ref).norm())
+    assert err < 3e-6, err
+    assert float((C.double() - 0.5 * ref).abs().max() / ref.abs().max()) < 1e-5
+    C2 = _engine.tcgen05_gemm3(A, B, transa=ta, transb=tb, alpha=0.25, C=C.clone(), accumulate=True)
+    torch.cuda.synchronize()
+    assert float((C2.double() - 0.75 * ref).norm() / ref.norm()) < 3e-6
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("likname", ["poisson_exp", "bernoulli"])
+def test_glm_step_through_tensor_core_gemms_vs_oracle(likname):
+    """One SVI step at a size whose three contractions run on the tcgen05 tf32x3
+    GEMM (M * S * D >= 2^26), injected noise, against the float64 oracle."""
+    rs = np.random.RandomState(17)
+    M, d, K, Kmix, L = 2048, 6, 192, 4, 32            # D = 384, S = 128
+    X = rs.randn(M, d).astype(np.float32).astype(np.float64)
+    ls = 1.5 * (1.0 + 0.1 * np.arange(d))
+    basis = bf.RandomRBF(nbases=K, Xdim=d, random_state=9,
+                         lenscale=Parameter(ls, Positive()), regularizer=Parameter(1.3, Positive()))
+    D = 2 * K
+    f = np.sin(X[:, 0]) + 0.3 * X[:, 1]
+    y = (rs.poisson(np.exp(f)) if likname == "poisson_exp"
+         else (rs.rand(M) < 1.0 / (1.0 + np.exp(-f)))).astype(float)
+    m = 0.1 * rs.randn(D, Kmix)
+    C = 0.05 + 0.1 * np.abs(rs.randn(D, Kmix))
+    eps = rs.randn(Kmix, L, D)
+    glm = rr.GeneralizedLinearModel(likelihood=LIK[likname](), basis=basis, K=Kmix, nsamples=L)
+    glm.B_, glm.D_, glm._it = 7.5, D, -1
+    glm.random_ = _Injected(eps)
+    old = config.GLM_HOST_RNG
+    config.GLM_HOST_RNG = True
+    try:
+        nelbo, (dm, dC, dreg, dlp, dbp) = glm._elbo(m, C, 1.3, [], ls, X, y)
+    finally:
+        config.GLM_HOST_RNG = old
+    lik_id = orc.LIK_POISSON_EXP if likname == "poisson_exp" else orc.LIK_BERNOULLI
+    blocks = [dict(kind="trig", W=basis.W, lenscale=ls, cols=None)]
+    ref = orc.glm_elbo(m, C, [1.3], lik_id, None, X, y, blocks, eps, 7.5)
+    assert abs(nelbo - ref["neg_elbo"]) <= 1e-4 * abs(ref["neg_elbo"])
+    assert relerr(dm, ref["dm"]) < 1e-4
+    assert relerr(dC, ref["dC"]) < 1e-4
+    assert relerr(dbp, ref["dbpars"][0]) < 1e-3
