@@ -356,6 +356,28 @@ static size_t glm_img_b(int op, int64_t R, int D, int S) {
   }
   return align_up(a, 1024);
 }
+// R (d x kt, float64) += C (d x kt, float32)
+__global__ void add_f32_to_f64_kernel(const float* __restrict__ Cf, double* __restrict__ R,
+                                      int64_t n) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) R[i] += (double)Cf[i];
+}
+
+// R += X^T Q (the lengthscale-gradient contraction): on the tensor cores as a
+// (d x kt x rows) product, d padded to one 256-row tile, when the scratch is there
+static int glm_xtq(const float* X, const float* Q, int rows, int d, int kt, double* R,
+                   float* Ctmp, uint8_t* imgA, uint8_t* imgB, cudaStream_t st) {
+  if (Ctmp && imgA && imgB && gemm3_worthwhile(256, kt, rows)) {
+    int rc = gemm3(d, kt, rows, 1.0f, X, 1, d, Q, kt, 1, Ctmp, kt, 0, imgA, imgB, st);
+    if (rc) return rc;
+    const int64_t n = (int64_t)d * kt;
+    add_f32_to_f64_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(Ctmp, R, n);
+    RR_LAUNCH_CHECK("add_f32_to_f64_kernel");
+    return RR_OK;
+  }
+  return xtq(X, Q, rows, d, kt, R, st);
+}
+
 // fp32-output product: tensor cores when the product is large enough to pay for
 // packing its operands, CUDA cores otherwise
 static int glm_gemm(int M, int N, int K, float alpha, const float* A, int64_t sAm, int64_t sAk,
@@ -375,7 +397,8 @@ size_t glm_workspace_bytes(int op, int64_t M, const rr_plan* pl, int S) {
   size_t q = align_up((size_t)R * (pl->ktot > 0 ? pl->ktot : 1) * 4, 256);
   size_t img = 0;
   if (gemm3_worthwhile((int)R, S, pl->D))
-    img = glm_img_a(op, R, pl->D, S) + glm_img_b(op, R, pl->D, S) + 2048;
+    img = glm_img_a(op, R, pl->D, S) + glm_img_b(op, R, pl->D, S) + 2048 +
+          align_up((size_t)pl->d * (pl->ktot > 0 ? pl->ktot : 1) * 4, 256);
   if (op == RR_OP_GLM_STEP) return 2 * phi + f + 2 * ws + q + img + 2048;
   return phi + f + img + 1024;
 }
@@ -417,6 +440,9 @@ extern "C" int rr_glm_step(const rr_plan* plan, const float* X, const float* y,
     imgA = W.take<uint8_t>(glm_img_a(RR_OP_GLM_STEP, R, D, S));
     imgB = W.take<uint8_t>(glm_img_b(RR_OP_GLM_STEP, R, D, S));
   }
+  // (d x kt) float staging of X^T Q; its operand images (256 x rows, kt x rows) fit in
+  // the ones above (kt < D, 256 <= S or D)
+  float* Ctmp = (imgA && imgB && kt > 0 && S >= 256) ? W.take<float>((size_t)d * kt) : nullptr;
   {
     int64_t total = (int64_t)S * D;
     draw_weights_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(
@@ -445,7 +471,7 @@ extern "C" int rr_glm_step(const rr_plan* plan, const float* X, const float* y,
       dim3 qg((kt + 255) / 256, rows);
       q_plain_kernel<<<qg, 256, 0, st>>>(*plan, Phi, T, D, rows, Q);
       RR_LAUNCH_CHECK("q_plain_kernel");
-      rc = xtq(X + s * d, Q, rows, d, kt, Rout, st);
+      rc = glm_xtq(X + s * d, Q, rows, d, kt, Rout, Ctmp, imgA, imgB, st);
       if (rc) return rc;
     }
   }

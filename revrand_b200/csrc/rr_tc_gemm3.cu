@@ -13,8 +13,10 @@
 //   g3_gemm_kernel   persistent CTA pairs (cta_group::2, M = 256, N = 256), 3-stage
 //                    ring of bulk copies (4 x 16 KB per CTA and stage), 12
 //                    tcgen05.mma.kind::tf32 per stage, accumulators double-buffered in
-//                    TMEM (2 x 256 columns); optional split-K (atomic epilogue) so that
-//                    short-and-wide products still fill the 74 CTA pairs
+//                    TMEM (2 x 256 columns); K is split into chains of 256 elements whose
+//                    partial products are combined with fp32 atomics (bounds the
+//                    truncation bias of the in-TMEM accumulation; also fills the 74 CTA
+//                    pairs when the output has few tiles)
 #include "rr_common.cuh"
 #include "rr_tc.cuh"
 
@@ -30,6 +32,7 @@ constexpr int G3_HALF = G3_IMG / 2;
 constexpr int G3_STAGES = 3;
 constexpr int G3_STAGE_BYTES = 4 * G3_HALF;   // A hi, A lo, B hi, B lo halves: 64 KB
 constexpr int G3_THREADS = 6 * 32;            // producer, MMA / relay, 4 epilogue warps
+constexpr int G3_CHAIN_KB = 8;                // k blocks per accumulation chain (see gemm3)
 
 __device__ __forceinline__ float g3_tf32(float x) {
   // round to 10 explicit mantissa bits, low 13 bits zero (the tensor core truncates)
@@ -84,9 +87,11 @@ struct G3Bars {
 struct G3Item {
   int rb, nb, kb0, kb1;
 };
-__device__ __forceinline__ G3Item g3_decode(int item, int NB, int nsplit, int nkb) {
+__device__ __forceinline__ G3Item g3_decode(int item, int NB, int nsplit, int nkb, int ntiles) {
   G3Item it;
-  const int tile = item / nsplit, ks = item - tile * nsplit;
+  // k chain slowest: the CTA pairs running together work on the same k range of
+  // different tiles and share its operand images in L2
+  const int ks = item / ntiles, tile = item - ks * ntiles;
   it.rb = tile / NB;
   it.nb = tile - it.rb * NB;
   it.kb0 = (int)(((int64_t)ks * nkb) / nsplit);
@@ -130,7 +135,7 @@ g3_gemm_kernel(const uint8_t* __restrict__ Aimg, const uint8_t* __restrict__ Bim
     if (elect_one()) {
       uint32_t g = 0;
       for (int item = pair; item < nitems; item += npairs) {
-        const G3Item it = g3_decode(item, NB, nsplit, nkb);
+        const G3Item it = g3_decode(item, NB, nsplit, nkb, nitems / nsplit);
         const uint8_t* a_src = Aimg + ((int64_t)it.rb * nkb) * 2 * G3_IMG + (int64_t)crank * G3_HALF;
         const uint8_t* b_src = Bimg + ((int64_t)it.nb * nkb) * 2 * G3_IMG + (int64_t)crank * G3_HALF;
         for (int kb = it.kb0; kb < it.kb1; ++kb, ++g) {
@@ -153,7 +158,7 @@ g3_gemm_kernel(const uint8_t* __restrict__ Aimg, const uint8_t* __restrict__ Bim
       const uint32_t idesc = make_idesc(2, G3_TM, G3_TN);     // tf32 x tf32 -> fp32
       uint32_t g = 0, itc = 0;
       for (int item = pair; item < nitems; item += npairs, ++itc) {
-        const G3Item it = g3_decode(item, NB, nsplit, nkb);
+        const G3Item it = g3_decode(item, NB, nsplit, nkb, nitems / nsplit);
         const uint32_t buf = itc & 1;
         mbar_wait_cl(&sb.acc_empty[buf], ((itc >> 1) & 1) ^ 1);
         tc_fence_after_sync();
@@ -187,7 +192,7 @@ g3_gemm_kernel(const uint8_t* __restrict__ Aimg, const uint8_t* __restrict__ Bim
       // ===================== relay (peer CTA): my stage landed =====================
       uint32_t g = 0;
       for (int item = pair; item < nitems; item += npairs) {
-        const G3Item it = g3_decode(item, NB, nsplit, nkb);
+        const G3Item it = g3_decode(item, NB, nsplit, nkb, nitems / nsplit);
         for (int kb = it.kb0; kb < it.kb1; ++kb, ++g) {
           const uint32_t s = g % G3_STAGES;
           mbar_wait_cl(&sb.full[s], (g / G3_STAGES) & 1);
@@ -201,7 +206,7 @@ g3_gemm_kernel(const uint8_t* __restrict__ Aimg, const uint8_t* __restrict__ Bim
     const int q = warp & 3;
     uint32_t itc = 0;
     for (int item = pair; item < nitems; item += npairs, ++itc) {
-      const G3Item it = g3_decode(item, NB, nsplit, nkb);
+      const G3Item it = g3_decode(item, NB, nsplit, nkb, nitems / nsplit);
       const uint32_t buf = itc & 1;
       const int row = it.rb * G3_TM + 128 * (int)crank + 32 * q + lane;
       const int col0 = it.nb * G3_TN;
@@ -281,14 +286,14 @@ int gemm3(int M, int N, int K, float alpha, const float* A, int64_t sAm, int64_t
   const int MB = (M + G3_TM - 1) / G3_TM, NB = (N + G3_TN - 1) / G3_TN;
   const int nkb = (K + G3_KB - 1) / G3_KB;
   int npairs = sm_count() / 2;
-  int nsplit = 1;
   const int tiles = MB * NB;
-  if (tiles < npairs) {
-    nsplit = npairs / tiles;
-    const int maxsplit = nkb / 8 > 0 ? nkb / 8 : 1;       // at least 8 k blocks per item
-    if (nsplit > maxsplit) nsplit = maxsplit;
-    if (nsplit < 1) nsplit = 1;
-  }
+  // The tensor core adds every MMA's result into the TMEM accumulator with truncation
+  // (measured: 768 accumulating MMAs, K = 2048, leave a 1.5e-5 relative bias), so one
+  // accumulation chain is at most G3_CHAIN_KB k blocks (96 MMAs: < 3e-6); the chains
+  // of a tile are combined by fp32 atomics (round to nearest).  Splitting K also
+  // fills the CTA pairs when the output has few tiles.
+  int nsplit = (nkb + G3_CHAIN_KB - 1) / G3_CHAIN_KB;
+  if (nsplit < 1) nsplit = 1;
   const int atomic = (nsplit > 1 || accumulate) ? 1 : 0;
   if (atomic && !accumulate)
     RR_CUDA_CHECK(cudaMemset2DAsync(C, (size_t)ldc * sizeof(float), 0, (size_t)N * sizeof(float),

@@ -844,11 +844,11 @@ def test_tcgen05_tf32x3_gemm_vs_float64(M, N, K, ta, tb):
     C = _engine.tcgen05_gemm3(A, B, transa=ta, transb=tb, alpha=0.5)
     torch.cuda.synchronize()
     err = float((C.double() - 0.5 * ref).norm() / (0.5 * ref).norm())
-    assert err < 3e-6, err
+    assert err < 5e-6, err
     assert float((C.double() - 0.5 * ref).abs().max() / ref.abs().max()) < 1e-5
     C2 = _engine.tcgen05_gemm3(A, B, transa=ta, transb=tb, alpha=0.25, C=C.clone(), accumulate=True)
     torch.cuda.synchronize()
-    assert float((C2.double() - 0.75 * ref).norm() / ref.norm()) < 3e-6
+    assert float((C2.double() - 0.75 * ref).norm() / ref.norm()) < 5e-6
 
 
 @pytest.mark.gpu
