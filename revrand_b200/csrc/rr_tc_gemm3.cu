@@ -10,13 +10,13 @@
 //   g3_pack_kernel   fp32 operand with arbitrary (row, k) strides -> tile-major tf32
 //                    images [row block of 256][k block of 32][hi | lo], every image a
 //                    contiguous 32 KB K-major SWIZZLE_128B tile, zero padded
-//   g3_gemm_kernel   persistent CTA pairs (cta_group::2, M = 256, N = 256), 3-stage
-//                    ring of bulk copies (4 x 16 KB per CTA and stage), 12
+//   g3_gemm_kernel   persistent CTA pairs (cta_group::2, M = 256, N = 128), 4-stage
+//                    ring of bulk copies (48 KB per CTA and stage), 12
 //                    tcgen05.mma.kind::tf32 per stage, accumulators double-buffered in
-//                    TMEM (2 x 256 columns); K is split into chains of 256 elements whose
-//                    partial products are combined with fp32 atomics (bounds the
-//                    truncation bias of the in-TMEM accumulation; also fills the 74 CTA
-//                    pairs when the output has few tiles)
+//                    TMEM; K is cut into chains of 256 elements that the epilogue warps
+//                    add up in fp32 registers (bounds the truncation bias of the
+//                    in-TMEM accumulation); split-K over work items (fp32 atomics)
+//                    only when the output has too few tiles for the 74 CTA pairs
 #include "rr_common.cuh"
 #include "rr_tc.cuh"
 
@@ -24,13 +24,14 @@ namespace rr {
 
 using namespace tc;
 
-constexpr int G3_TM = 256;
-constexpr int G3_TN = 256;
+constexpr int G3_TM = 256;                    // rows of A per tile (128 per CTA)
+constexpr int G3_TN = 128;                    // rows of B per tile (64 per CTA)
 constexpr int G3_KB = 32;                     // tf32 elements per k block (one 128-byte line)
-constexpr int G3_IMG = G3_TM * 128;           // one image: 32 KB
-constexpr int G3_HALF = G3_IMG / 2;
-constexpr int G3_STAGES = 3;
-constexpr int G3_STAGE_BYTES = 4 * G3_HALF;   // A hi, A lo, B hi, B lo halves: 64 KB
+constexpr int G3_IMG = 256 * 128;             // one operand image: 256 rows x 128 B = 32 KB
+constexpr int G3_A_HALF = (G3_TM / 2) * 128;  // 16 KB
+constexpr int G3_B_HALF = (G3_TN / 2) * 128;  // 8 KB
+constexpr int G3_STAGES = 4;
+constexpr int G3_STAGE_BYTES = 2 * G3_A_HALF + 2 * G3_B_HALF;   // A hi, A lo, B hi, B lo: 48 KB
 constexpr int G3_THREADS = 6 * 32;            // producer, MMA / relay, 4 epilogue warps
 constexpr int G3_CHAIN_KB = 8;                // k blocks per accumulation chain (see gemm3)
 
@@ -89,7 +90,7 @@ struct G3Item {
 };
 __device__ __forceinline__ G3Item g3_decode(int item, int NB, int nsplit, int nkb, int ntiles) {
   G3Item it;
-  // k chain slowest: the CTA pairs running together work on the same k range of
+  // k range slowest: the CTA pairs running together work on the same k range of
   // different tiles and share its operand images in L2
   const int ks = item / ntiles, tile = item - ks * ntiles;
   it.rb = tile / NB;
@@ -99,6 +100,12 @@ __device__ __forceinline__ G3Item g3_decode(int item, int NB, int nsplit, int nk
   return it;
 }
 
+// The tensor core adds every MMA's result into the TMEM accumulator with truncation
+// (measured: 768 accumulating MMAs, K = 2048, leave a 1.5e-5 relative bias against
+// float64).  So the k range of a work item is cut into CHAINS of G3_CHAIN_KB k blocks
+// (96 MMAs: < 3e-6): the issuer alternates between two TMEM accumulators, one per
+// chain, and the epilogue warps add each finished chain into fp32 REGISTERS (round to
+// nearest, 128 per thread) while the next chain runs -- one write of C per item.
 __global__ void __launch_bounds__(G3_THREADS, 1)
 g3_gemm_kernel(const uint8_t* __restrict__ Aimg, const uint8_t* __restrict__ Bimg, int M, int N,
                int nkb, int NB, int nsplit, int nitems, float alpha, float* __restrict__ C,
@@ -110,6 +117,7 @@ g3_gemm_kernel(const uint8_t* __restrict__ Aimg, const uint8_t* __restrict__ Bim
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const uint32_t crank = cluster_ctarank();
   const int pair = blockIdx.x >> 1, npairs = gridDim.x >> 1;
+  const int ntiles = nitems / nsplit;
 
   if (tid == 0) {
     for (int s = 0; s < G3_STAGES; ++s) {
@@ -123,7 +131,7 @@ g3_gemm_kernel(const uint8_t* __restrict__ Aimg, const uint8_t* __restrict__ Bim
     }
     mbar_fence_init();
   }
-  if (warp == 1) tmem_alloc_2cta(&sb.tmem_base, 512);
+  if (warp == 1) tmem_alloc_2cta(&sb.tmem_base, 2 * G3_TN);
   tc_fence_before_sync();
   __syncthreads();
   cluster_sync_all();
@@ -135,9 +143,12 @@ g3_gemm_kernel(const uint8_t* __restrict__ Aimg, const uint8_t* __restrict__ Bim
     if (elect_one()) {
       uint32_t g = 0;
       for (int item = pair; item < nitems; item += npairs) {
-        const G3Item it = g3_decode(item, NB, nsplit, nkb, nitems / nsplit);
-        const uint8_t* a_src = Aimg + ((int64_t)it.rb * nkb) * 2 * G3_IMG + (int64_t)crank * G3_HALF;
-        const uint8_t* b_src = Bimg + ((int64_t)it.nb * nkb) * 2 * G3_IMG + (int64_t)crank * G3_HALF;
+        const G3Item it = g3_decode(item, NB, nsplit, nkb, ntiles);
+        // A: this CTA's 128 rows of the 256-row block; B: its 64 rows of the 128-row
+        // tile, i.e. of half (nb & 1) of B's 256-row block nb >> 1
+        const uint8_t* a_src = Aimg + ((int64_t)it.rb * nkb) * 2 * G3_IMG + (int64_t)crank * G3_A_HALF;
+        const uint8_t* b_src = Bimg + ((int64_t)(it.nb >> 1) * nkb) * 2 * G3_IMG +
+                               (int64_t)(it.nb & 1) * (2 * G3_B_HALF) + (int64_t)crank * G3_B_HALF;
         for (int kb = it.kb0; kb < it.kb1; ++kb, ++g) {
           const uint32_t s = g % G3_STAGES;
           mbar_wait_cl(&sb.empty[s], ((g / G3_STAGES) & 1) ^ 1);
@@ -145,10 +156,10 @@ g3_gemm_kernel(const uint8_t* __restrict__ Aimg, const uint8_t* __restrict__ Bim
           mbar_expect_tx(&sb.full[s], G3_STAGE_BYTES);
           const uint8_t* ak = a_src + (int64_t)kb * 2 * G3_IMG;
           const uint8_t* bk = b_src + (int64_t)kb * 2 * G3_IMG;
-          bulk_g2s(dst, ak, G3_HALF, &sb.full[s]);
-          bulk_g2s(dst + G3_HALF, ak + G3_IMG, G3_HALF, &sb.full[s]);
-          bulk_g2s(dst + 2 * G3_HALF, bk, G3_HALF, &sb.full[s]);
-          bulk_g2s(dst + 3 * G3_HALF, bk + G3_IMG, G3_HALF, &sb.full[s]);
+          bulk_g2s(dst, ak, G3_A_HALF, &sb.full[s]);
+          bulk_g2s(dst + G3_A_HALF, ak + G3_IMG, G3_A_HALF, &sb.full[s]);
+          bulk_g2s(dst + 2 * G3_A_HALF, bk, G3_B_HALF, &sb.full[s]);
+          bulk_g2s(dst + 2 * G3_A_HALF + G3_B_HALF, bk + G3_IMG, G3_B_HALF, &sb.full[s]);
         }
       }
     }
@@ -156,43 +167,46 @@ g3_gemm_kernel(const uint8_t* __restrict__ Aimg, const uint8_t* __restrict__ Bim
     if (crank == 0) {
       // ========================== MMA issuer (leader CTA) ==========================
       const uint32_t idesc = make_idesc(2, G3_TM, G3_TN);     // tf32 x tf32 -> fp32
-      uint32_t g = 0, itc = 0;
-      for (int item = pair; item < nitems; item += npairs, ++itc) {
-        const G3Item it = g3_decode(item, NB, nsplit, nkb, nitems / nsplit);
-        const uint32_t buf = itc & 1;
-        mbar_wait_cl(&sb.acc_empty[buf], ((itc >> 1) & 1) ^ 1);
-        tc_fence_after_sync();
-        for (int kb = it.kb0; kb < it.kb1; ++kb, ++g) {
-          const uint32_t s = g % G3_STAGES;
-          const uint32_t ph = (g / G3_STAGES) & 1;
-          mbar_wait_cl(&sb.full[s], ph);
-          mbar_wait_cl(&sb.peer_full[s], ph);
+      uint32_t g = 0, cc = 0;                                  // stage and chain counters
+      for (int item = pair; item < nitems; item += npairs) {
+        const G3Item it = g3_decode(item, NB, nsplit, nkb, ntiles);
+        for (int c0 = it.kb0; c0 < it.kb1; c0 += G3_CHAIN_KB, ++cc) {
+          const int c1 = c0 + G3_CHAIN_KB < it.kb1 ? c0 + G3_CHAIN_KB : it.kb1;
+          const uint32_t buf = cc & 1;
+          mbar_wait_cl(&sb.acc_empty[buf], ((cc >> 1) & 1) ^ 1);
           tc_fence_after_sync();
-          if (elect_one()) {
-            const uint32_t a0 = smem_u32(smem + s * G3_STAGE_BYTES);
-            const uint64_t dah = make_desc_sw128(a0), dal = make_desc_sw128(a0 + G3_HALF);
-            const uint64_t dbh = make_desc_sw128(a0 + 2 * G3_HALF),
-                           dbl = make_desc_sw128(a0 + 3 * G3_HALF);
-            const uint32_t acc = tmem + buf * G3_TN;
+          for (int kb = c0; kb < c1; ++kb, ++g) {
+            const uint32_t s = g % G3_STAGES;
+            const uint32_t ph = (g / G3_STAGES) & 1;
+            mbar_wait_cl(&sb.full[s], ph);
+            mbar_wait_cl(&sb.peer_full[s], ph);
+            tc_fence_after_sync();
+            if (elect_one()) {
+              const uint32_t a0 = smem_u32(smem + s * G3_STAGE_BYTES);
+              const uint32_t b0 = a0 + 2 * G3_A_HALF;
+              const uint64_t dah = make_desc_sw128(a0), dal = make_desc_sw128(a0 + G3_A_HALF);
+              const uint64_t dbh = make_desc_sw128(b0), dbl = make_desc_sw128(b0 + G3_B_HALF);
+              const uint32_t acc = tmem + buf * G3_TN;
 #pragma unroll
-            for (int k = 0; k < G3_KB / 8; ++k) {
-              const uint64_t adv = (uint64_t)(2 * k);
-              // small terms first
-              umma2_tf32_ss(acc, dal + adv, dbh + adv, idesc, (kb > it.kb0) | (k != 0));
-              umma2_tf32_ss(acc, dah + adv, dbl + adv, idesc, 1);
-              umma2_tf32_ss(acc, dah + adv, dbh + adv, idesc, 1);
+              for (int k = 0; k < G3_KB / 8; ++k) {
+                const uint64_t adv = (uint64_t)(2 * k);
+                // small terms first
+                umma2_tf32_ss(acc, dal + adv, dbh + adv, idesc, (kb > c0) | (k != 0));
+                umma2_tf32_ss(acc, dah + adv, dbl + adv, idesc, 1);
+                umma2_tf32_ss(acc, dah + adv, dbh + adv, idesc, 1);
+              }
+              umma2_commit_mc(&sb.empty[s]);
+              if (kb == c1 - 1) umma2_commit_mc(&sb.acc_full[buf]);
             }
-            umma2_commit_mc(&sb.empty[s]);
-            if (kb == it.kb1 - 1) umma2_commit_mc(&sb.acc_full[buf]);
+            __syncwarp();
           }
-          __syncwarp();
         }
       }
     } else {
       // ===================== relay (peer CTA): my stage landed =====================
       uint32_t g = 0;
       for (int item = pair; item < nitems; item += npairs) {
-        const G3Item it = g3_decode(item, NB, nsplit, nkb, nitems / nsplit);
+        const G3Item it = g3_decode(item, NB, nsplit, nkb, ntiles);
         for (int kb = it.kb0; kb < it.kb1; ++kb, ++g) {
           const uint32_t s = g % G3_STAGES;
           mbar_wait_cl(&sb.full[s], (g / G3_STAGES) & 1);
@@ -204,42 +218,54 @@ g3_gemm_kernel(const uint8_t* __restrict__ Aimg, const uint8_t* __restrict__ Bim
   } else {
     // ============================ epilogue (warps 2..5) ============================
     const int q = warp & 3;
-    uint32_t itc = 0;
-    for (int item = pair; item < nitems; item += npairs, ++itc) {
-      const G3Item it = g3_decode(item, NB, nsplit, nkb, nitems / nsplit);
-      const uint32_t buf = itc & 1;
+    uint32_t cc = 0;
+    const bool vec_ok = ((ldc & 3) == 0) && ((reinterpret_cast<uintptr_t>(C) & 15) == 0);
+    for (int item = pair; item < nitems; item += npairs) {
+      const G3Item it = g3_decode(item, NB, nsplit, nkb, ntiles);
       const int row = it.rb * G3_TM + 128 * (int)crank + 32 * q + lane;
       const int col0 = it.nb * G3_TN;
-      mbar_wait_cl(&sb.acc_full[buf], (itc >> 1) & 1);
-      tc_fence_after_sync();
-      const uint32_t tacc = tmem + ((uint32_t)(32 * q) << 16) + buf * G3_TN;
-      float* crow = C + (int64_t)row * ldc;
-      const bool vec_ok = ((ldc & 3) == 0) && ((reinterpret_cast<uintptr_t>(C) & 15) == 0);
-#pragma unroll 1
-      for (int c8 = 0; c8 < G3_TN / 32; ++c8) {
-        float v[32];
-        tmem_ld32_nowait(tacc + (uint32_t)(32 * c8), v);
-        tmem_ld_wait();
-        if (c8 == G3_TN / 32 - 1) {         // all TMEM reads of this item are done
-          tc_fence_before_sync();
-          __syncwarp();
-          if (lane == 0) mbar_arrive_cluster(mapa_u32(smem_u32(&sb.acc_empty[buf]), 0));
+      float sum[G3_TN];
+#pragma unroll
+      for (int j = 0; j < G3_TN; ++j) sum[j] = 0.0f;
+      for (int c0 = it.kb0; c0 < it.kb1; c0 += G3_CHAIN_KB, ++cc) {
+        const uint32_t buf = cc & 1;
+        mbar_wait_cl(&sb.acc_full[buf], (cc >> 1) & 1);
+        tc_fence_after_sync();
+        const uint32_t tacc = tmem + ((uint32_t)(32 * q) << 16) + buf * G3_TN;
+#pragma unroll
+        for (int c8 = 0; c8 < G3_TN / 32; ++c8) {
+          float v[32];
+          tmem_ld32_nowait(tacc + (uint32_t)(32 * c8), v);
+          tmem_ld_wait();
+          if (c8 == G3_TN / 32 - 1) {       // all TMEM reads of this chain are done
+            tc_fence_before_sync();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_cluster(mapa_u32(smem_u32(&sb.acc_empty[buf]), 0));
+          }
+#pragma unroll
+          for (int j = 0; j < 32; ++j) sum[32 * c8 + j] += v[j];
         }
-        const int c = col0 + 32 * c8;
-        if (row < M && c < N) {
+      }
+      if (row < M) {
+        float* crow = C + (int64_t)row * ldc;
+#pragma unroll
+        for (int c8 = 0; c8 < G3_TN / 32; ++c8) {
+          const int c = col0 + 32 * c8;
+          if (c >= N) break;
           if (atomic) {
 #pragma unroll
             for (int j = 0; j < 32; ++j)
-              if (c + j < N) atomicAdd(crow + c + j, alpha * v[j]);
+              if (c + j < N) atomicAdd(crow + c + j, alpha * sum[32 * c8 + j]);
           } else if (vec_ok && c + 32 <= N) {
 #pragma unroll
             for (int j = 0; j < 32; j += 4)
               *reinterpret_cast<float4*>(crow + c + j) =
-                  make_float4(alpha * v[j], alpha * v[j + 1], alpha * v[j + 2], alpha * v[j + 3]);
+                  make_float4(alpha * sum[32 * c8 + j], alpha * sum[32 * c8 + j + 1],
+                              alpha * sum[32 * c8 + j + 2], alpha * sum[32 * c8 + j + 3]);
           } else {
 #pragma unroll
             for (int j = 0; j < 32; ++j)
-              if (c + j < N) crow[c + j] = alpha * v[j];
+              if (c + j < N) crow[c + j] = alpha * sum[32 * c8 + j];
           }
         }
       }
@@ -248,12 +274,12 @@ g3_gemm_kernel(const uint8_t* __restrict__ Aimg, const uint8_t* __restrict__ Bim
   tc_fence_before_sync();
   __syncthreads();
   cluster_sync_all();
-  if (warp == 1) tmem_dealloc_2cta(tmem, 512);
+  if (warp == 1) tmem_dealloc_2cta(tmem, 2 * G3_TN);
 }
 
 // ---- host -------------------------------------------------------------------------
 size_t gemm3_image_bytes(int64_t R, int64_t K) {
-  const int64_t rbs = (R + G3_TM - 1) / G3_TM, nkb = (K + G3_KB - 1) / G3_KB;
+  const int64_t rbs = (R + 255) / 256, nkb = (K + G3_KB - 1) / G3_KB;
   return (size_t)(rbs * nkb * 2 * G3_IMG) + 1024;
 }
 
@@ -264,8 +290,8 @@ bool gemm3_worthwhile(int M, int N, int K) {
 
 static int g3_pack(const float* src, int64_t sR, int64_t sK, int R, int K, uint8_t* img,
                    cudaStream_t st) {
-  const int rbs = (R + G3_TM - 1) / G3_TM, nkb = (K + G3_KB - 1) / G3_KB;
-  dim3 grid((unsigned)nkb, (unsigned)(rbs * (G3_TM / 32)));
+  const int rbs = (R + 255) / 256, nkb = (K + G3_KB - 1) / G3_KB;
+  dim3 grid((unsigned)nkb, (unsigned)(rbs * (256 / 32)));
   g3_pack_kernel<<<grid, 256, 0, st>>>(src, sR, sK, R, K, nkb, img);
   RR_LAUNCH_CHECK("g3_pack_kernel");
   return RR_OK;
@@ -287,13 +313,15 @@ int gemm3(int M, int N, int K, float alpha, const float* A, int64_t sAm, int64_t
   const int nkb = (K + G3_KB - 1) / G3_KB;
   int npairs = sm_count() / 2;
   const int tiles = MB * NB;
-  // The tensor core adds every MMA's result into the TMEM accumulator with truncation
-  // (measured: 768 accumulating MMAs, K = 2048, leave a 1.5e-5 relative bias), so one
-  // accumulation chain is at most G3_CHAIN_KB k blocks (96 MMAs: < 3e-6); the chains
-  // of a tile are combined by fp32 atomics (round to nearest).  Splitting K also
-  // fills the CTA pairs when the output has few tiles.
-  int nsplit = (nkb + G3_CHAIN_KB - 1) / G3_CHAIN_KB;
-  if (nsplit < 1) nsplit = 1;
+  // split K over work items (combined with fp32 atomics) only when the output has too
+  // few tiles to fill the CTA pairs; every item keeps at least one whole chain
+  int nsplit = 1;
+  if (tiles < npairs) {
+    nsplit = npairs / tiles;
+    const int maxsplit = nkb / G3_CHAIN_KB > 0 ? nkb / G3_CHAIN_KB : 1;
+    if (nsplit > maxsplit) nsplit = maxsplit;
+    if (nsplit < 1) nsplit = 1;
+  }
   const int atomic = (nsplit > 1 || accumulate) ? 1 : 0;
   if (atomic && !accumulate)
     RR_CUDA_CHECK(cudaMemset2DAsync(C, (size_t)ldc * sizeof(float), 0, (size_t)N * sizeof(float),
