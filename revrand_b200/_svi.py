@@ -211,8 +211,50 @@ class DeviceSVI(object):
         self._left_in_chunk = steps
         self.h2d_bytes += need * 8
 
+    # -- random starts ---------------------------------------------------------------
+    def random_starts(self, params, nstarts):
+        """Best of ``nstarts`` draws from the parameters' distributions, each scored
+        on the next minibatch (decorators.py:541-583 with a data generator): the draws
+        and the minibatch indices come from the host generator in the reference's
+        order (batch, then candidate), go down in blocks, and the objectives are
+        evaluated back to back on the device; ONE read (the arg-min) at the end.
+        Loads the best candidate as the state and returns it (raw space, flat)."""
+        t = self.t
+        rs, N, B = self.rs, self.N, self.B
+        carry = np.zeros(0, dtype=np.int64)
+        cands, inds = [], []
+        for _ in range(nstarts):
+            while len(carry) < B:
+                carry = np.concatenate((carry, rs.permutation(N)))
+            inds.append(carry[:B])
+            carry = carry[B:]
+            cands.append(flatten_values(_map_params(lambda p: p.rvs(rs), params)))
+            # (the host loop seeds the device noise generator from the same stream at
+            # its first evaluation, i.e. right here)
+            self.glm._device_generator(self.dev)
+        objs = t.empty(nstarts, dtype=t.float64, device=self.dev)
+        blk = max(1, min(self.chunk_steps, 64))
+        for b0 in range(0, nstarts, blk):
+            b1 = min(nstarts, b0 + blk)
+            xc = t.from_numpy(np.stack(cands[b0:b1])).pin_memory().to(self.dev, non_blocking=True)
+            ic = t.from_numpy(np.concatenate(inds[b0:b1])).pin_memory()
+            self.idx_dev[:ic.numel()].copy_(ic, non_blocking=True)
+            self.cursor.zero_()
+            self.h2d_bytes += xc.numel() * 8 + ic.numel() * 8
+            for i in range(b1 - b0):
+                xd = xc[i]
+                self.z.copy_(t.where(self.pos, t.log(t.where(self.pos, xd, t.ones_like(xd))), xd))
+                objs[b0 + i] = self._body(update=False)
+            t.cuda.current_stream().synchronize()      # the pinned blocks may go now
+        objs = t.where(t.isnan(objs), t.full_like(objs, float("inf")), objs)
+        best = int(t.argmin(objs).item())
+        log.info("Best start found with objective = {}".format(float(objs[best].item())))
+        self.set_x(cands[best])
+        self._left_in_chunk = 0            # the SGD phase starts its own index stream
+        return cands[best]
+
     # -- one step ----------------------------------------------------------------------
-    def _body(self):
+    def _body(self, update=True):
         t, glm, plan = self.t, self.glm, self.plan
         D, K, L = self.D, self.K, self.L
         off = self.off
@@ -264,6 +306,8 @@ class DeviceSVI(object):
         g = t.cat(parts)
         ELBO = (Ell.sum() * glm.B_ - 0.5 * D * K * LOG2PI - 0.5 * K * t.log(Lam).sum()
                 - 0.5 * ((m ** 2 + C) * iL[:, None]).sum() - logzk.sum() + math.log(K)) / K
+        if not update:
+            return -ELBO
         # log warp (decorators.py:329-403), sgd.py:380-415
         g = t.where(self.pos, g * x, g)
         slot = self.itd % self.ntrace
@@ -274,6 +318,7 @@ class DeviceSVI(object):
         g = t.where(z >= self.upper, t.clamp(g, min=0.0), g)
         znew = self.updater(z, g, t)
         self.z.copy_(t.minimum(t.maximum(znew, self.lower), self.upper))
+        return None
 
     def step(self):
         """One SVI iteration; False once ``maxiter`` steps have run."""

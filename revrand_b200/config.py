@@ -59,3 +59,6 @@ PIPELINE_STARTS = os.environ.get("REVRAND_B200_PIPELINE_STARTS", "1") != "0"
 GLM_DEVICE_LOOP = os.environ.get("REVRAND_B200_GLM_DEVICE_LOOP", "1") != "0"
 # ... replayed as a CUDA graph from its third step on (False: eager launches).
 GLM_DEVICE_GRAPH = os.environ.get("REVRAND_B200_GLM_DEVICE_GRAPH", "1") != "0"
+# ... and its random starts are scored back to back on the device (one read at the end);
+# False: one ``_elbo`` call (host assembly) per start.
+GLM_DEVICE_STARTS = os.environ.get("REVRAND_B200_GLM_DEVICE_STARTS", "1") != "0"

@@ -185,11 +185,14 @@ class GeneralizedLinearModel(BaseEstimator, RegressorMixin):
         from .optimize.sgd import gen_batch
         from .optimize.structured import _map_params, _random_starts, flatten_values
         x0 = flatten_values(_map_params(lambda p: p.rvs(None), params))
-        if self.nstarts > 0:
-            data_gen = gen_batch(data, self.batch_size, random_state=self.random_)
-            x0 = flatten_values(_random_starts(self._elbo, params, True, (), self.nstarts,
-                                               self.random_, data_gen))
         run = _svi.DeviceSVI(self, params, data, self.maxiter, self.random_, x0=x0)
+        if self.nstarts > 0:
+            if config.GLM_DEVICE_STARTS:
+                run.random_starts(params, self.nstarts)
+            else:
+                data_gen = gen_batch(data, self.batch_size, random_state=self.random_)
+                run.set_x(flatten_values(_random_starts(self._elbo, params, True, (),
+                                                        self.nstarts, self.random_, data_gen)))
         return run.run().result()
 
     def svi_stepper(self, X, y, likelihood_args=(), maxiter=10 ** 9):
@@ -239,12 +242,18 @@ class GeneralizedLinearModel(BaseEstimator, RegressorMixin):
         if config.GLM_HOST_RNG:
             e = np.stack([self.random_.randn(L, D) for _ in range(Kmix)])
             return eng.to_device(e)
+        gen = self._device_generator(dev)
+        return t.randn((Kmix, L, D), generator=gen, device=dev, dtype=t.float32)
+
+    def _device_generator(self, dev):
+        """The device noise generator, seeded from ``self.random_`` on first use (one
+        ``randint`` draw, at the model's first objective evaluation)."""
         gen = getattr(self, "_devgen", None)
         if gen is None:
-            gen = t.Generator(device=dev)
+            gen = eng.torch().Generator(device=dev)
             gen.manual_seed(int(self.random_.randint(0, 2 ** 31 - 1)))
             self._devgen = gen
-        return t.randn((Kmix, L, D), generator=gen, device=dev, dtype=t.float32)
+        return gen
 
     def _get_plan(self, d, bpars):
         plan = getattr(self, "_plan_cache", None)
