@@ -885,3 +885,34 @@ def test_glm_step_through_tensor_core_gemms_vs_oracle(likname):
     assert relerr(dm, ref["dm"]) < 1e-4
     assert relerr(dC, ref["dC"]) < 1e-4
     assert relerr(dbp, ref["dbpars"][0]) < 1e-3
+
+
+@pytest.mark.gpu
+def test_slm_predictive_moments_through_tensor_core_gemm_vs_oracle():
+    """predict_moments at a size whose Phi C product runs on the tcgen05 tf32x3 GEMM
+    (slm.py:239-244): predictive mean and variance against the float64 oracle."""
+    rs = np.random.RandomState(23)
+    N, d, K = 6000, 5, 512
+    X, y = _synthetic(N, d, seed=41)
+    ls = 1.5 * (1.0 + 0.1 * np.arange(d))
+    basis = bf.RandomRBF(nbases=K, Xdim=d, random_state=3, lenscale=Parameter(ls, Positive())) \
+        + bf.LinearBasis(onescol=True)
+    slm = rr.StandardLinearModel(basis=basis)
+    slm.obj_ = -np.inf
+    slm._elbo(X, y, 0.05, [1.3, 2.0], ls)
+    slm.var_, slm.regularizer_, slm.hypers_ = 0.05, [1.3, 2.0], ls
+    Xs = rs.randn(5000, d).astype(np.float32).astype(np.float64)
+    Ey, Vy = slm.predict_moments(Xs)
+    blocks = [dict(kind="trig", W=basis.bases[0].W, lenscale=ls, cols=None),
+              dict(kind="linear", onescol=True)]
+    ref = orc.slm_elbo(X, y, 0.05, [1.3, 2.0], blocks)
+    oEy, oVy = orc.slm_predict_moments(Xs, blocks, ref["m"], ref["C"], 0.05)
+    assert relerr(Ey, oEy) < 1e-4
+    np.testing.assert_allclose(Vy - 0.05, oVy - 0.05, rtol=2e-4, atol=1e-9)
+    # ... and from host copies of the posterior (a fitted, unpickled model)
+    slm2 = rr.StandardLinearModel(basis=basis)
+    slm2.var_, slm2.regularizer_, slm2.hypers_ = 0.05, [1.3, 2.0], ls
+    slm2.weights_, slm2.covariance_ = slm.weights_, slm.covariance_
+    Ey2, Vy2 = slm2.predict_moments(Xs)
+    np.testing.assert_allclose(Ey2, Ey, rtol=1e-5, atol=1e-7)
+    np.testing.assert_allclose(Vy2, Vy, rtol=1e-5)
