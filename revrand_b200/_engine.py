@@ -637,6 +637,7 @@ _BLOCK_INV_LEAF = 128         # diagonal blocks inverted by ONE batched trsm (cu
                               # batched trsm is fast up to 256: 0.11 ms for 32 x 128^2,
                               # 2.0 ms for 8 x 512^2 at D = 4096)
 _GRAM_LEAF = 512              # recursion leaf of L^-T L^-1
+_TRI_INV_SHARD_MIN = 1024     # levels of L^-1 from this block size on are split over ranks
 _BLOCK_INV_CUDA_ONLY = True   # tests flip this to exercise the blocked paths on CPU
 _BLOCK_INV_BATCHED = True     # level-by-level batched triangular inverse (False: recursion)
 
@@ -691,13 +692,29 @@ def _tri_inv_lower(L, out):
         inv = t.linalg.solve_triangular(Vd.contiguous(), eye, upper=False)
         Op.view(nb, b, nb, b).diagonal(dim1=0, dim2=2).permute(2, 0, 1).copy_(inv)
         c = b
+        rank, ws = world()
         while c < Dp:
             P = Dp // (2 * c)
             L21 = _diag_blocks(Lp, P, c, 1, 0)
             A = _diag_blocks(Op, P, c, 0, 0)
             B = _diag_blocks(Op, P, c, 1, 1)
-            X = t.bmm(B, t.bmm(L21, A))
-            _diag_blocks(Op, P, c, 1, 0).copy_(X.neg_())
+            if ws > 1 and c >= _TRI_INV_SHARD_MIN and c >= ws:
+                # Row-sharded job (every rank holds the same L): the top levels are a
+                # few big GEMMs -- each rank forms a column slice of every pair's block
+                # and the slices are all-gathered, so the replicated (serial) part of an
+                # evaluation shrinks with the number of GPUs.
+                cw = -(-c // ws)
+                lo, hi = min(rank * cw, c), min((rank + 1) * cw, c)
+                mine = t.zeros((P, c, cw), dtype=L.dtype, device=L.device)
+                if hi > lo:
+                    mine[:, :, :hi - lo] = t.bmm(B, t.bmm(L21, A[:, :, lo:hi]))
+                full = t.empty((ws * P, c, cw), dtype=L.dtype, device=L.device)
+                t.distributed.all_gather_into_tensor(full, mine)
+                X = full.view(ws, P, c, cw).permute(1, 2, 0, 3).reshape(P, c, ws * cw)[:, :, :c]
+                _diag_blocks(Op, P, c, 1, 0).copy_(-X)
+            else:
+                X = t.bmm(B, t.bmm(L21, A))
+                _diag_blocks(Op, P, c, 1, 0).copy_(X.neg_())
             c *= 2
         if Op is not out:
             out.copy_(Op[:n, :n])

@@ -53,6 +53,7 @@ def _worker(rank, world, port, ret):
         # same through the GEMM-rich blocked path used on the GPU for D >= 1024
         _engine._BLOCK_INV_MIN, _engine._BLOCK_INV_LEAF = 8, 4
         _engine._BLOCK_INV_CUDA_ONLY = False
+        _engine._TRI_INV_SHARD_MIN = 8     # top levels of L^-1 split over the two ranks
         post2 = _engine.solve_posterior(torch.from_numpy(A), torch.from_numpy(Pf.T.dot(y)),
                                         0.3, torch.from_numpy(lam))
         ok = ok and np.allclose(post2.C.numpy(), Cref, rtol=1e-9, atol=1e-12)
