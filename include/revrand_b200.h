@@ -224,6 +224,30 @@ int rr_slm_gradpass(const rr_plan* plan, const float* X, const float* y,
                     int32_t engine, rr_context* ctx, void* stream);
 
 /*
+ * The two passes of one evaluation, sharing the feature map.  slm.py:145 forms
+ * Phi = basis.transform(X) ONCE per _elbo call and uses it for Phi^T Phi (:146), the
+ * residuals (:161) and the gradients (:193-197).  rr_slm_suffstats_keep is
+ * rr_slm_suffstats on the tensor-core engine that also leaves Phi behind as an fp16
+ * image in the caller's buffer `kept` (rr_slm_kept_features_bytes(plan, N) bytes,
+ * 1024-byte aligned; 0 = this plan / row count cannot keep its features);
+ * rr_slm_gradpass_kept is rr_slm_gradpass reading that image instead of evaluating
+ * the feature map a second time.  The image is only meaningful for the SAME plan
+ * contents (Wt), X and N as the call that wrote it.  Workspace of the second call:
+ * rr_workspace_bytes(RR_OP_GRADPASS_KEPT, ...).  sqerr here comes from fp16 feature
+ * values (relative accuracy ~1e-5): callers that need more take
+ * sum Err^2 = y'y - 2 p'm + m'G m from the float64 statistics, or rr_slm_residual.
+ */
+size_t rr_slm_kept_features_bytes(const rr_plan* plan, int64_t N);
+int rr_slm_suffstats_keep(const rr_plan* plan, const float* X, const float* y,
+                          int64_t N, double* G, double* p, double* yy, void* kept,
+                          size_t kept_bytes, void* workspace, size_t workspace_bytes,
+                          rr_context* ctx, void* stream);
+int rr_slm_gradpass_kept(const rr_plan* plan, const float* X, const float* y,
+                         int64_t N, const float* m, const float* C, double* R,
+                         double* sqerr, const void* kept, size_t kept_bytes,
+                         void* workspace, size_t workspace_bytes, void* stream);
+
+/*
  * Predictive moments (slm.py:239-242): Ey = Phi m, Vf = rowsum((Phi C) * Phi).
  */
 int rr_slm_predict(const rr_plan* plan, const float* X, int64_t N,
@@ -288,6 +312,7 @@ int rr_glm_quantiles(const float* F, int64_t N, int32_t S, int32_t lik, float li
 #define RR_OP_GLM_STEP 4
 #define RR_OP_GLM_PREDICT 5
 #define RR_OP_RESIDUAL 6
+#define RR_OP_GRADPASS_KEPT 7
 size_t rr_workspace_bytes(int32_t op, int64_t N, int32_t d, int32_t ktot,
                           int32_t D, int32_t aux0, int32_t aux1,
                           int32_t engine);

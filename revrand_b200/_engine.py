@@ -464,6 +464,47 @@ def slm_suffstats(plan, Xd, yd, stats, engine=_cabi.RR_ENGINE_AUTO,
           "rr_slm_suffstats")
 
 
+def kept_features_buffer(plan, N, max_bytes):
+    """Device buffer for the fp16 feature image the value pass can leave behind for
+    the gradient pass of the same evaluation (rr_slm_suffstats_keep), or None when
+    the plan / row count cannot keep its features or the image is larger than
+    ``max_bytes`` or half of the free device memory."""
+    t = require_cuda()
+    need = int(_cabi.load().rr_slm_kept_features_bytes(C.byref(plan.struct), int(N)))
+    if need == 0 or need > max_bytes:
+        return None
+    free, _ = t.cuda.mem_get_info()
+    if need + 1024 > free // 2:
+        return None
+    raw = t.empty(need + 1024, dtype=t.uint8, device=device())
+    off = (-raw.data_ptr()) % 1024
+    return raw[off:off + need]
+
+
+def slm_suffstats_keep(plan, Xd, yd, stats, kept, want_yy=True):
+    """Value pass on the tensor-core engine that also writes the kept feature image."""
+    lib = _cabi.load()
+    N = Xd.shape[0]
+    ws = workspace(_ws_bytes(_cabi.RR_OP_SUFFSTATS, N, plan, engine=_cabi.RR_ENGINE_TCGEN05))
+    check(lib.rr_slm_suffstats_keep(C.byref(plan.struct), _ptr(Xd), _ptr(yd), N,
+                                    _ptr(stats.G), _ptr(stats.p),
+                                    _ptr(stats.yy) if want_yy else C.c_void_p(0),
+                                    _ptr(kept), kept.numel(), _ptr(ws), ws.numel(),
+                                    context(), _stream_ptr()),
+          "rr_slm_suffstats_keep")
+
+
+def slm_gradpass_kept(plan, Xd, yd, m32, C32, R, sqerr, kept):
+    """Residual + gradient pass from the kept feature image of the same evaluation."""
+    lib = _cabi.load()
+    N = Xd.shape[0]
+    ws = workspace(_ws_bytes(_cabi.RR_OP_GRADPASS_KEPT, N, plan))
+    check(lib.rr_slm_gradpass_kept(C.byref(plan.struct), _ptr(Xd), _ptr(yd), N,
+                                   _ptr(m32), _ptr(C32), _ptr(R), _ptr(sqerr),
+                                   _ptr(kept), kept.numel(), _ptr(ws), ws.numel(),
+                                   _stream_ptr()), "rr_slm_gradpass_kept")
+
+
 def slm_residual(plan, Xd, yd, m32, err=None, sqerr=None):
     t = require_cuda()
     lib = _cabi.load()
@@ -613,9 +654,12 @@ class Posterior(object):
     an evaluation only needs diag(C), m, logdet and -- for the gradient pass --
     a float32 image of C."""
 
-    def __init__(self, m, diagC, logdet, trgc, Linv=None, C=None, dg=None, C32=None):
+    def __init__(self, m, diagC, logdet, trgc, Linv=None, C=None, dg=None, C32=None, ok=None):
         self.m, self.diagC, self.logdet, self.trgc = m, diagC, logdet, trgc
         self._Linv, self._C, self._C32 = Linv, C, C32
+        # device scalar 1.0 / 0.0: the Cholesky factorisation was stable (None: the
+        # caller was told synchronously, or this is the clamped-spectrum solve)
+        self.ok = ok if ok is not None else m.new_ones(())
         # (max / min of the Cholesky diagonal)^2: a cheap lower bound on cond(iC)
         self.cond_est = None if dg is None else (dg.max() / dg.min()) ** 2
 
@@ -821,7 +865,7 @@ def _inverse_from_factor(L):
     return full[:D]
 
 
-def solve_posterior(G, p, var, lam, need_C=True):
+def solve_posterior(G, p, var, lam, need_C=True, defer_check=False):
     """C = (diag(1/lam) + G/var)^-1, logdet(iC), m = C p / var, tr(G C).
 
     Semantics of ``solve_posdef`` (revrand/mathfun/linalg.py:84-125): Cholesky;
@@ -837,6 +881,12 @@ def solve_posterior(G, p, var, lam, need_C=True):
     all of C; it is then formed by potri in float64 (forming it as
     (L^-1)^T (L^-1) in reduced precision loses the small entries of C to
     cancellation and derails the optimiser).
+
+    ``defer_check=True``: the Cholesky branch is taken WITHOUT asking the device
+    whether the factorisation was stable -- no host synchronisation, so the caller
+    can queue the rest of the evaluation behind the solve while the value pass is
+    still running.  The verdict comes back as the device scalar ``Posterior.ok``
+    (1.0 / 0.0); a caller that reads 0 repeats the solve with ``defer_check=False``.
     """
     t = torch()
     D = G.shape[0]
@@ -844,16 +894,19 @@ def solve_posterior(G, p, var, lam, need_C=True):
     iC.diagonal().add_(1.0 / lam)
     L, info = t.linalg.cholesky_ex(iC)
     dg = L.diagonal()
-    ok = bool(((info == 0) & (dg >= CHOLTHRESH).all()).item())
+    okt = (info == 0) & (dg >= CHOLTHRESH).all()
+    ok = True if defer_check else bool(okt.item())
     if ok and need_C and world()[1] > 1 and _use_blocked(L) and D >= 2 * world()[1]:
-        return _posterior_sharded(L, dg, p, var, lam)
+        post = _posterior_sharded(L, dg, p, var, lam)
+        post.ok = okt.double()
+        return post
     if ok and need_C:
         Cm = _inverse_from_factor(L)
         diagC = Cm.diagonal().clone()
         m = (Cm @ p) / var
         logdet = 2.0 * t.log(dg).sum()
         trgc = var * (D - (diagC / lam).sum())
-        return Posterior(m, diagC, logdet, trgc, C=Cm, dg=dg)
+        return Posterior(m, diagC, logdet, trgc, C=Cm, dg=dg, ok=okt.double())
     if ok:
         if _use_blocked(L):
             Linv = t.empty_like(L)
@@ -865,7 +918,7 @@ def solve_posterior(G, p, var, lam, need_C=True):
         m = (Linv.T @ (Linv @ p)) / var
         logdet = 2.0 * t.log(dg).sum()
         trgc = var * (D - (diagC / lam).sum())
-        return Posterior(m, diagC, logdet, trgc, Linv=Linv, dg=dg)
+        return Posterior(m, diagC, logdet, trgc, Linv=Linv, dg=dg, ok=okt.double())
     # Clamped-spectrum fallback (svd_solve, linalg.py:128-179).  iC is symmetric, so
     # its SVD is its eigendecomposition with s = |w|, U = V sign(w), Vh = V^T; syevd
     # is the robust dense routine on the device (gesvd returns NaN / exact zeros on

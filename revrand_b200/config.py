@@ -62,3 +62,11 @@ GLM_DEVICE_GRAPH = os.environ.get("REVRAND_B200_GLM_DEVICE_GRAPH", "1") != "0"
 # ... and its random starts are scored back to back on the device (one read at the end);
 # False: one ``_elbo`` call (host assembly) per start.
 GLM_DEVICE_STARTS = os.environ.get("REVRAND_B200_GLM_DEVICE_STARTS", "1") != "0"
+
+# An evaluation with gradients forms the feature map ONCE (as slm.py:145 does): the
+# value pass leaves an fp16 image of Phi behind and the gradient pass reads it
+# instead of evaluating sin/cos a second time.  The image takes 2 bytes per (row,
+# feature) of device memory (8.3 GB per GPU at config 2); larger than this, or than
+# half of the free memory, and the gradient pass regenerates Phi in row chunks.
+KEEP_FEATURES_MAX_BYTES = int(float(os.environ.get("REVRAND_B200_KEEP_FEATURES_MAX_GB", "64"))
+                              * (1 << 30))

@@ -130,6 +130,7 @@ extern "C" size_t rr_workspace_bytes(int32_t op, int64_t N, int32_t d,
     case RR_OP_GRADPASS:
     case RR_OP_PREDICT:
     case RR_OP_RESIDUAL:
+    case RR_OP_GRADPASS_KEPT:
       return rr::slm_workspace_bytes(op, N, &pl, engine);
     case RR_OP_GLM_STEP:
       return rr::glm_workspace_bytes(op, N, &pl, aux0 * aux1);

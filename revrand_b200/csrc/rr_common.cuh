@@ -132,9 +132,18 @@ int tc_suffstats(const rr_plan* plan, const float* X, const float* y, int64_t N,
                  cudaStream_t st);
 int tc3_suffstats_supported(const rr_plan* plan);
 size_t tc3_suffstats_workspace(const rr_plan* plan, int64_t N);
+// kept != NULL: also leave the fp16 feature image of the gradient pass behind
 int tc3_suffstats(const rr_plan* plan, const float* X, const float* y, int64_t N,
                   double* G, double* p, void* ws, size_t ws_bytes, rr_context* ctx,
-                  cudaStream_t st);
+                  cudaStream_t st, void* kept = nullptr);
+// Kept features (rr_slm_suffstats_keep -> rr_slm_gradpass_kept): padded column count of
+// the image (a multiple of 64) and its size in bytes for N rows.
+int64_t kept_features_cols(const rr_plan* plan);
+size_t kept_features_bytes(const rr_plan* plan, int64_t N);
+size_t tc_gradpass_kept_workspace(const rr_plan* plan, int64_t N);
+int tc_gradpass_kept(const rr_plan* plan, const float* X, const float* y, int64_t N,
+                     const float* m, const float* C, double* R, double* sqerr,
+                     const void* kept, void* ws, size_t ws_bytes, cudaStream_t st);
 size_t tc_gradpass_workspace(const rr_plan* plan, int64_t N);
 int tc_gradpass_supported(const rr_plan* plan);
 int tc_gradpass(const rr_plan* plan, const float* X, const float* y, int64_t N,

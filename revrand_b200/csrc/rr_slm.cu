@@ -208,6 +208,47 @@ extern "C" int rr_slm_suffstats(const rr_plan* plan, const float* X,
                         workspace_bytes, st);
 }
 
+extern "C" size_t rr_slm_kept_features_bytes(const rr_plan* plan, int64_t N) {
+  if (plan == nullptr || N < tc_auto_min_rows()) return 0;
+  return kept_features_bytes(plan, N);
+}
+
+extern "C" int rr_slm_suffstats_keep(const rr_plan* plan, const float* X, const float* y,
+                                     int64_t N, double* G, double* p, double* yy, void* kept,
+                                     size_t kept_bytes, void* workspace,
+                                     size_t workspace_bytes, rr_context* ctx, void* stream) {
+  RR_REQUIRE(plan && X && G && kept, "null pointer");
+  RR_REQUIRE(N > 0, "no rows");
+  const size_t need = kept_features_bytes(plan, N);
+  if (need == 0 || plan->kind != nullptr) {
+    set_error("kept features need a plan both tensor-core passes support");
+    return RR_ERR_UNSUPPORTED;
+  }
+  RR_REQUIRE(kept_bytes >= need, "kept feature buffer too small (rr_slm_kept_features_bytes)");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (yy && y) {
+    sumsq_kernel<<<sm_count() * 4, 256, 0, st>>>(y, N, yy);
+    RR_LAUNCH_CHECK("sumsq_kernel");
+  }
+  return tc3_suffstats(plan, X, y, N, G, y ? p : nullptr, workspace, workspace_bytes, ctx, st, kept);
+}
+
+extern "C" int rr_slm_gradpass_kept(const rr_plan* plan, const float* X, const float* y,
+                                    int64_t N, const float* m, const float* C, double* R,
+                                    double* sqerr, const void* kept, size_t kept_bytes,
+                                    void* workspace, size_t workspace_bytes, void* stream) {
+  RR_REQUIRE(plan && X && y && m && C && R && sqerr && kept, "null pointer");
+  RR_REQUIRE(N > 0, "no rows");
+  const size_t need = kept_features_bytes(plan, N);
+  if (need == 0 || plan->ktot == 0) {
+    set_error("kept features need a plan both tensor-core passes support");
+    return RR_ERR_UNSUPPORTED;
+  }
+  RR_REQUIRE(kept_bytes >= need, "kept feature buffer too small (rr_slm_kept_features_bytes)");
+  return tc_gradpass_kept(plan, X, y, N, m, C, R, sqerr, kept, workspace, workspace_bytes,
+                          (cudaStream_t)stream);
+}
+
 extern "C" int rr_slm_residual(const rr_plan* plan, const float* X,
                                const float* y, int64_t N, const float* m,
                                float* err, double* sqerr, void* workspace,
@@ -287,6 +328,7 @@ extern "C" int rr_slm_predict(const rr_plan* plan, const float* X, int64_t N,
 
 namespace rr {
 size_t slm_workspace_bytes(int op, int64_t N, const rr_plan* pl, int engine) {
+  if (op == RR_OP_GRADPASS_KEPT) return tc_gradpass_kept_workspace(pl, N);
   size_t s = simt_ws(op, N, pl);
   if (op != RR_OP_PREDICT && op != RR_OP_RESIDUAL) {
     const int e = pick_engine(engine, pl, N, op == RR_OP_GRADPASS);

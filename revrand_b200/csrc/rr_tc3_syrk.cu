@@ -245,10 +245,22 @@ __device__ __forceinline__ void t3_emit(uint8_t* __restrict__ img, int64_t kb, i
 constexpr bool T3_EXACT = RR_T3_EXACT_PROJECTION != 0;
 constexpr int T3_PARTS = T3_EXACT ? 3 : 2;
 
+//
+// KEEP: the block also leaves its values behind as fp16 in the tile-major operand
+// image of the gradient pass (rr_tc_gradpass.cu: [row block of 256][k block of 64
+// internal features] = one 32 KB SWIZZLE_128B image; internal order = blocks of
+// [64 cos | 64 sin] per 64 frequencies, then the affine columns), so that the
+// gradient pass of the same evaluation does not have to evaluate the feature map a
+// second time.  A trigonometric block owns 64 rows x 4 k blocks of that image: it
+// stages them in shared memory in their final byte order and writes them out as four
+// contiguous 8 KB runs.
+constexpr int T3_KEEP_BYTES = 4 * S3_KB * 128;    // staging: 4 k blocks x 64 rows x 128 B
+
+template <bool KEEP>
 __global__ void __launch_bounds__(256, 2)
 t3_digits_kernel(rr_plan plan, const float* __restrict__ X, const float* __restrict__ y,
                  int64_t rows, int Fp, int gy_trig, const unsigned int* __restrict__ scales,
-                 uint8_t* __restrict__ img) {
+                 uint8_t* __restrict__ img, uint8_t* __restrict__ phi16, int nkb16) {
   extern __shared__ float xs[];            // [T3_PARTS][64][stride]: tf32 parts of the slab
   const int d = plan.d, ktot = plan.ktot;
   const int kp = (d + 7) & ~7;             // input dimensions padded to whole k-steps
@@ -256,10 +268,17 @@ t3_digits_kernel(rr_plan plan, const float* __restrict__ X, const float* __restr
   float* xh = xs;
   float* xm = xs + S3_KB * stride;
   float* xl = xs + (T3_PARTS - 1) * S3_KB * stride;    // EXACT only (aliases xm otherwise)
+  // KEEP: staging area behind the slab (16-byte aligned: stride is a multiple of 4)
+  uint8_t* stage = reinterpret_cast<uint8_t*>(xs + T3_PARTS * S3_KB * stride);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int64_t kb = blockIdx.x;
   const int64_t n0 = kb * S3_KB;
   const bool trig = (int)blockIdx.y < gy_trig;
+  if (KEEP && trig) {
+    // frequencies past ktot and rows past the end stay zero in the image
+    uint4* z = reinterpret_cast<uint4*>(stage);
+    for (int e = tid; e < T3_KEEP_BYTES / 16; e += 256) z[e] = make_uint4(0u, 0u, 0u, 0u);
+  }
   for (int e = tid; e < S3_KB * kp; e += 256) {
     const int r = e / kp, i = e - r * kp;
     const float x = (i < d && n0 + r < rows) ? X[(n0 + r) * d + i] : 0.0f;
@@ -278,6 +297,20 @@ t3_digits_kernel(rr_plan plan, const float* __restrict__ X, const float* __restr
     // ---- affine columns, y, padding -------------------------------------------
     const int fl = tid >> 2, q = tid & 3;
     const int e = ((int)blockIdx.y - gy_trig) * T3_OTHER + fl;
+    if (KEEP && e < (nkb16 - 4 * gy_trig) * 64) {
+      // internal feature 256 gy_trig + e of the kept image: the raw column value (zero
+      // in the padding up to a whole k block)
+      const int fc = 256 * gy_trig + e;
+      uint8_t* line = phi16 + ((int64_t)(n0 >> 8) * nkb16 + (fc >> 6)) * 32768 +
+                      (int64_t)(n0 & 255) * 128 + (fc & 7) * 2;
+      const uint32_t c4 = (uint32_t)((fc & 63) >> 3);
+#pragma unroll
+      for (int b = 0; b < 16; ++b) {
+        const int r = t3_row_of(q, b);
+        const float v = (e < plan.next && n0 + r < rows) ? ext_value(plan, e, xh + r * stride, 1) : 0.0f;
+        *reinterpret_cast<__half*>(line + r * 128 + ((c4 ^ (uint32_t)(r & 7)) << 4)) = __float2half_rn(v);
+      }
+    }
     int f;
     int kq[16];
     if (e < plan.next) {
@@ -331,7 +364,8 @@ t3_digits_kernel(rr_plan plan, const float* __restrict__ X, const float* __restr
   // ---- trigonometric features ------------------------------------------------------
   const int g = lane >> 2, q = lane & 3;
   const int f0 = (int)blockIdx.y * T3_FREQS + 16 * warp;     // first frequency of this warp
-  if (f0 >= ktot) return;
+  if (!KEEP && f0 >= ktot) return;
+  if (f0 < ktot) {
   const int fA = f0 + g, fB = f0 + g + 8;
   float acc[8][4];
 #pragma unroll
@@ -376,17 +410,42 @@ t3_digits_kernel(rr_plan plan, const float* __restrict__ X, const float* __restr
     const int k = h ? fB : fA;
     if (k >= ktot) continue;
     int kc[16], ksn[16];
+    // KEEP: local frequency fl -> k block pair fl >> 6, 16-byte chunk (fl & 63) >> 3,
+    // element g inside the chunk (16 warp + 8 h is a multiple of 8)
+    const int fl = 16 * warp + 8 * h + g;
+    uint8_t* kcos = stage + (2 * (fl >> 6)) * (S3_KB * 128) + 2 * g;
+    const uint32_t kchunk = (uint32_t)((fl & 63) >> 3);
 #pragma unroll
     for (int b = 0; b < 16; ++b) {
       float sv, cv;
       t3_sincos_turns(acc[b >> 1][2 * h + (b & 1)], sv, cv);
-      const bool live = n0 + t3_row_of(q, b) < rows;
+      const int r = t3_row_of(q, b);
+      const bool live = n0 + r < rows;
       kc[b] = t3_quant(live ? cv : 0.0f);
       ksn[b] = t3_quant(live ? sv : 0.0f);
+      if (KEEP) {
+        // (q differs -> r & 7 differs -> four distinct chunks: conflict-free)
+        uint8_t* a = kcos + r * 128 + ((kchunk ^ (uint32_t)(r & 7)) << 4);
+        *reinterpret_cast<__half*>(a) = __float2half_rn(live ? cv : 0.0f);
+        *reinterpret_cast<__half*>(a + S3_KB * 128) = __float2half_rn(live ? sv : 0.0f);
+      }
     }
     const int fc = plan.col_cos[k], fs = plan.col_sin[k];
     if (fc >= 0) t3_emit(img, kb, Fp, fc, q, kc);
     if (fs >= 0) t3_emit(img, kb, Fp, fs, q, ksn);
+  }
+  }
+  if (KEEP) {
+    __syncthreads();
+    // four contiguous 8 KB runs: rows n0 .. n0+63 of k blocks 4 y .. 4 y + 3
+    uint8_t* dst = phi16 + ((int64_t)(n0 >> 8) * nkb16 + 4 * (int)blockIdx.y) * 32768 +
+                   (int64_t)(n0 & 255) * 128;
+    const uint4* src = reinterpret_cast<const uint4*>(stage);
+#pragma unroll
+    for (int i = 0; i < T3_KEEP_BYTES / 16 / 256; ++i) {
+      const int e = i * 256 + tid;
+      *reinterpret_cast<uint4*>(dst + (int64_t)(e >> 9) * 32768 + (e & 511) * 16) = src[e];
+    }
   }
 }
 
@@ -696,15 +755,17 @@ static int launch_syrk(const uint8_t* img, const S3Shape& s, int nkb, double* T,
 
 static int tc3_groups(const rr_plan* pl, const S3Shape& s, const float* X, const float* y,
                       int64_t N, const unsigned int* scales, uint8_t* const imgs[2], double* T,
-                      bool overlap, cudaStream_t sg, cudaStream_t st, cudaEvent_t ev_gen[2],
-                      cudaEvent_t ev_mma[2]) {
+                      uint8_t* phi16, bool overlap, cudaStream_t sg, cudaStream_t st,
+                      cudaEvent_t ev_gen[2], cudaEvent_t ev_mma[2]) {
   const int d = pl->d, D = s.D;
   const int gy_trig = (pl->ktot + T3_FREQS - 1) / T3_FREQS;
   const int nother = pl->next + 3 + (s.Fp - (D + 3));
   const int gy_other = (nother + T3_OTHER - 1) / T3_OTHER;
-  const size_t dsmem = (size_t)T3_PARTS * S3_KB * (((d + 7) & ~7) + 4) * sizeof(float);
+  const int nkb16 = (int)(kept_features_cols(pl) / 64);
+  const size_t dsmem = (size_t)T3_PARTS * S3_KB * (((d + 7) & ~7) + 4) * sizeof(float) +
+                       (phi16 ? T3_KEEP_BYTES : 0);
   if (dsmem > 48 * 1024)
-    RR_CUDA_CHECK(cudaFuncSetAttribute(t3_digits_kernel,
+    RR_CUDA_CHECK(cudaFuncSetAttribute(phi16 ? t3_digits_kernel<true> : t3_digits_kernel<false>,
                                        cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dsmem));
   int g = 0;
   int64_t step = 0;
@@ -718,8 +779,14 @@ static int tc3_groups(const rr_plan* pl, const S3Shape& s, const float* X, const
     const int buf = g & 1;
     if (overlap && g >= 2) RR_CUDA_CHECK(cudaStreamWaitEvent(sg, ev_mma[buf], 0));
     dim3 grid((unsigned)nkb, (unsigned)(gy_trig + gy_other));
-    t3_digits_kernel<<<grid, 256, dsmem, sg>>>(*pl, X + r0 * d, y ? y + r0 : nullptr, rows, s.Fp,
-                                               gy_trig, scales, imgs[buf]);
+    if (phi16)   // groups start on multiples of 32768 rows: whole 256-row images
+      t3_digits_kernel<true><<<grid, 256, dsmem, sg>>>(
+          *pl, X + r0 * d, y ? y + r0 : nullptr, rows, s.Fp, gy_trig, scales, imgs[buf],
+          phi16 + (r0 >> 8) * (int64_t)nkb16 * 32768, nkb16);
+    else
+      t3_digits_kernel<false><<<grid, 256, dsmem, sg>>>(*pl, X + r0 * d, y ? y + r0 : nullptr,
+                                                        rows, s.Fp, gy_trig, scales, imgs[buf],
+                                                        nullptr, nkb16);
     RR_LAUNCH_CHECK("t3_digits_kernel");
     if (overlap) {
       RR_CUDA_CHECK(cudaEventRecord(ev_gen[buf], sg));
@@ -733,8 +800,23 @@ static int tc3_groups(const rr_plan* pl, const S3Shape& s, const float* X, const
 }
 
 int tc3_suffstats(const rr_plan* pl, const float* X, const float* y, int64_t N, double* G,
-                  double* p, void* ws, size_t ws_bytes, rr_context* ctx, cudaStream_t st) {
+                  double* p, void* ws, size_t ws_bytes, rr_context* ctx, cudaStream_t st,
+                  void* kept) {
   const S3Shape s = s3_shape(pl, N);
+  uint8_t* phi16 = static_cast<uint8_t*>(kept);
+  if (phi16 != nullptr) {
+    if (!tc_gradpass_supported(pl) || (reinterpret_cast<uintptr_t>(phi16) & 1023) != 0) {
+      set_error("kept features: plan not supported by the tensor-core gradient pass, or the "
+                "buffer is not 1024-byte aligned");
+      return RR_ERR_INVALID;
+    }
+    if (N % 256 != 0) {
+      // rows past the end of the last 256-row image: the K blocks of the generator
+      // stop at the next multiple of 64
+      const int64_t cols = kept_features_cols(pl);
+      RR_CUDA_CHECK(cudaMemsetAsync(phi16 + (N / 256) * cols * 512, 0, (size_t)cols * 512, st));
+    }
+  }
   const int D = s.D, d = pl->d;
   Workspace W(ws, ws_bytes);
   double* T = W.take<double>((size_t)(D + 3) * s.ldT);
@@ -783,8 +865,8 @@ int tc3_suffstats(const rr_plan* pl, const float* X, const float* y, int64_t N, 
   }
 
   {
-    const int rc = tc3_groups(pl, s, X, (p != nullptr) ? y : nullptr, N, scales, imgs, T, overlap, sg,
-                              st, ev_gen, ev_mma);
+    const int rc = tc3_groups(pl, s, X, (p != nullptr) ? y : nullptr, N, scales, imgs, T, phi16,
+                              overlap, sg, st, ev_gen, ev_mma);
     if (rc) {   // join whatever the helper stream still has queued, then report
       if (overlap && cudaEventRecord(ev_fork, sg) == cudaSuccess) cudaStreamWaitEvent(st, ev_fork, 0);
       return rc;

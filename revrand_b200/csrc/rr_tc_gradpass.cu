@@ -270,6 +270,91 @@ static int launch_phi_fit(const rr_plan* pl, const float* X, int rows, int rows_
   return RR_OK;
 }
 
+// ---- fitted values from a kept fp16 feature image ---------------------------------
+// mi[f] = weight of internal feature f in f = Phi m: amp * m[column] for the
+// trigonometric features, m[column] for the affine ones, 0 in the padding.
+__global__ void __launch_bounds__(256)
+mint_kernel(rr_plan plan, const float* __restrict__ m, int Dp, int Dk, float* __restrict__ mi) {
+  const int f = blockIdx.x * blockDim.x + threadIdx.x;
+  if (f >= Dk) return;
+  float v = 0.0f;
+  if (f < Dp) {
+    const int th = feat_theta(f);
+    if (th < plan.ktot) {
+      const int c = feat_is_sin(f) ? plan.col_sin[th] : plan.col_cos[th];
+      if (c >= 0) v = plan.amp[th] * m[c];
+    }
+  } else if (f - Dp < plan.next) {
+    v = m[plan.ext_col[f - Dp]];
+  }
+  mi[f] = v;
+}
+
+// err = y - Phi m, sqerr += sum err^2 from the tile-major fp16 image.  Block = one
+// 256-row image column (all k blocks), warp = 32 rows; a warp instruction reads four
+// whole 128-byte lines (lane = row sub-index x 16-byte chunk), so the pass streams
+// the image once at HBM speed.  MI_SMEM: the weights fit in shared memory.
+template <bool MI_SMEM>
+__global__ void __launch_bounds__(256)
+fit16_kernel(const uint8_t* __restrict__ PhT, int nkb, const float* __restrict__ mi,
+             const float* __restrict__ y, int64_t rows, float* __restrict__ err,
+             double* __restrict__ sqerr) {
+  extern __shared__ float mis[];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (MI_SMEM) {
+    for (int e = tid; e < nkb * 64; e += 256) mis[e] = mi[e];
+    __syncthreads();
+  }
+  const float* mw = MI_SMEM ? mis : mi;
+  const int rsub = lane >> 3, p = lane & 7;
+  const uint8_t* base = PhT + (int64_t)blockIdx.x * nkb * G2_IMG + (32 * warp + rsub) * 128 + p * 16;
+  float acc[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) acc[i] = 0.0f;
+  for (int kb = 0; kb < nkb; ++kb) {
+    const uint8_t* img = base + (int64_t)kb * G2_IMG;
+    uint4 v[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] = __ldg(reinterpret_cast<const uint4*>(img + i * 512));
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      // row 32 warp + 4 i + rsub: its chunk at position p holds features 8 (p ^ (row & 7)) ..
+      const int c = p ^ ((4 * i + rsub) & 7);
+      const float4 w0 = *reinterpret_cast<const float4*>(mw + kb * 64 + 8 * c);
+      const float4 w1 = *reinterpret_cast<const float4*>(mw + kb * 64 + 8 * c + 4);
+      const __half2* h = reinterpret_cast<const __half2*>(&v[i]);
+      const float2 a = __half22float2(h[0]), b = __half22float2(h[1]);
+      const float2 c2 = __half22float2(h[2]), d2 = __half22float2(h[3]);
+      float t = acc[i];
+      t = fmaf(a.x, w0.x, t);
+      t = fmaf(a.y, w0.y, t);
+      t = fmaf(b.x, w0.z, t);
+      t = fmaf(b.y, w0.w, t);
+      t = fmaf(c2.x, w1.x, t);
+      t = fmaf(c2.y, w1.y, t);
+      t = fmaf(d2.x, w1.z, t);
+      t = fmaf(d2.y, w1.w, t);
+      acc[i] = t;
+    }
+  }
+  double sq = 0.0;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    float t = acc[i];
+    t += __shfl_xor_sync(0xffffffffu, t, 1);
+    t += __shfl_xor_sync(0xffffffffu, t, 2);
+    t += __shfl_xor_sync(0xffffffffu, t, 4);
+    const int64_t n = (int64_t)blockIdx.x * 256 + 32 * warp + 4 * i + rsub;
+    if (p == 0 && n < rows) {
+      const float e = y[n] - t;
+      err[n] = e;
+      sq += (double)e * (double)e;
+    }
+  }
+  sq = warp_sum(sq);
+  if (lane == 0 && sq != 0.0) atomicAdd(sqerr, sq);
+}
+
 // ---- GEMM + fused epilogue ------------------------------------------------------
 struct G2Bars {
   uint64_t full[G2_STAGES];        // own bulk copies landed (complete_tx)
@@ -582,6 +667,72 @@ static int launch_gp2(const rr_plan* pl, const float* X, const float* err, int r
                                    m, cmax, R));
   RR_LAUNCH_CHECK("gp2_kernel");
   return RR_OK;
+}
+
+// ---- gradient pass from a kept feature image ----------------------------------------
+int64_t kept_features_cols(const rr_plan* pl) { return gp_dk(pl); }
+size_t kept_features_bytes(const rr_plan* pl, int64_t N) {
+  if (!tc_gradpass_supported(pl) || !tc3_suffstats_supported(pl) || N <= 0) return 0;
+  return (size_t)((N + G2_TM - 1) / G2_TM) * (size_t)gp_dk(pl) * 512;
+}
+size_t tc_gradpass_kept_workspace(const rr_plan* pl, int64_t N) {
+  const int64_t Dp = gp_dp(pl), Dk = gp_dk(pl);
+  return align_up((size_t)Dp * Dk * 2, 1024) + 1024 + align_up((size_t)N * 4, 256) +
+         align_up((size_t)Dk * 4, 256) + 8192;
+}
+
+// The value pass of the same evaluation left Phi behind (tc3_suffstats, kept != NULL):
+// residuals in one streaming pass over the image, then ONE persistent GEMM launch over
+// all rows -- no second evaluation of the feature map, no per-chunk launches.
+int tc_gradpass_kept(const rr_plan* pl, const float* X, const float* y, int64_t N,
+                     const float* m, const float* C, double* R, double* sqerr,
+                     const void* kept, void* ws, size_t wsb, cudaStream_t st) {
+  const int Dp = gp_dp(pl), Dk = gp_dk(pl), FB = Dp / G2_TN, nkb = Dk / G2_KT;
+  const uint8_t* PhT = static_cast<const uint8_t*>(kept);
+  if (N >= ((int64_t)1 << 31) - 256 || (reinterpret_cast<uintptr_t>(PhT) & 1023) != 0) {
+    set_error("kept gradient pass: too many rows for one launch, or image not 1024-byte aligned");
+    return RR_ERR_INVALID;
+  }
+  Workspace W(ws, wsb);
+  uint8_t* BtT = W.take<uint8_t>(align_up((size_t)Dp * Dk * 2, 1024) + 1024);
+  float* err = W.take<float>((size_t)N);
+  float* mi = W.take<float>((size_t)Dk);
+  unsigned int* cmax = W.take<unsigned int>(1);
+  if (!BtT || !err || !mi || !cmax) {
+    set_error("kept gradient pass workspace too small (need %zu bytes)",
+              tc_gradpass_kept_workspace(pl, N));
+    return RR_ERR_WORKSPACE;
+  }
+  BtT = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(BtT) + 1023) & ~(uintptr_t)1023);
+  RR_CUDA_CHECK(cudaMemsetAsync(cmax, 0, sizeof(unsigned int), st));
+  mint_kernel<<<(Dk + 255) / 256, 256, 0, st>>>(*pl, m, Dp, Dk, mi);
+  RR_LAUNCH_CHECK("mint_kernel");
+  const int RB = (int)((N + G2_TM - 1) / G2_TM);
+  {
+    const size_t smem = (size_t)Dk * sizeof(float);
+    if (smem <= 160 * 1024) {
+      if (smem > 48 * 1024)
+        RR_CUDA_CHECK(cudaFuncSetAttribute(fit16_kernel<true>,
+                                           cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      fit16_kernel<true><<<RB, 256, smem, st>>>(PhT, nkb, mi, y, N, err, sqerr);
+    } else {
+      fit16_kernel<false><<<RB, 256, 0, st>>>(PhT, nkb, mi, y, N, err, sqerr);
+    }
+    RR_LAUNCH_CHECK("fit16_kernel");
+  }
+  absmax_kernel<<<sm_count() * 4, 256, 0, st>>>(C, (int64_t)pl->D * pl->D, cmax);
+  RR_LAUNCH_CHECK("absmax_kernel");
+  {
+    dim3 grid((Dk + 255) / 256, Dp);
+    prep_c_kernel<<<grid, 256, 0, st>>>(*pl, C, Dp, Dk, cmax, BtT);
+    RR_LAUNCH_CHECK("prep_c_kernel");
+  }
+  const int d = pl->d, rows = (int)N;
+  if (d <= 4) return launch_gp2<1>(pl, X, err, rows, RB, FB, nkb, PhT, BtT, m, cmax, R, st);
+  if (d <= 8) return launch_gp2<2>(pl, X, err, rows, RB, FB, nkb, PhT, BtT, m, cmax, R, st);
+  if (d <= 16) return launch_gp2<4>(pl, X, err, rows, RB, FB, nkb, PhT, BtT, m, cmax, R, st);
+  if (d <= 24) return launch_gp2<6>(pl, X, err, rows, RB, FB, nkb, PhT, BtT, m, cmax, R, st);
+  return launch_gp2<8>(pl, X, err, rows, RB, FB, nkb, PhT, BtT, m, cmax, R, st);
 }
 
 // Residuals only (value-only evaluations; any feature plan):

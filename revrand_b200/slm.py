@@ -74,7 +74,22 @@ class _SLMProblem(object):
         self.R = self.rflat[:nfl - 1].view(self.plan.d, max(self.plan.ktot, 1))
         self.sqerr = self.rflat[nfl - 1:]
         self.yy = None
+        self._kept = None          # fp16 feature image shared by the two passes
+        self._kept_tried = False
         self._refresh_col_scale()
+
+    def _kept_buffer(self):
+        """The fp16 feature image the value pass leaves behind for the gradient pass
+        of the same evaluation (config.KEEP_FEATURES_MAX_BYTES), or None."""
+        from . import _cabi
+        if not self._kept_tried:
+            self._kept_tried = True
+            if (self.engine in (_cabi.RR_ENGINE_AUTO, _cabi.RR_ENGINE_TCGEN05)
+                    and self.plan.ktot and self.uses_tcgen05()
+                    and self.Xd.shape[0] >= eng.auto_min_rows()):
+                self._kept = eng.kept_features_buffer(self.plan, self.Xd.shape[0],
+                                                      config.KEEP_FEATURES_MAX_BYTES)
+        return self._kept
 
     def _refresh_col_scale(self):
         """max |X[:, i]|, max |y| over all rows of all ranks: the fixed-point scales
@@ -149,16 +164,37 @@ class _SLMProblem(object):
         if plan.trig:
             plan.set_lenscales([h for h in hypers])
         st.zero_()
-        eng.slm_suffstats(plan, self.Xd, self.yd, st, engine=self.engine,
-                          want_yy=self.yy is None)
-        eng.allreduce_sum_(st.flat)
-        if self.yy is None:
-            self.yy = float(st.yy.item())
+        # (every upload happens BEFORE the value pass is queued: a pageable host-to-device
+        # copy behind it in stream order would block the host until the pass is done)
         lam_np, slices = self.basis.regularizer_diagonal(self.Xhost_probe, *regs)
         slices = slices if isinstance(slices, list) else [slice(0, self.D)]
         lam = eng.to_device(lam_np, t.float64)
+        kept = self._kept_buffer() if (want_grad and plan.ktot) else None
+        if kept is not None:
+            eng.slm_suffstats_keep(plan, self.Xd, self.yd, st, kept, want_yy=self.yy is None)
+        else:
+            eng.slm_suffstats(plan, self.Xd, self.yd, st, engine=self.engine,
+                              want_yy=self.yy is None)
+        eng.allreduce_sum_(st.flat)
+        if self.yy is None:
+            self.yy = float(st.yy.item())
+        for defer in (True, False):
+            # first without asking the device whether the Cholesky factor was stable:
+            # nothing between the value pass and the final read waits for the device,
+            # so the host queues the solve and the gradient pass while the value pass
+            # is still running.  The factor's verdict comes back with the scalars; the
+            # rare unstable point repeats the solve on the checked path (clamped
+            # spectrum, linalg.py:128-179) -- the statistics and the kept features stand.
+            out = self._finish(var, lam_np, lam, slices, want_grad, kept, defer)
+            if out is not None:
+                return out
+
+    def _finish(self, var, lam_np, lam, slices, want_grad, kept, defer):
+        """Solve + residual / gradient pass + the one read-back of an evaluation."""
+        t = eng.torch()
+        plan, st = self.plan, self.stats
         post = eng.solve_posterior(st.G, st.p, float(var), lam,
-                                   need_C=bool(want_grad and plan.ktot))
+                                   need_C=bool(want_grad and plan.ktot), defer_check=defer)
         m, logdet, trgc = post.m, post.logdet, post.trgc
         mc = m * m + post.diagC
         q = t.stack([mc[s].sum() for s in slices])
@@ -168,8 +204,12 @@ class _SLMProblem(object):
         g = None
         from_stats = False
         if want_grad and plan.ktot:
-            eng.slm_gradpass(plan, self.Xd, self.yd, m32, post.C32(), self.R,
-                             self.sqerr, engine=self.engine)
+            if kept is not None:
+                eng.slm_gradpass_kept(plan, self.Xd, self.yd, m32, post.C32(), self.R,
+                                      self.sqerr, kept)
+            else:
+                eng.slm_gradpass(plan, self.Xd, self.yd, m32, post.C32(), self.R,
+                                 self.sqerr, engine=self.engine)
             eng.allreduce_sum_(self.rflat)
         else:
             # value-only evaluation: sum Err^2 = y'y - 2 p'm + m'G m from the (already
@@ -180,13 +220,16 @@ class _SLMProblem(object):
             from_stats = True
             self.sqerr.copy_((self.yy - 2.0 * st.p.dot(m) + m.dot(st.G @ m)).reshape(1))
         cond = post.cond_est if post.cond_est is not None else logdet.new_zeros(())
-        parts = [logdet.reshape(1), trgc.reshape(1), self.sqerr, cond.reshape(1), q]
+        parts = [logdet.reshape(1), trgc.reshape(1), self.sqerr, cond.reshape(1),
+                 post.ok.reshape(1), q]
         if want_grad and plan.ktot:
             WR = plan._Wfull_dev * self.R[:, :plan.ktot]
             g = t.stack([WR[:, ko:ko + b.K].sum(dim=1)
                          for b, ko in zip(plan.trig, plan.freq_offsets)])
             parts.append(g.reshape(-1))
         host = t.cat(parts).cpu().numpy()
+        if defer and not host[4] == 1.0:
+            return None
         if from_stats and not host[2] > config.SQERR_FROM_STATS_MIN * self.yy:
             self.rflat.zero_()
             eng.slm_residual(plan, self.Xd, self.yd, m32, sqerr=self.sqerr)
@@ -194,9 +237,9 @@ class _SLMProblem(object):
             host[2] = float(self.sqerr.item())
         out["logdet"], out["trgc"], out["sqerr"] = host[0], host[1], host[2]
         out["cond_est"] = host[3]
-        out["q"] = host[4:4 + len(slices)]
+        out["q"] = host[5:5 + len(slices)]
         if g is not None:
-            out["g"] = host[4 + len(slices):].reshape(len(plan.trig), plan.d)
+            out["g"] = host[5 + len(slices):].reshape(len(plan.trig), plan.d)
         return out
 
 

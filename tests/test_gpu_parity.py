@@ -922,3 +922,58 @@ def test_slm_predictive_moments_through_tensor_core_gemm_vs_oracle():
     Ey2, Vy2 = slm2.predict_moments(Xs)
     np.testing.assert_allclose(Ey2, Ey, rtol=1e-5, atol=1e-7)
     np.testing.assert_allclose(Vy2, Vy, rtol=1e-5)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("N,d,K,linear", [(20011, 21, 200, False), (33000, 6, 160, True),
+                                          (16384, 8, 64, False)])
+def test_kept_feature_image_equals_regenerated_features(N, d, K, linear):
+    """An evaluation with gradients forms the feature map once (slm.py:145): the value
+    pass leaves an fp16 image of Phi behind (rr_slm_suffstats_keep) and the gradient
+    pass reads it (rr_slm_gradpass_kept).  Against the path that regenerates Phi in the
+    gradient pass: statistics bit-identical (the digit image does not change), the
+    lengthscale gradients equal to fp16 rounding, and both against the float64 oracle."""
+    from revrand_b200.slm import _SLMProblem
+    X, y = _synthetic(N, d, seed=17)
+    ls = 2.5 * (1.0 + 0.07 * np.arange(d))
+    rbf = bf.RandomRBF(nbases=K, Xdim=d, random_state=8, lenscale=Parameter(ls, Positive()),
+                       regularizer=Parameter(1.3, Positive()))
+    basis = rbf + bf.LinearBasis(onescol=True, regularizer=Parameter(2.0, Positive())) \
+        if linear else rbf
+    regs = [1.3, 2.0] if linear else [1.3]
+    out = {}
+    old_engine, old_keep = config.ENGINE, config.KEEP_FEATURES_MAX_BYTES
+    config.ENGINE = "tcgen05"
+    try:
+        for keep in (True, False):
+            config.KEEP_FEATURES_MAX_BYTES = (1 << 40) if keep else 0
+            prob = _SLMProblem(basis, X, y)
+            r = prob.evaluate(0.05, regs, [ls])
+            assert (prob._kept is not None) == keep
+            # (G and p only: yy is a float64 atomic sum)
+            out[keep] = (prob.stats.flat[:-1].clone(), r["g"].copy(), r["sqerr"], r["logdet"])
+            if keep:    # a second evaluation reuses the buffer
+                r2 = prob.evaluate(0.05, regs, [ls])
+                np.testing.assert_allclose(r2["g"], r["g"], rtol=1e-4, atol=1e-6 * np.abs(r["g"]).max())
+    finally:
+        config.ENGINE, config.KEEP_FEATURES_MAX_BYTES = old_engine, old_keep
+    assert bool((out[True][0] == out[False][0]).all())
+    assert out[True][3] == out[False][3]
+    assert relerr(out[True][1], out[False][1]) < 2e-3
+    assert abs(out[True][2] - out[False][2]) <= 1e-4 * out[False][2]
+    blocks = [dict(kind="trig", W=rbf.W, lenscale=ls, cols=None)]
+    if linear:
+        blocks.append(dict(kind="linear", onescol=True, cols=None))
+    ref = orc.slm_elbo(X, y, 0.05, regs, blocks)
+    # evaluate() returns R.W summed per block; the host turns it into d(-ELBO)/dl
+    # (slm._elbo); compare through the model
+    config.ENGINE = "tcgen05"
+    try:
+        slm = rr.StandardLinearModel(basis=basis)
+        slm.obj_ = -np.inf
+        nelbo, (dv, dr, dl) = slm._elbo(X, y, 0.05, regs if linear else regs[0], ls)
+        assert slm._cached_problem._kept is not None
+    finally:
+        config.ENGINE = old_engine
+    assert abs(nelbo - ref["neg_elbo"]) <= 1e-4 * abs(ref["neg_elbo"])
+    assert relerr(dl, ref["dhyp"][0]) < 5e-3
