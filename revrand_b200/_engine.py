@@ -813,21 +813,27 @@ def _posterior_sharded(L, dg, p, var, lam):
     t = torch()
     rank, ws = world()
     D = L.shape[0]
-    per = (D + ws - 1) // ws
-    lo = min(rank * per, D)
-    hi = min(lo + per, D)
     Li = t.empty_like(L)
     _tri_inv_lower(L, Li)
     diagC = (Li * Li).sum(dim=0)
     m = (Li.T @ (Li @ p)) / var
-    rows = t.zeros((per, D), dtype=t.float32, device=L.device)
-    if hi > lo:
-        rows[:hi - lo] = (Li[:, lo:hi].T @ Li).float()
-    full = t.empty((ws * per, D), dtype=t.float32, device=L.device)
-    t.distributed.all_gather_into_tensor(full, rows)
+    # Rows [lo, hi) of C = Li^T Li only involve rows >= lo of the lower-triangular Li:
+    # C[lo:hi, :] = Li[lo:, lo:hi]^T Li[lo:, :].  The cost of a slab falls linearly with
+    # lo, so the rows are cut into 2 ws slabs and rank r takes slabs r and 2 ws - 1 - r:
+    # every rank does the same D^3 / (4 ws) multiply-adds, half of the dense product.
+    per = (D + 2 * ws - 1) // (2 * ws)
+    rows = t.zeros((2, per, D), dtype=t.float32, device=L.device)
+    for j, sl in enumerate((rank, 2 * ws - 1 - rank)):
+        lo = min(sl * per, D)
+        hi = min(lo + per, D)
+        if hi > lo:
+            rows[j, :hi - lo] = (Li[lo:, lo:hi].T @ Li[lo:, :]).float()
+    full = t.empty((ws, 2, per, D), dtype=t.float32, device=L.device)
+    t.distributed.all_gather_into_tensor(full.view(ws * 2 * per, D), rows.view(2 * per, D))
+    C32 = t.cat([full[:, 0].reshape(ws * per, D), full[:, 1].flip(0).reshape(ws * per, D)])[:D]
     logdet = 2.0 * t.log(dg).sum()
     trgc = var * (D - (diagC / lam).sum())
-    return Posterior(m, diagC, logdet, trgc, Linv=Li, dg=dg, C32=full[:D].contiguous())
+    return Posterior(m, diagC, logdet, trgc, Linv=Li, dg=dg, C32=C32.contiguous())
 
 
 def _inverse_from_factor(L):

@@ -24,7 +24,7 @@ def _worker(rank, world, port, ret):
         from oracle import oracle as orc
         from revrand_b200 import _engine
         rs = np.random.RandomState(0)
-        N, d, K = 501, 3, 8
+        N, d, K = 501, 3, 9
         X, y = rs.randn(N, d), rs.randn(N)
         W = np.random.RandomState(1).randn(d, K)
         assert _engine.world() == (rank, world)
@@ -57,6 +57,10 @@ def _worker(rank, world, port, ret):
         post2 = _engine.solve_posterior(torch.from_numpy(A), torch.from_numpy(Pf.T.dot(y)),
                                         0.3, torch.from_numpy(lam))
         ok = ok and np.allclose(post2.C.numpy(), Cref, rtol=1e-9, atol=1e-12)
+        # ... and the float32 image of C the gradient pass reads: row slabs of
+        # Li^T Li formed by the ranks (two slabs each, triangular part only), all-gathered
+        ok = ok and post2._C32 is not None
+        ok = ok and np.allclose(post2.C32().numpy(), Cref, rtol=1e-5, atol=1e-7 * np.abs(Cref).max())
         # ranks of a sharded fit share rank 0's random starts, and a basis that
         # differs between ranks is refused
         mine = np.random.RandomState(100 + rank)

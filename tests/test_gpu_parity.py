@@ -783,9 +783,11 @@ def test_fit_with_pipelined_starts_equals_sequential_starts():
         # L-BFGS-B stops on a relative reduction of 2e-9; where exactly it stops depends
         # on rounding (the gradient pass accumulates with atomics): 1e-3 in the ELBO
         np.testing.assert_allclose(obj, 884.1130585887014, rtol=1e-5)
-        np.testing.assert_allclose(var, 0.009382774997534381, rtol=1e-3)
-        np.testing.assert_allclose(reg, 2.604544348753961, rtol=1e-2)
-        np.testing.assert_allclose(hyp, 2.3147175684812105, rtol=1e-3)
+        # (the objective is flat in the regulariser: runs that agree to 1e-6 in the ELBO
+        # stop 1 % apart in it)
+        np.testing.assert_allclose(var, 0.009382774997534381, rtol=5e-3)
+        np.testing.assert_allclose(reg, 2.604544348753961, rtol=5e-2)
+        np.testing.assert_allclose(hyp, 2.3147175684812105, rtol=5e-3)
 
 
 @pytest.mark.gpu
