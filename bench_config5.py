@@ -107,9 +107,15 @@ def main(args):
         prob.evaluate(var, regs, hyp, want_grad=True)          # warm-up (allocations, plans)
         ph = {}
 
+        kept = prob._kept_buffer()     # the fp16 feature image shared by the two passes
+
         def f_value():
             st.zero_()
-            _engine.slm_suffstats(plan, prob.Xd, prob.yd, st, engine=prob.engine, want_yy=False)
+            if kept is not None:
+                _engine.slm_suffstats_keep(plan, prob.Xd, prob.yd, st, kept, want_yy=False)
+            else:
+                _engine.slm_suffstats(plan, prob.Xd, prob.yd, st, engine=prob.engine,
+                                      want_yy=False)
         ph["value_pass_ms"], _ = timed(f_value)
         ph["allreduce_stats_ms"], _ = timed(lambda: _engine.allreduce_sum_(st.flat))
         lam = torch.ones(D, dtype=torch.float64, device="cuda")
@@ -119,8 +125,12 @@ def main(args):
 
         def f_grad():
             prob.rflat.zero_()
-            _engine.slm_gradpass(plan, prob.Xd, prob.yd, m32, C32, prob.R, prob.sqerr,
-                                 engine=prob.engine)
+            if kept is not None:
+                _engine.slm_gradpass_kept(plan, prob.Xd, prob.yd, m32, C32, prob.R, prob.sqerr,
+                                          kept)
+            else:
+                _engine.slm_gradpass(plan, prob.Xd, prob.yd, m32, C32, prob.R, prob.sqerr,
+                                     engine=prob.engine)
         ph["gradient_pass_ms"], _ = timed(f_grad)
         ph["allreduce_grad_ms"], _ = timed(lambda: _engine.allreduce_sum_(prob.rflat))
         del post, C32
@@ -149,10 +159,11 @@ def main(args):
             "check": {"logdet": float(r["logdet"]), "m_norm": float(r["m"].norm().item())},
             "workspace_gb": float(_engine._workspace[local].numel()) / 2 ** 30
             if local in _engine._workspace else None,
+            "kept_features_gb": None if kept is None else float(kept.numel()) / 2 ** 30,
         }
         if rank == 0:
             print(json.dumps(line), flush=True)
-        del prob, plan, st
+        del prob, plan, st, kept
         _engine._workspace.clear()
         torch.cuda.empty_cache()
     if world > 1:

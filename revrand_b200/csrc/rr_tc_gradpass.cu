@@ -43,11 +43,11 @@ constexpr int G2_STAGES = 5;
 constexpr int G2_STAGE_BYTES = 2 * G2_HALF;   // A half + B half
 constexpr int G2_THREADS = 6 * 32;      // producer, MMA / relay, 4 epilogue warps
 constexpr int G2_RED = 4 * 32 * 32;     // floats of one cross-warp reduction buffer
-// Phi chunk budget.  The chunk does not have to fit in L2: tiles are visited with
-// the output-feature block fastest, so the CTA pairs running at any time share a
-// handful of 2 MB row-block panels of Phi plus the 32 MB image of C; each panel is
-// fetched from HBM once and then hit in L2 by the other 15 feature blocks.  Large
-// chunks amortise the per-launch pipeline fill and the exposed last epilogue.
+// Phi chunk budget.  The chunk does not have to fit in L2: tiles are visited in
+// supertiles (g2_tile), so the CTA pairs running at any time share a handful of
+// row-block panels of Phi and of panels of the C image; each panel is fetched from
+// HBM once per supertile and then hit in L2.  Large chunks amortise the per-launch
+// pipeline fill and the exposed last epilogue.
 constexpr int64_t G2_SCRATCH_BYTES = 320ll << 20;
 
 // internal feature f -> (frequency, is_sin): blocks of [64 cos | 64 sin]
@@ -365,6 +365,22 @@ struct G2Bars {
   uint32_t tmem_base;
 };
 
+// Tile order.  Tile t of the launch -> (row block rb, output-feature block fb), visited
+// in supertiles of G2_SUPER row blocks x all FB feature blocks with the row block
+// fastest: the ~74 tiles in flight at any time then touch ~G2_SUPER row panels of Phi
+// and ~74 / G2_SUPER panels of the C image instead of 2 and all FB -- for K >= 4096 the
+// C image (135 MB at K = 4096) no longer fits in L2, and with the feature block fastest
+// every row block streamed all of it from HBM.
+constexpr int G2_SUPER = 8;
+__device__ __forceinline__ void g2_tile(int t, int RB, int FB, int& rb, int& fb) {
+  const int per = G2_SUPER * FB;
+  const int s = t / per, tl = t - s * per;
+  const int left = RB - s * G2_SUPER;
+  const int rs = left < G2_SUPER ? left : G2_SUPER;
+  fb = tl / rs;
+  rb = s * G2_SUPER + (tl - fb * rs);
+}
+
 template <int IG>   // input dimensions per reducing warp: d <= 4 * IG
 __global__ void __launch_bounds__(G2_THREADS, 1)
 gp2_kernel(rr_plan plan, const float* __restrict__ X, const float* __restrict__ err,
@@ -413,7 +429,8 @@ gp2_kernel(rr_plan plan, const float* __restrict__ X, const float* __restrict__ 
     if (elect_one()) {
       uint32_t g = 0;
       for (int t = pair; t < ntiles; t += npairs) {
-        const int rb = t / FB, fb = t - rb * FB;
+        int rb, fb;
+        g2_tile(t, RB, FB, rb, fb);
         const uint8_t* a_src = PhT + ((int64_t)rb * nkb) * G2_IMG + (int64_t)crank * G2_HALF;
         const uint8_t* b_src = BtT + ((int64_t)fb * nkb) * G2_IMG + (int64_t)crank * G2_HALF;
         for (int kb = 0; kb < nkb; ++kb, ++g) {
@@ -476,7 +493,8 @@ gp2_kernel(rr_plan plan, const float* __restrict__ X, const float* __restrict__ 
     const float cmax = __uint_as_float(*cmax_bits);
     uint32_t it = 0;
     for (int t = pair; t < ntiles; t += npairs, ++it) {
-      const int rb = t / FB, fb = t - rb * FB;
+      int rb, fb;
+      g2_tile(t, RB, FB, rb, fb);
       const uint32_t buf = it & 1;
       const int row0 = rb * G2_TM + 128 * (int)crank;       // first row of this CTA's half
       // tables for this tile (the previous tile's readers are past their last barrier)
@@ -670,9 +688,18 @@ static int launch_gp2(const rr_plan* pl, const float* X, const float* err, int r
 }
 
 // ---- gradient pass from a kept feature image ----------------------------------------
+// Keeping pays while ONE persistent launch over all rows keeps its operand panels in
+// L2: the CTA pairs of a long launch drift apart, and then the ~17 panels (Dk x 512
+// bytes each) their tiles touch must fit as a whole.  Measured at 1.25e6 rows
+// (gpurun_out/final_r02z.log): K = 512 kept 14.1 ms / regenerated 15.2 ms per
+// evaluation, K = 2048 100 / 100-108, K = 4096 425 / 405, K = 8192 1823 / 1663 -- past
+// ~6000 columns the chunked pass (which restarts its pairs in step every 320 MB of
+// Phi) is the faster one, and the generator's extra output no longer pays.
+constexpr int G2_KEEP_MAX_COLS = 6144;
 int64_t kept_features_cols(const rr_plan* pl) { return gp_dk(pl); }
 size_t kept_features_bytes(const rr_plan* pl, int64_t N) {
   if (!tc_gradpass_supported(pl) || !tc3_suffstats_supported(pl) || N <= 0) return 0;
+  if (gp_dk(pl) > G2_KEEP_MAX_COLS) return 0;
   return (size_t)((N + G2_TM - 1) / G2_TM) * (size_t)gp_dk(pl) * 512;
 }
 size_t tc_gradpass_kept_workspace(const rr_plan* pl, int64_t N) {
