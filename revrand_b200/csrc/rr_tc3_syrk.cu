@@ -251,10 +251,13 @@ constexpr int T3_PARTS = T3_EXACT ? 3 : 2;
 // internal features] = one 32 KB SWIZZLE_128B image; internal order = blocks of
 // [64 cos | 64 sin] per 64 frequencies, then the affine columns), so that the
 // gradient pass of the same evaluation does not have to evaluate the feature map a
-// second time.  A trigonometric block owns 64 rows x 4 k blocks of that image: it
-// stages them in shared memory in their final byte order and writes them out as four
-// contiguous 8 KB runs.
-constexpr int T3_KEEP_BYTES = 4 * S3_KB * 128;    // staging: 4 k blocks x 64 rows x 128 B
+// second time.  A trigonometric block owns 64 rows x 4 k blocks of that image.  It
+// stages first its cosines, then its sines (two k blocks = 16 KB each time) in
+// shared memory in their final byte order and writes them out as contiguous 8 KB
+// runs.  The staging area ALIASES the input slab (dead after the projection): with
+// 16 KB of shared memory the block still fits next to a resident GEMM CTA (197 KB of
+// the SM's 228 KB), which is what lets generation overlap the tensor-core work.
+constexpr int T3_KEEP_BYTES = 2 * S3_KB * 128;    // staging: 2 k blocks x 64 rows x 128 B
 
 template <bool KEEP>
 __global__ void __launch_bounds__(256, 2)
@@ -268,17 +271,11 @@ t3_digits_kernel(rr_plan plan, const float* __restrict__ X, const float* __restr
   float* xh = xs;
   float* xm = xs + S3_KB * stride;
   float* xl = xs + (T3_PARTS - 1) * S3_KB * stride;    // EXACT only (aliases xm otherwise)
-  // KEEP: staging area behind the slab (16-byte aligned: stride is a multiple of 4)
-  uint8_t* stage = reinterpret_cast<uint8_t*>(xs + T3_PARTS * S3_KB * stride);
+  uint8_t* stage = reinterpret_cast<uint8_t*>(xs);      // KEEP: aliases the slab
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int64_t kb = blockIdx.x;
   const int64_t n0 = kb * S3_KB;
   const bool trig = (int)blockIdx.y < gy_trig;
-  if (KEEP && trig) {
-    // frequencies past ktot and rows past the end stay zero in the image
-    uint4* z = reinterpret_cast<uint4*>(stage);
-    for (int e = tid; e < T3_KEEP_BYTES / 16; e += 256) z[e] = make_uint4(0u, 0u, 0u, 0u);
-  }
   for (int e = tid; e < S3_KB * kp; e += 256) {
     const int r = e / kp, i = e - r * kp;
     const float x = (i < d && n0 + r < rows) ? X[(n0 + r) * d + i] : 0.0f;
@@ -365,14 +362,13 @@ t3_digits_kernel(rr_plan plan, const float* __restrict__ X, const float* __restr
   const int g = lane >> 2, q = lane & 3;
   const int f0 = (int)blockIdx.y * T3_FREQS + 16 * warp;     // first frequency of this warp
   if (!KEEP && f0 >= ktot) return;
-  if (f0 < ktot) {
   const int fA = f0 + g, fB = f0 + g + 8;
   float acc[8][4];
 #pragma unroll
   for (int nt = 0; nt < 8; ++nt)
 #pragma unroll
     for (int j = 0; j < 4; ++j) acc[nt][j] = 0.0f;
-  for (int ks = 0; ks < kp; ks += 8) {
+  for (int ks = 0; ks < kp && f0 < ktot; ks += 8) {
     // A fragment (frequencies x input dimensions): a0 (g, q), a1 (g+8, q), a2 (g, q+4), a3 (g+8, q+4)
     uint32_t ah[4], am[4], al[4];
 #pragma unroll
@@ -404,47 +400,75 @@ t3_digits_kernel(rr_plan plan, const float* __restrict__ X, const float* __restr
       t3_mma_tf32(acc[nt], ah, bh0, bh1);
     }
   }
+  if (KEEP) __syncthreads();      // every warp is done with the slab: staging may overwrite it
+  __half2 skeep[2][8];            // KEEP: this lane's sines, until the cosines have left
   // accumulator fragment: c0 (g, 2q), c1 (g, 2q+1), c2 (g+8, 2q), c3 (g+8, 2q+1) of row tile nt
 #pragma unroll
   for (int h = 0; h < 2; ++h) {
     const int k = h ? fB : fA;
-    if (k >= ktot) continue;
+    const bool valid = k < ktot;
+    if (!KEEP && !valid) continue;
     int kc[16], ksn[16];
     // KEEP: local frequency fl -> k block pair fl >> 6, 16-byte chunk (fl & 63) >> 3,
-    // element g inside the chunk (16 warp + 8 h is a multiple of 8)
+    // element g inside the chunk (16 warp + 8 h is a multiple of 8).  Every (row,
+    // frequency) slot of the staging area has exactly one owner, valid or not, so
+    // frequencies past ktot and rows past the end are written as zeros.
     const int fl = 16 * warp + 8 * h + g;
-    uint8_t* kcos = stage + (2 * (fl >> 6)) * (S3_KB * 128) + 2 * g;
+    uint8_t* kcos = stage + (fl >> 6) * (S3_KB * 128) + 2 * g;
     const uint32_t kchunk = (uint32_t)((fl & 63) >> 3);
+    float sprev = 0.0f;
 #pragma unroll
     for (int b = 0; b < 16; ++b) {
-      float sv, cv;
-      t3_sincos_turns(acc[b >> 1][2 * h + (b & 1)], sv, cv);
+      float sv = 0.0f, cv = 0.0f;
       const int r = t3_row_of(q, b);
-      const bool live = n0 + r < rows;
-      kc[b] = t3_quant(live ? cv : 0.0f);
-      ksn[b] = t3_quant(live ? sv : 0.0f);
+      const bool live = valid && n0 + r < rows;
+      if (live) t3_sincos_turns(acc[b >> 1][2 * h + (b & 1)], sv, cv);
+      kc[b] = t3_quant(cv);
+      ksn[b] = t3_quant(sv);
       if (KEEP) {
         // (q differs -> r & 7 differs -> four distinct chunks: conflict-free)
-        uint8_t* a = kcos + r * 128 + ((kchunk ^ (uint32_t)(r & 7)) << 4);
-        *reinterpret_cast<__half*>(a) = __float2half_rn(live ? cv : 0.0f);
-        *reinterpret_cast<__half*>(a + S3_KB * 128) = __float2half_rn(live ? sv : 0.0f);
+        *reinterpret_cast<__half*>(kcos + r * 128 + ((kchunk ^ (uint32_t)(r & 7)) << 4)) =
+            __float2half_rn(cv);
+        if (b & 1) skeep[h][b >> 1] = __floats2half2_rn(sprev, sv);
+        sprev = sv;
       }
     }
-    const int fc = plan.col_cos[k], fs = plan.col_sin[k];
-    if (fc >= 0) t3_emit(img, kb, Fp, fc, q, kc);
-    if (fs >= 0) t3_emit(img, kb, Fp, fs, q, ksn);
-  }
+    if (valid) {
+      const int fc = plan.col_cos[k], fs = plan.col_sin[k];
+      if (fc >= 0) t3_emit(img, kb, Fp, fc, q, kc);
+      if (fs >= 0) t3_emit(img, kb, Fp, fs, q, ksn);
+    }
   }
   if (KEEP) {
-    __syncthreads();
-    // four contiguous 8 KB runs: rows n0 .. n0+63 of k blocks 4 y .. 4 y + 3
+    // rows n0 .. n0+63 of k blocks 4 y (cos, frequencies 0..63 of the block), 4 y + 1
+    // (their sines), 4 y + 2, 4 y + 3 (frequencies 64..127): one contiguous 8 KB run each
     uint8_t* dst = phi16 + ((int64_t)(n0 >> 8) * nkb16 + 4 * (int)blockIdx.y) * 32768 +
                    (int64_t)(n0 & 255) * 128;
     const uint4* src = reinterpret_cast<const uint4*>(stage);
 #pragma unroll
-    for (int i = 0; i < T3_KEEP_BYTES / 16 / 256; ++i) {
-      const int e = i * 256 + tid;
-      *reinterpret_cast<uint4*>(dst + (int64_t)(e >> 9) * 32768 + (e & 511) * 16) = src[e];
+    for (int part = 0; part < 2; ++part) {       // 0: cosines, 1: sines
+      if (part == 1) {
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          const int fl = 16 * warp + 8 * h + g;
+          uint8_t* ksin = stage + (fl >> 6) * (S3_KB * 128) + 2 * g;
+          const uint32_t kchunk = (uint32_t)((fl & 63) >> 3);
+#pragma unroll
+          for (int b = 0; b < 16; ++b) {
+            const int r = t3_row_of(q, b);
+            *reinterpret_cast<__half*>(ksin + r * 128 + ((kchunk ^ (uint32_t)(r & 7)) << 4)) =
+                (b & 1) ? __high2half(skeep[h][b >> 1]) : __low2half(skeep[h][b >> 1]);
+          }
+        }
+      }
+      __syncthreads();
+#pragma unroll
+      for (int i = 0; i < T3_KEEP_BYTES / 16 / 256; ++i) {
+        const int e = i * 256 + tid;          // pair e >> 9, 16-byte piece e & 511 of its run
+        *reinterpret_cast<uint4*>(dst + (int64_t)(2 * (e >> 9) + part) * 32768 + (e & 511) * 16) =
+            src[e];
+      }
+      if (part == 0) __syncthreads();         // the cosines have left: sines may overwrite them
     }
   }
 }
@@ -762,8 +786,8 @@ static int tc3_groups(const rr_plan* pl, const S3Shape& s, const float* X, const
   const int nother = pl->next + 3 + (s.Fp - (D + 3));
   const int gy_other = (nother + T3_OTHER - 1) / T3_OTHER;
   const int nkb16 = (int)(kept_features_cols(pl) / 64);
-  const size_t dsmem = (size_t)T3_PARTS * S3_KB * (((d + 7) & ~7) + 4) * sizeof(float) +
-                       (phi16 ? T3_KEEP_BYTES : 0);
+  size_t dsmem = (size_t)T3_PARTS * S3_KB * (((d + 7) & ~7) + 4) * sizeof(float);
+  if (phi16 && dsmem < (size_t)T3_KEEP_BYTES) dsmem = T3_KEEP_BYTES;   // staging aliases the slab
   if (dsmem > 48 * 1024)
     RR_CUDA_CHECK(cudaFuncSetAttribute(phi16 ? t3_digits_kernel<true> : t3_digits_kernel<false>,
                                        cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dsmem));
