@@ -110,6 +110,16 @@ typedef enum rr_likelihood {
 #define RR_ENGINE_TCGEN05_FUSED16 4 /* round-1 fused kind::f16 value pass, 2^-5 grid
                                        (kept for A/B measurements) */
 
+#define RR_ENGINE_MASK 0xff
+/* Flag for the gradient pass, OR-ed into `engine` (rr_slm_gradpass, rr_workspace_bytes)
+ * or passed as `flags` (rr_slm_gradpass_kept).  The tensor-core gradient pass multiplies
+ * Phi by an fp16 image of C; its rounding (2^-12 per entry) is harmless where the
+ * quadratic form Phi C dPhi does not cancel (config 2: 1.6e-5 on the gradients), but on
+ * a strongly correlated feature set (64 frequencies on 3-D inputs, cond(C) 3e5) it cost
+ * 1.5e-2.  With this flag a second GEMM over the rounding residual restores C to ~22
+ * bits, at twice the tensor-core work of the pass. */
+#define RR_GRAD_SPLIT_C 0x100
+
 /* Helper stream + events for the passes that overlap generation with tensor-core
  * work (see Conventions).  Created on the current device. */
 typedef struct rr_context rr_context;
@@ -245,7 +255,8 @@ int rr_slm_suffstats_keep(const rr_plan* plan, const float* X, const float* y,
 int rr_slm_gradpass_kept(const rr_plan* plan, const float* X, const float* y,
                          int64_t N, const float* m, const float* C, double* R,
                          double* sqerr, const void* kept, size_t kept_bytes,
-                         void* workspace, size_t workspace_bytes, void* stream);
+                         void* workspace, size_t workspace_bytes, int32_t flags,
+                         void* stream);
 
 /*
  * Predictive moments (slm.py:239-242): Ey = Phi m, Vf = rowsum((Phi C) * Phi).

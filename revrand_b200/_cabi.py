@@ -19,6 +19,7 @@ RR_ENGINE_TCGEN05_FUSED16 = 4
 RR_OP_SUFFSTATS, RR_OP_GRADPASS, RR_OP_PREDICT = 1, 2, 3
 RR_OP_GLM_STEP, RR_OP_GLM_PREDICT, RR_OP_RESIDUAL = 4, 5, 6
 RR_OP_GRADPASS_KEPT = 7
+RR_GRAD_SPLIT_C = 0x100
 (RR_LIK_GAUSSIAN, RR_LIK_BERNOULLI, RR_LIK_BINOMIAL, RR_LIK_POISSON_EXP,
  RR_LIK_POISSON_SOFTPLUS) = range(5)
 
@@ -66,7 +67,7 @@ SIGNATURES = {
     "rr_slm_suffstats_keep": (C.c_int, [_PLAN, _P, _P, _I64, _P, _P, _P, _P, _SZ, _P, _SZ,
                                         _P, _P]),
     "rr_slm_gradpass_kept": (C.c_int, [_PLAN, _P, _P, _I64, _P, _P, _P, _P, _P, _SZ, _P, _SZ,
-                                       _P]),
+                                       _I32, _P]),
     "rr_slm_predict": (C.c_int, [_PLAN, _P, _I64, _P, _P, _P, _P, _P, _SZ, _P]),
     "rr_glm_step": (C.c_int, [_PLAN, _P, _P, _P, _I64, _P, _P, _I32, _P, _I32,
                               _I32, _F32, _P, _P, _P, _P, _P, _P, _SZ, _P]),

@@ -494,15 +494,21 @@ def slm_suffstats_keep(plan, Xd, yd, stats, kept, want_yy=True):
           "rr_slm_suffstats_keep")
 
 
+def _grad_flags():
+    from . import config
+    return _cabi.RR_GRAD_SPLIT_C if config.GRADIENT_SPLIT_C else 0
+
+
 def slm_gradpass_kept(plan, Xd, yd, m32, C32, R, sqerr, kept):
     """Residual + gradient pass from the kept feature image of the same evaluation."""
     lib = _cabi.load()
     N = Xd.shape[0]
-    ws = workspace(_ws_bytes(_cabi.RR_OP_GRADPASS_KEPT, N, plan))
+    flags = _grad_flags()
+    ws = workspace(_ws_bytes(_cabi.RR_OP_GRADPASS_KEPT, N, plan, engine=flags))
     check(lib.rr_slm_gradpass_kept(C.byref(plan.struct), _ptr(Xd), _ptr(yd), N,
                                    _ptr(m32), _ptr(C32), _ptr(R), _ptr(sqerr),
                                    _ptr(kept), kept.numel(), _ptr(ws), ws.numel(),
-                                   _stream_ptr()), "rr_slm_gradpass_kept")
+                                   flags, _stream_ptr()), "rr_slm_gradpass_kept")
 
 
 def slm_residual(plan, Xd, yd, m32, err=None, sqerr=None):
@@ -523,6 +529,7 @@ def slm_gradpass(plan, Xd, yd, m32, C32, R, sqerr,
     """Residual + gradient pass: sqerr += sum (y - Phi m)^2, R += X^T Q."""
     lib = _cabi.load()
     N = Xd.shape[0]
+    engine = engine | _grad_flags()
     nb = _ws_bytes(_cabi.RR_OP_GRADPASS, N, plan, engine=engine)
     ws = workspace(nb)
     check(lib.rr_slm_gradpass(C.byref(plan.struct), _ptr(Xd), _ptr(yd), N,

@@ -70,3 +70,11 @@ GLM_DEVICE_STARTS = os.environ.get("REVRAND_B200_GLM_DEVICE_STARTS", "1") != "0"
 # half of the free memory, and the gradient pass regenerates Phi in row chunks.
 KEEP_FEATURES_MAX_BYTES = int(float(os.environ.get("REVRAND_B200_KEEP_FEATURES_MAX_GB", "64"))
                               * (1 << 30))
+
+# The tensor-core gradient pass multiplies Phi by an fp16 image of the posterior
+# covariance C.  Its rounding is harmless where the quadratic form Phi C dPhi does
+# not cancel (config 2: 1.6e-5 on the lengthscale gradients) but reached 1.5e-2 on a
+# strongly correlated feature set (64 frequencies on 3-D inputs, cond(C) = 3e5).
+# True: a second GEMM over the rounding residual of C (RR_GRAD_SPLIT_C) restores C
+# to ~22 bits, at twice the tensor-core work of the gradient pass.
+GRADIENT_SPLIT_C = os.environ.get("REVRAND_B200_GRADIENT_SPLIT_C", "0") == "1"

@@ -140,15 +140,17 @@ int tc3_suffstats(const rr_plan* plan, const float* X, const float* y, int64_t N
 // the image (a multiple of 64) and its size in bytes for N rows.
 int64_t kept_features_cols(const rr_plan* plan);
 size_t kept_features_bytes(const rr_plan* plan, int64_t N);
-size_t tc_gradpass_kept_workspace(const rr_plan* plan, int64_t N);
+size_t tc_gradpass_kept_workspace(const rr_plan* plan, int64_t N, bool split_c);
 int tc_gradpass_kept(const rr_plan* plan, const float* X, const float* y, int64_t N,
                      const float* m, const float* C, double* R, double* sqerr,
-                     const void* kept, void* ws, size_t ws_bytes, cudaStream_t st);
-size_t tc_gradpass_workspace(const rr_plan* plan, int64_t N);
+                     const void* kept, void* ws, size_t ws_bytes, bool split_c,
+                     cudaStream_t st);
+// split_c: a second GEMM over the fp16 rounding residual of C (RR_GRAD_SPLIT_C)
+size_t tc_gradpass_workspace(const rr_plan* plan, int64_t N, bool split_c);
 int tc_gradpass_supported(const rr_plan* plan);
 int tc_gradpass(const rr_plan* plan, const float* X, const float* y, int64_t N,
                 const float* m, const float* C, double* R, double* sqerr, void* ws,
-                size_t ws_bytes, rr_context* ctx, cudaStream_t st);
+                size_t ws_bytes, rr_context* ctx, bool split_c, cudaStream_t st);
 int phi_residual(const rr_plan* plan, const float* X, const float* y, int64_t N,
                  const float* m, float* err, double* sqerr, float* fbuf,
                  cudaStream_t st);

@@ -15,6 +15,7 @@ constexpr int64_t SIMT_CHUNK = 8192;  // rows of Phi held in the workspace
 // 0 = SIMT, -1 = a tensor-core engine was demanded but cannot run this plan.
 // Gradient pass: 1 = tcgen05 (rr_tc_gradpass.cu), 0 = SIMT, -1 as above.
 static int pick_engine(int engine, const rr_plan* plan, int64_t N, bool grad = false) {
+  engine &= RR_ENGINE_MASK;
   if (engine == RR_ENGINE_SIMT) return 0;
   if (grad) {
     const bool ok = tc_gradpass_supported(plan) != 0;
@@ -236,7 +237,8 @@ extern "C" int rr_slm_suffstats_keep(const rr_plan* plan, const float* X, const 
 extern "C" int rr_slm_gradpass_kept(const rr_plan* plan, const float* X, const float* y,
                                     int64_t N, const float* m, const float* C, double* R,
                                     double* sqerr, const void* kept, size_t kept_bytes,
-                                    void* workspace, size_t workspace_bytes, void* stream) {
+                                    void* workspace, size_t workspace_bytes, int32_t flags,
+                                    void* stream) {
   RR_REQUIRE(plan && X && y && m && C && R && sqerr && kept, "null pointer");
   RR_REQUIRE(N > 0, "no rows");
   const size_t need = kept_features_bytes(plan, N);
@@ -246,7 +248,7 @@ extern "C" int rr_slm_gradpass_kept(const rr_plan* plan, const float* X, const f
   }
   RR_REQUIRE(kept_bytes >= need, "kept feature buffer too small (rr_slm_kept_features_bytes)");
   return tc_gradpass_kept(plan, X, y, N, m, C, R, sqerr, kept, workspace, workspace_bytes,
-                          (cudaStream_t)stream);
+                          (flags & RR_GRAD_SPLIT_C) != 0, (cudaStream_t)stream);
 }
 
 extern "C" int rr_slm_residual(const rr_plan* plan, const float* X,
@@ -281,7 +283,8 @@ extern "C" int rr_slm_gradpass(const rr_plan* plan, const float* X,
     return RR_ERR_UNSUPPORTED;
   }
   if (use_tc)
-    return tc_gradpass(plan, X, y, N, m, C, R, sqerr, workspace, workspace_bytes, ctx, st);
+    return tc_gradpass(plan, X, y, N, m, C, R, sqerr, workspace, workspace_bytes, ctx,
+                       (engine & RR_GRAD_SPLIT_C) != 0, st);
   return simt_gradpass(plan, X, y, N, m, C, R, sqerr, workspace, workspace_bytes, st);
 }
 
@@ -328,12 +331,13 @@ extern "C" int rr_slm_predict(const rr_plan* plan, const float* X, int64_t N,
 
 namespace rr {
 size_t slm_workspace_bytes(int op, int64_t N, const rr_plan* pl, int engine) {
-  if (op == RR_OP_GRADPASS_KEPT) return tc_gradpass_kept_workspace(pl, N);
+  const bool split_c = (engine & RR_GRAD_SPLIT_C) != 0;
+  if (op == RR_OP_GRADPASS_KEPT) return tc_gradpass_kept_workspace(pl, N, split_c);
   size_t s = simt_ws(op, N, pl);
   if (op != RR_OP_PREDICT && op != RR_OP_RESIDUAL) {
     const int e = pick_engine(engine, pl, N, op == RR_OP_GRADPASS);
     if (e > 0) {
-      size_t t = op == RR_OP_GRADPASS ? tc_gradpass_workspace(pl, N)
+      size_t t = op == RR_OP_GRADPASS ? tc_gradpass_workspace(pl, N, split_c)
                  : (e == 1 ? tc3_suffstats_workspace(pl, N) : tc_suffstats_workspace(pl, N));
       return t > 256 ? t : 256;
     }

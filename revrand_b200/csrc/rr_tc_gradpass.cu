@@ -77,9 +77,13 @@ __global__ void absmax_kernel(const float* __restrict__ C, int64_t n,
 // Rows fo: the Dp (padded) trigonometric output features; columns fj: all Dk
 // reduction features = the trigonometric ones followed by the affine columns
 // (Linear / Bias bases, amplitude 1) padded to a multiple of 64.
+// part 1 (RR_GRAD_SPLIT_C): what fp16 rounding removed from the same entry, scaled up
+// by G2_LO_SCALE into fp16's normal range -- a second GEMM over it restores C to ~22
+// bits (the lengthscale gradients are linear in C).
+constexpr float G2_LO_SCALE = 2048.0f;
 __global__ void __launch_bounds__(256)
 prep_c_kernel(rr_plan plan, const float* __restrict__ C, int Dp, int Dk,
-              const unsigned int* __restrict__ cmax_bits, uint8_t* __restrict__ BtT) {
+              const unsigned int* __restrict__ cmax_bits, uint8_t* __restrict__ BtT, int part) {
   const int fj = blockIdx.x * blockDim.x + threadIdx.x;
   const int fo = blockIdx.y;
   if (fj >= Dk) return;
@@ -99,7 +103,9 @@ prep_c_kernel(rr_plan plan, const float* __restrict__ C, int Dp, int Dk,
       v = s * C[(int64_t)co * plan.D + plan.ext_col[fj - Dp]];
     }
   }
-  *reinterpret_cast<__half*>(BtT + tile_off(fo, fj, Dk / G2_KT)) = __float2half_rn(v);
+  __half hv = __float2half_rn(v);
+  if (part == 1) hv = __float2half_rn((v - __half2float(hv)) * G2_LO_SCALE);
+  *reinterpret_cast<__half*>(BtT + tile_off(fo, fj, Dk / G2_KT)) = hv;
 }
 
 // ---- Phi chunk + fitted values --------------------------------------------------
@@ -386,7 +392,7 @@ __global__ void __launch_bounds__(G2_THREADS, 1)
 gp2_kernel(rr_plan plan, const float* __restrict__ X, const float* __restrict__ err,
            int rows, int RB, int FB, int nkb, const uint8_t* __restrict__ PhT,
            const uint8_t* __restrict__ BtT, const float* __restrict__ m,
-           const unsigned int* __restrict__ cmax_bits, double* __restrict__ R) {
+           const unsigned int* __restrict__ cmax_bits, float cscale, double* __restrict__ R) {
   constexpr int DPAD = 4 * IG;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>(
@@ -490,7 +496,8 @@ gp2_kernel(rr_plan plan, const float* __restrict__ X, const float* __restrict__ 
     const int q = warp & 3;               // TMEM lane quadrant this warp may read
     const int rl = 32 * q + lane;         // accumulator lane = row inside this CTA's half
     const int ew = warp - 2;              // which group of input dims this warp reduces
-    const float cmax = __uint_as_float(*cmax_bits);
+    // (err == NULL, cscale = 1 / G2_LO_SCALE: the correction pass over the low part of C)
+    const float cmax = __uint_as_float(*cmax_bits) * cscale;
     uint32_t it = 0;
     for (int t = pair; t < ntiles; t += npairs, ++it) {
       int rb, fb;
@@ -508,7 +515,7 @@ gp2_kernel(rr_plan plan, const float* __restrict__ X, const float* __restrict__ 
       {
         const int th = fb * (G2_TN / 2) + et;
         amp_loc[et] = th < ktot ? plan.amp[th] : 0.0f;
-        err_loc[et] = (row0 + et < rows) ? err[row0 + et] : 0.0f;
+        err_loc[et] = (err != nullptr && row0 + et < rows) ? err[row0 + et] : 0.0f;
       }
       for (int e = et; e < 128 * DPAD; e += 128) {
         const int r = e / DPAD, i = e - r * DPAD;
@@ -652,16 +659,17 @@ static int gp_chunk_blocks(const rr_plan* pl, int64_t N) {
   return best;
 }
 
-size_t tc_gradpass_workspace(const rr_plan* pl, int64_t N) {
+size_t tc_gradpass_workspace(const rr_plan* pl, int64_t N, bool split_c) {
   const int64_t Dp = gp_dp(pl), Dk = gp_dk(pl);
   return 2 * (align_up((size_t)gp_chunk_blocks(pl, N) * G2_TM * Dk * 2, 1024) + 1024) +
-         align_up((size_t)Dp * Dk * 2, 1024) + align_up((size_t)N * 4, 256) + 8192;
+         (split_c ? 2 : 1) * (align_up((size_t)Dp * Dk * 2, 1024) + 1024 + 256) +
+         align_up((size_t)N * 4, 256) + 8192;
 }
 
 template <int IG>
 static int launch_gp2(const rr_plan* pl, const float* X, const float* err, int rows,
                       int RB, int FB, int nkb, const uint8_t* PhT, const uint8_t* BtT,
-                      const float* m, const unsigned int* cmax, double* R,
+                      const float* m, const unsigned int* cmax, float cscale, double* R,
                       cudaStream_t st) {
   const size_t smem = (size_t)G2_STAGES * G2_STAGE_BYTES + 2 * G2_RED * 4 +
                       128 * 4 * IG * 4 + 1024;
@@ -682,9 +690,20 @@ static int launch_gp2(const rr_plan* pl, const float* X, const float* err, int r
   cfg.attrs = attr;
   cfg.numAttrs = 1;
   RR_CUDA_CHECK(cudaLaunchKernelEx(&cfg, gp2_kernel<IG>, *pl, X, err, rows, RB, FB, nkb, PhT, BtT,
-                                   m, cmax, R));
+                                   m, cmax, cscale, R));
   RR_LAUNCH_CHECK("gp2_kernel");
   return RR_OK;
+}
+
+static int launch_gp2_d(const rr_plan* pl, const float* X, const float* err, int rows, int RB,
+                        int FB, int nkb, const uint8_t* PhT, const uint8_t* BtT, const float* m,
+                        const unsigned int* cmax, float cscale, double* R, cudaStream_t st) {
+  const int d = pl->d;
+  if (d <= 4) return launch_gp2<1>(pl, X, err, rows, RB, FB, nkb, PhT, BtT, m, cmax, cscale, R, st);
+  if (d <= 8) return launch_gp2<2>(pl, X, err, rows, RB, FB, nkb, PhT, BtT, m, cmax, cscale, R, st);
+  if (d <= 16) return launch_gp2<4>(pl, X, err, rows, RB, FB, nkb, PhT, BtT, m, cmax, cscale, R, st);
+  if (d <= 24) return launch_gp2<6>(pl, X, err, rows, RB, FB, nkb, PhT, BtT, m, cmax, cscale, R, st);
+  return launch_gp2<8>(pl, X, err, rows, RB, FB, nkb, PhT, BtT, m, cmax, cscale, R, st);
 }
 
 // ---- gradient pass from a kept feature image ----------------------------------------
@@ -702,10 +721,10 @@ size_t kept_features_bytes(const rr_plan* pl, int64_t N) {
   if (gp_dk(pl) > G2_KEEP_MAX_COLS) return 0;
   return (size_t)((N + G2_TM - 1) / G2_TM) * (size_t)gp_dk(pl) * 512;
 }
-size_t tc_gradpass_kept_workspace(const rr_plan* pl, int64_t N) {
+size_t tc_gradpass_kept_workspace(const rr_plan* pl, int64_t N, bool split_c) {
   const int64_t Dp = gp_dp(pl), Dk = gp_dk(pl);
-  return align_up((size_t)Dp * Dk * 2, 1024) + 1024 + align_up((size_t)N * 4, 256) +
-         align_up((size_t)Dk * 4, 256) + 8192;
+  return (split_c ? 2 : 1) * (align_up((size_t)Dp * Dk * 2, 1024) + 1024 + 256) +
+         align_up((size_t)N * 4, 256) + align_up((size_t)Dk * 4, 256) + 8192;
 }
 
 // The value pass of the same evaluation left Phi behind (tc3_suffstats, kept != NULL):
@@ -713,7 +732,7 @@ size_t tc_gradpass_kept_workspace(const rr_plan* pl, int64_t N) {
 // all rows -- no second evaluation of the feature map, no per-chunk launches.
 int tc_gradpass_kept(const rr_plan* pl, const float* X, const float* y, int64_t N,
                      const float* m, const float* C, double* R, double* sqerr,
-                     const void* kept, void* ws, size_t wsb, cudaStream_t st) {
+                     const void* kept, void* ws, size_t wsb, bool split_c, cudaStream_t st) {
   const int Dp = gp_dp(pl), Dk = gp_dk(pl), FB = Dp / G2_TN, nkb = Dk / G2_KT;
   const uint8_t* PhT = static_cast<const uint8_t*>(kept);
   if (N >= ((int64_t)1 << 31) - 256 || (reinterpret_cast<uintptr_t>(PhT) & 1023) != 0) {
@@ -722,15 +741,17 @@ int tc_gradpass_kept(const rr_plan* pl, const float* X, const float* y, int64_t 
   }
   Workspace W(ws, wsb);
   uint8_t* BtT = W.take<uint8_t>(align_up((size_t)Dp * Dk * 2, 1024) + 1024);
+  uint8_t* BtL = split_c ? W.take<uint8_t>(align_up((size_t)Dp * Dk * 2, 1024) + 1024) : nullptr;
   float* err = W.take<float>((size_t)N);
   float* mi = W.take<float>((size_t)Dk);
   unsigned int* cmax = W.take<unsigned int>(1);
-  if (!BtT || !err || !mi || !cmax) {
+  if (!BtT || (split_c && !BtL) || !err || !mi || !cmax) {
     set_error("kept gradient pass workspace too small (need %zu bytes)",
-              tc_gradpass_kept_workspace(pl, N));
+              tc_gradpass_kept_workspace(pl, N, split_c));
     return RR_ERR_WORKSPACE;
   }
   BtT = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(BtT) + 1023) & ~(uintptr_t)1023);
+  if (BtL) BtL = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(BtL) + 1023) & ~(uintptr_t)1023);
   RR_CUDA_CHECK(cudaMemsetAsync(cmax, 0, sizeof(unsigned int), st));
   mint_kernel<<<(Dk + 255) / 256, 256, 0, st>>>(*pl, m, Dp, Dk, mi);
   RR_LAUNCH_CHECK("mint_kernel");
@@ -751,15 +772,17 @@ int tc_gradpass_kept(const rr_plan* pl, const float* X, const float* y, int64_t 
   RR_LAUNCH_CHECK("absmax_kernel");
   {
     dim3 grid((Dk + 255) / 256, Dp);
-    prep_c_kernel<<<grid, 256, 0, st>>>(*pl, C, Dp, Dk, cmax, BtT);
+    prep_c_kernel<<<grid, 256, 0, st>>>(*pl, C, Dp, Dk, cmax, BtT, 0);
     RR_LAUNCH_CHECK("prep_c_kernel");
+    if (split_c) {
+      prep_c_kernel<<<grid, 256, 0, st>>>(*pl, C, Dp, Dk, cmax, BtL, 1);
+      RR_LAUNCH_CHECK("prep_c_kernel");
+    }
   }
-  const int d = pl->d, rows = (int)N;
-  if (d <= 4) return launch_gp2<1>(pl, X, err, rows, RB, FB, nkb, PhT, BtT, m, cmax, R, st);
-  if (d <= 8) return launch_gp2<2>(pl, X, err, rows, RB, FB, nkb, PhT, BtT, m, cmax, R, st);
-  if (d <= 16) return launch_gp2<4>(pl, X, err, rows, RB, FB, nkb, PhT, BtT, m, cmax, R, st);
-  if (d <= 24) return launch_gp2<6>(pl, X, err, rows, RB, FB, nkb, PhT, BtT, m, cmax, R, st);
-  return launch_gp2<8>(pl, X, err, rows, RB, FB, nkb, PhT, BtT, m, cmax, R, st);
+  int rc = launch_gp2_d(pl, X, err, (int)N, RB, FB, nkb, PhT, BtT, m, cmax, 1.0f, R, st);
+  if (rc == RR_OK && split_c)
+    rc = launch_gp2_d(pl, X, nullptr, (int)N, RB, FB, nkb, PhT, BtL, m, cmax, 1.0f / G2_LO_SCALE, R, st);
+  return rc;
 }
 
 // Residuals only (value-only evaluations; any feature plan):
@@ -795,7 +818,7 @@ static int join_helper(int rc, bool overlap, cudaStream_t sp, cudaStream_t st, c
 
 int tc_gradpass(const rr_plan* pl, const float* X, const float* y, int64_t N,
                 const float* m, const float* C, double* R, double* sqerr, void* ws,
-                size_t wsb, rr_context* ctx, cudaStream_t st) {
+                size_t wsb, rr_context* ctx, bool split_c, cudaStream_t st) {
   const int Dp = gp_dp(pl), Dk = gp_dk(pl), FB = Dp / G2_TN, nkb = Dk / G2_KT;
   const int RBc = gp_chunk_blocks(pl, N);
   const int64_t RC = (int64_t)RBc * G2_TM;
@@ -804,17 +827,19 @@ int tc_gradpass(const rr_plan* pl, const float* X, const float* y, int64_t N,
   PhTb[0] = W.take<uint8_t>(align_up((size_t)RC * Dk * 2, 1024) + 1024);
   PhTb[1] = W.take<uint8_t>(align_up((size_t)RC * Dk * 2, 1024) + 1024);
   uint8_t* BtT = W.take<uint8_t>(align_up((size_t)Dp * Dk * 2, 1024) + 1024);
+  uint8_t* BtL = split_c ? W.take<uint8_t>(align_up((size_t)Dp * Dk * 2, 1024) + 1024) : nullptr;
   float* err = W.take<float>((size_t)N);      // fitted values, then residuals
   unsigned int* cmax = W.take<unsigned int>(1);
   cudaStream_t sp = st;                                                   // Phi stream
   cudaEvent_t ev_fork = nullptr, ev_phi[2] = {nullptr, nullptr}, ev_gemm[2] = {nullptr, nullptr};
   if (ctx_aux(ctx, &sp, &ev_fork, ev_phi, ev_gemm) != RR_OK) return RR_ERR_CUDA;
   const bool overlap = sp != st;
-  if (!PhTb[0] || !PhTb[1] || !BtT || !err || !cmax) {
+  if (!PhTb[0] || !PhTb[1] || !BtT || (split_c && !BtL) || !err || !cmax) {
     set_error("tcgen05 gradpass workspace too small (need %zu bytes)",
-              tc_gradpass_workspace(pl, N));
+              tc_gradpass_workspace(pl, N, split_c));
     return RR_ERR_WORKSPACE;
   }
+  if (BtL) BtL = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(BtL) + 1023) & ~(uintptr_t)1023);
   // the bulk copies need 16-byte aligned images
   for (int i = 0; i < 2; ++i)
     PhTb[i] = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(PhTb[i]) + 1023) & ~(uintptr_t)1023);
@@ -829,8 +854,12 @@ int tc_gradpass(const rr_plan* pl, const float* X, const float* y, int64_t N,
   RR_LAUNCH_CHECK("absmax_kernel");
   {
     dim3 grid((Dk + 255) / 256, Dp);
-    prep_c_kernel<<<grid, 256, 0, st>>>(*pl, C, Dp, Dk, cmax, BtT);
+    prep_c_kernel<<<grid, 256, 0, st>>>(*pl, C, Dp, Dk, cmax, BtT, 0);
     RR_LAUNCH_CHECK("prep_c_kernel");
+    if (split_c) {
+      prep_c_kernel<<<grid, 256, 0, st>>>(*pl, C, Dp, Dk, cmax, BtL, 1);
+      RR_LAUNCH_CHECK("prep_c_kernel");
+    }
   }
   const int d = pl->d;
   int c = 0;
@@ -855,11 +884,9 @@ int tc_gradpass(const rr_plan* pl, const float* X, const float* y, int64_t N,
     }
     const float* Xc = X + s * d;
     const float* ec = err + s;
-    if (d <= 4) rc = launch_gp2<1>(pl, Xc, ec, rows, RB, FB, nkb, PhT, BtT, m, cmax, R, st);
-    else if (d <= 8) rc = launch_gp2<2>(pl, Xc, ec, rows, RB, FB, nkb, PhT, BtT, m, cmax, R, st);
-    else if (d <= 16) rc = launch_gp2<4>(pl, Xc, ec, rows, RB, FB, nkb, PhT, BtT, m, cmax, R, st);
-    else if (d <= 24) rc = launch_gp2<6>(pl, Xc, ec, rows, RB, FB, nkb, PhT, BtT, m, cmax, R, st);
-    else rc = launch_gp2<8>(pl, Xc, ec, rows, RB, FB, nkb, PhT, BtT, m, cmax, R, st);
+    rc = launch_gp2_d(pl, Xc, ec, rows, RB, FB, nkb, PhT, BtT, m, cmax, 1.0f, R, st);
+    if (rc == RR_OK && split_c)
+      rc = launch_gp2_d(pl, Xc, nullptr, rows, RB, FB, nkb, PhT, BtL, m, cmax, 1.0f / G2_LO_SCALE, R, st);
     if (rc) return join_helper(rc, overlap, sp, st, ev_fork);
     if (overlap) RR_CUDA_CHECK(cudaEventRecord(ev_gemm[buf], st));
   }

@@ -979,3 +979,35 @@ def test_kept_feature_image_equals_regenerated_features(N, d, K, linear):
         config.ENGINE = old_engine
     assert abs(nelbo - ref["neg_elbo"]) <= 1e-4 * abs(ref["neg_elbo"])
     assert relerr(dl, ref["dhyp"][0]) < 5e-3
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("keep", [True, False])
+def test_gradient_pass_with_split_covariance_on_correlated_features(keep):
+    """64 frequencies on 3-D inputs with long lengthscales: a strongly correlated
+    feature set (cond(C) = 3e5) on which the quadratic form Phi C dPhi cancels, so the
+    fp16 rounding of C in the tensor-core gradient pass shows (1.5e-2 in an emulation
+    on the host, oracle in float64).  RR_GRAD_SPLIT_C (config.GRADIENT_SPLIT_C) adds a
+    GEMM over the rounding residual and must bring the gradients back under 1e-3."""
+    N, d, K = 16384, 3, 64
+    X, y = _synthetic(N, d, seed=17)
+    ls = 2.5 * (1.0 + 0.07 * np.arange(d))
+    rbf = bf.RandomRBF(nbases=K, Xdim=d, random_state=8, lenscale=Parameter(ls, Positive()),
+                       regularizer=Parameter(1.3, Positive()))
+    ref = orc.slm_elbo(X, y, 0.05, [1.3], [dict(kind="trig", W=rbf.W, lenscale=ls, cols=None)])
+    errs = {}
+    old = config.ENGINE, config.KEEP_FEATURES_MAX_BYTES, config.GRADIENT_SPLIT_C
+    config.ENGINE = "tcgen05"
+    config.KEEP_FEATURES_MAX_BYTES = (1 << 40) if keep else 0
+    try:
+        for split in (False, True):
+            config.GRADIENT_SPLIT_C = split
+            slm = rr.StandardLinearModel(basis=rbf)
+            slm.obj_ = -np.inf
+            _, (dv, dr, dl) = slm._elbo(X, y, 0.05, 1.3, ls)
+            assert (slm._cached_problem._kept is not None) == keep
+            errs[split] = relerr(dl, ref["dhyp"][0])
+    finally:
+        config.ENGINE, config.KEEP_FEATURES_MAX_BYTES, config.GRADIENT_SPLIT_C = old
+    assert errs[True] < 1e-3, errs
+    assert errs[True] < 0.2 * errs[False], errs
