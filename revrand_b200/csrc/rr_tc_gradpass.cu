@@ -372,25 +372,28 @@ struct G2Bars {
 };
 
 // Tile order.  Tile t of the launch -> (row block rb, output-feature block fb), visited
-// in supertiles of G2_SUPER row blocks x all FB feature blocks with the row block
-// fastest: the ~74 tiles in flight at any time then touch ~G2_SUPER row panels of Phi
-// and ~74 / G2_SUPER panels of the C image instead of 2 and all FB -- for K >= 4096 the
-// C image (135 MB at K = 4096) no longer fits in L2, and with the feature block fastest
-// every row block streamed all of it from HBM.
-constexpr int G2_SUPER = 8;
-__device__ __forceinline__ void g2_tile(int t, int RB, int FB, int& rb, int& fb) {
-  const int per = G2_SUPER * FB;
+// in supertiles of `sup` row blocks x all FB feature blocks with the row block fastest.
+// sup = 1 (feature block fastest) while the fp16 image of C fits in L2 next to a few
+// row panels of Phi (32 MB at K = 2048: every panel of Phi is then read from HBM exactly
+// once, 8.5 GB per pass under ncu; with sup = 8 it was 19 GB and 5 % slower).  For
+// K >= 4096 the C image (135 MB) does not fit, and with the feature block fastest every
+// row block streamed all of it from HBM: sup = 8 lets the ~74 tiles in flight share
+// ~8 row panels and ~9 panels of C (gradient pass at K = 4096, 1.25e6 rows: 140 -> 130 ms).
+constexpr int G2_SUPER_BIG = 8;
+constexpr size_t G2_C_IMAGE_L2_BYTES = (size_t)48 << 20;
+__device__ __forceinline__ void g2_tile(int t, int RB, int FB, int sup, int& rb, int& fb) {
+  const int per = sup * FB;
   const int s = t / per, tl = t - s * per;
-  const int left = RB - s * G2_SUPER;
-  const int rs = left < G2_SUPER ? left : G2_SUPER;
+  const int left = RB - s * sup;
+  const int rs = left < sup ? left : sup;
   fb = tl / rs;
-  rb = s * G2_SUPER + (tl - fb * rs);
+  rb = s * sup + (tl - fb * rs);
 }
 
 template <int IG>   // input dimensions per reducing warp: d <= 4 * IG
 __global__ void __launch_bounds__(G2_THREADS, 1)
 gp2_kernel(rr_plan plan, const float* __restrict__ X, const float* __restrict__ err,
-           int rows, int RB, int FB, int nkb, const uint8_t* __restrict__ PhT,
+           int rows, int RB, int FB, int sup, int nkb, const uint8_t* __restrict__ PhT,
            const uint8_t* __restrict__ BtT, const float* __restrict__ m,
            const unsigned int* __restrict__ cmax_bits, float cscale, double* __restrict__ R) {
   constexpr int DPAD = 4 * IG;
@@ -436,7 +439,7 @@ gp2_kernel(rr_plan plan, const float* __restrict__ X, const float* __restrict__ 
       uint32_t g = 0;
       for (int t = pair; t < ntiles; t += npairs) {
         int rb, fb;
-        g2_tile(t, RB, FB, rb, fb);
+        g2_tile(t, RB, FB, sup, rb, fb);
         const uint8_t* a_src = PhT + ((int64_t)rb * nkb) * G2_IMG + (int64_t)crank * G2_HALF;
         const uint8_t* b_src = BtT + ((int64_t)fb * nkb) * G2_IMG + (int64_t)crank * G2_HALF;
         for (int kb = 0; kb < nkb; ++kb, ++g) {
@@ -501,7 +504,7 @@ gp2_kernel(rr_plan plan, const float* __restrict__ X, const float* __restrict__ 
     uint32_t it = 0;
     for (int t = pair; t < ntiles; t += npairs, ++it) {
       int rb, fb;
-      g2_tile(t, RB, FB, rb, fb);
+      g2_tile(t, RB, FB, sup, rb, fb);
       const uint32_t buf = it & 1;
       const int row0 = rb * G2_TM + 128 * (int)crank;       // first row of this CTA's half
       // tables for this tile (the previous tile's readers are past their last barrier)
@@ -689,8 +692,9 @@ static int launch_gp2(const rr_plan* pl, const float* X, const float* err, int r
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  RR_CUDA_CHECK(cudaLaunchKernelEx(&cfg, gp2_kernel<IG>, *pl, X, err, rows, RB, FB, nkb, PhT, BtT,
-                                   m, cmax, cscale, R));
+  const int sup = ((size_t)FB * G2_TN * nkb * G2_KT * 2 > G2_C_IMAGE_L2_BYTES) ? G2_SUPER_BIG : 1;
+  RR_CUDA_CHECK(cudaLaunchKernelEx(&cfg, gp2_kernel<IG>, *pl, X, err, rows, RB, FB, sup, nkb, PhT,
+                                   BtT, m, cmax, cscale, R));
   RR_LAUNCH_CHECK("gp2_kernel");
   return RR_OK;
 }
