@@ -342,11 +342,18 @@ class DeviceSVI(object):
             if self.graph is None:
                 g, side = self._capture_pending
                 t.cuda.synchronize()
+                from . import _cabi
+                l0 = _cabi.load().rr_launch_count()
                 with t.cuda.graph(g, stream=side):
                     self._body()
+                # kernels of this library inside one replay (the library's launch
+                # counter only sees the capture)
+                self.graph_launches = int(_cabi.load().rr_launch_count() - l0)
+                self.graph_replays = 0
                 self.graph = g
                 # (capture does not execute: fall through and replay it now)
             self.graph.replay()
+            self.graph_replays += 1
         self._left_in_chunk -= 1
         it = self.it
         self.it += 1

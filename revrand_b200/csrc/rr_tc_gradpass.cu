@@ -6,23 +6,29 @@
 //   R += X^T Q                                                  (d x ktot, float64)
 //
 // dPhi (N x 2K x d in the reference, basis_functions.py:888-901) is never
-// formed, and Phi only ever exists as an fp16 row chunk (up to 320 MB, two
-// ping-pong buffers) in the caller's workspace.  Per row chunk:
+// formed.  Phi reaches the GEMM as a TILE-MAJOR fp16 image: every (256 rows x 64
+// features) block is one contiguous 32 KB image already in the 128-byte-swizzled
+// K-major layout tcgen05 wants, so an operand stage is a single cp.async.bulk.
 //
-//   1. phi_fit_kernel: one pass over the chunk's (row, frequency) pairs on the
-//      CUDA cores: fp32 projection, exact range reduction, MUFU sin/cos.  It
-//      accumulates f = Phi m in fp32 from the very same trig values (so the
-//      residuals cost no extra transcendental work) and writes the fp16 Phi
-//      chunk TILE-MAJOR: every (256 rows x 64 features) block is one contiguous
-//      32 KB image already in the 128-byte-swizzled K-major layout tcgen05
-//      wants, so that the GEMM below loads an operand stage with a single
-//      cp.async.bulk instead of thousands of per-thread copies.
-//   2. gp2_kernel: persistent CTA pairs (cta_group::2, M = 256 rows, N = 256
-//      output features, K = all features) stream those images through a
-//      5-stage bulk-copy ring; accumulators are double-buffered in TMEM
-//      (2 x 256 columns) so that the epilogue of one tile (Q in registers,
-//      X^T Q on the CUDA cores, float64 atomics into R) overlaps the tensor
-//      work of the next.
+//   A. tc_gradpass_kept (rr_slm_gradpass_kept; up to 6144 feature columns): the
+//      value pass of the same evaluation left the whole image behind
+//      (t3_digits_kernel<true>, rr_tc3_syrk.cu) -- the feature map is evaluated once
+//      per evaluation, as at slm.py:145.  mint_kernel + fit16_kernel stream it once
+//      for the residuals (89 % of DRAM peak), then ONE persistent gp2_kernel launch
+//      covers all rows.
+//   B. tc_gradpass (rr_slm_gradpass; large K, or no room for the image): per row
+//      chunk (up to 320 MB, two ping-pong buffers) phi_fit_kernel regenerates the
+//      chunk on the CUDA cores -- fp32 projection, exact range reduction, MUFU
+//      sin/cos -- and accumulates f = Phi m from the same trig values on the
+//      context's helper stream while gp2_kernel works on the previous chunk.
+//
+//   gp2_kernel: persistent CTA pairs (cta_group::2, M = 256 rows, N = 256 output
+//   features, K = all features) stream the images through a 5-stage bulk-copy ring;
+//   accumulators are double-buffered in TMEM (2 x 256 columns) so that the epilogue
+//   of one tile (Q in registers, X^T Q on the CUDA cores, float64 atomics into R)
+//   overlaps the tensor work of the next.  Tiles are visited in supertiles
+//   (g2_tile) sized so that the operand panels in flight stay in L2.
+//   RR_GRAD_SPLIT_C adds a second launch over the fp16 rounding residual of C.
 //
 // Replaces: revrand/slm.py:161-162, 193-197 + basis_functions.py:109-152, 888-901.
 #include <stdlib.h>
