@@ -1011,3 +1011,38 @@ def test_gradient_pass_with_split_covariance_on_correlated_features(keep):
         config.ENGINE, config.KEEP_FEATURES_MAX_BYTES, config.GRADIENT_SPLIT_C = old
     assert errs[True] < 1e-3, errs
     assert errs[True] < 0.2 * errs[False], errs
+
+
+@pytest.mark.gpu
+def test_config5_large_K_ragged_vs_oracle():
+    """Config-5 shape at K = 4096: BasisCat(RandomRBF(4096) + LinearBasis(onescol)),
+    D = 8214 = 4096 * 2 + 22 columns (ragged against every tile size), on a row subsample
+    (N = 16411).  Exercises the 33 x 52 triangular tile set of the int8 value pass, the
+    gradient GEMM in supertile order (the fp16 image of C is 135 MB: larger than L2) on
+    regenerated features (8256 columns are past the kept-image limit), and the blocked
+    float64 inverse at D = 8214, against the float64 oracle."""
+    N, d, K = 16411, 21, 4096
+    X, y = _synthetic(N, d, seed=23)
+    ls = 3.0
+    rbf = bf.RandomRBF(nbases=K, Xdim=d, random_state=5, lenscale=Parameter(ls, Positive()),
+                       regularizer=Parameter(1.3, Positive()))
+    lin = bf.LinearBasis(onescol=True, regularizer=Parameter(2.0, Positive()))
+    old = config.ENGINE
+    config.ENGINE = "tcgen05"
+    try:
+        slm = rr.StandardLinearModel(basis=rbf + lin)
+        slm.obj_ = -np.inf
+        nelbo, (dv, dr, dl) = slm._elbo(X, y, 0.05, [1.3, 2.0], ls)
+        prob = slm._cached_problem
+        assert prob.uses_tcgen05() and prob.D == 2 * K + d + 1 and prob._kept is None
+    finally:
+        config.ENGINE = old
+    blocks = [dict(kind="trig", W=rbf.W, lenscale=np.array([ls]), cols=None),
+              dict(kind="linear", onescol=True, cols=None)]
+    ref = orc.slm_elbo_chunked(X, y, 0.05, [1.3, 2.0], blocks, chunk=4096)
+    assert abs(nelbo - ref["neg_elbo"]) <= 1e-4 * abs(ref["neg_elbo"])
+    assert relerr(slm.weights_, ref["m"]) < 1e-4
+    np.testing.assert_allclose(slm.covariance_.diagonal(), ref["C"].diagonal(), rtol=1e-4)
+    assert abs(dv - ref["dvar"]) <= 1e-4 * abs(ref["dvar"])
+    np.testing.assert_allclose(np.ravel(dr), np.ravel(ref["dreg"]), rtol=1e-4)
+    assert relerr(np.ravel(dl), np.ravel(ref["dhyp"][0])) < 5e-3
