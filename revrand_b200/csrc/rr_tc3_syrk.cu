@@ -486,11 +486,10 @@ struct S3Bars {
 struct S3Item {
   int ib, jb;
   int kb0, nkb;      // K blocks of this chain inside the launch's image
-  int skip, nn;      // leading B columns that lie wholly below the diagonal, and the rest
 };
 
 __device__ __forceinline__ S3Item s3_decode(int item, int ntiles, int NIB, int NJB,
-                                            int nkb_total, int diag_skip) {
+                                            int nkb_total) {
   S3Item it;
   const int chain = item / ntiles;
   int t = item - chain * ntiles;
@@ -502,12 +501,6 @@ __device__ __forceinline__ S3Item s3_decode(int item, int ntiles, int NIB, int N
   }
   it.ib = ib;
   it.jb = s3_jmin(ib) + t;
-  // The first tile of a row panel starts left of the diagonal: its columns
-  // [160 jb, 256 ib) are below it for every row of the panel and are neither loaded
-  // nor multiplied (a multiple of 32 columns: the MMA's N shrinks to 160 - skip).
-  it.skip = diag_skip ? S3_TM * it.ib - S3_TN * it.jb : 0;
-  if (it.skip < 0) it.skip = 0;
-  it.nn = S3_TN - it.skip;
   it.kb0 = chain * S3_CHAIN_KB;
   const int left = nkb_total - it.kb0;
   it.nkb = left < S3_CHAIN_KB ? left : S3_CHAIN_KB;
@@ -518,7 +511,7 @@ __device__ __forceinline__ S3Item s3_decode(int item, int ntiles, int NIB, int N
 // accumulator lanes are 32 consecutive fa).
 __global__ void __launch_bounds__(S3_THREADS, 1)
 t3_syrk_kernel(const uint8_t* __restrict__ img, int Fp, int nkb_total, int D, int NIB, int NJB,
-               int ntiles, int nitems, double* __restrict__ T, int64_t ldT, int diag_skip) {
+               int ntiles, int nitems, double* __restrict__ T, int64_t ldT) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>(
       (reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -551,23 +544,22 @@ t3_syrk_kernel(const uint8_t* __restrict__ img, int Fp, int nkb_total, int D, in
     if (elect_one()) {
       uint32_t g = 0;
       for (int item = pair; item < nitems; item += npairs) {
-        const S3Item it = s3_decode(item, ntiles, NIB, NJB, nkb_total, diag_skip);
+        const S3Item it = s3_decode(item, ntiles, NIB, NJB, nkb_total);
         const uint8_t* a_src = img + ((int64_t)it.kb0 * 3) * plane +
                                (int64_t)(S3_TM * it.ib + (S3_TM / 2) * (int)crank) * 64;
         const uint8_t* b_src = img + ((int64_t)it.kb0 * 3) * plane +
-                               (int64_t)(S3_TN * it.jb + it.skip + (it.nn / 2) * (int)crank) * 64;
-        const uint32_t b_bytes = (uint32_t)(it.nn / 2) * S3_KB;    // this CTA's half of B, one plane
+                               (int64_t)(S3_TN * it.jb + (S3_TN / 2) * (int)crank) * 64;
         for (int kb = 0; kb < it.nkb; ++kb, ++g) {
           const uint32_t s = g % S3_STAGES;
           mbar_wait_cl(&sb.empty[s], ((g / S3_STAGES) & 1) ^ 1);
           const uint32_t dst = smem_u32(smem + s * S3_STAGE_BYTES);
-          mbar_expect_tx(&sb.full[s], 3 * (S3_A_PLANE + b_bytes));
+          mbar_expect_tx(&sb.full[s], S3_STAGE_BYTES);
 #pragma unroll
           for (int j = 0; j < 3; ++j) {
             bulk_g2s(dst + j * S3_A_PLANE, a_src + ((int64_t)kb * 3 + j) * plane, S3_A_PLANE,
                      &sb.full[s]);
             bulk_g2s(dst + 3 * S3_A_PLANE + j * S3_B_PLANE,
-                     b_src + ((int64_t)kb * 3 + j) * plane, b_bytes, &sb.full[s]);
+                     b_src + ((int64_t)kb * 3 + j) * plane, S3_B_PLANE, &sb.full[s]);
           }
         }
       }
@@ -575,11 +567,11 @@ t3_syrk_kernel(const uint8_t* __restrict__ img, int Fp, int nkb_total, int D, in
   } else if (warp == 1) {
     if (crank == 0) {
       // ========================== MMA issuer (leader CTA) ==========================
+      const uint32_t idesc = make_idesc_i8(S3_TM, S3_TN);
       const uint32_t acc0 = tmem, acc1 = tmem + S3_TN, acc2 = tmem + 2 * S3_TN;
       uint32_t g = 0, itc = 0;
       for (int item = pair; item < nitems; item += npairs, ++itc) {
-        const S3Item it = s3_decode(item, ntiles, NIB, NJB, nkb_total, diag_skip);
-        const uint32_t idesc = make_idesc_i8(S3_TM, (uint32_t)it.nn);
+        const S3Item it = s3_decode(item, ntiles, NIB, NJB, nkb_total);
         mbar_wait_cl(&sb.acc_empty, (itc & 1) ^ 1);
         tc_fence_after_sync();
         for (int kb = 0; kb < it.nkb; ++kb, ++g) {
@@ -616,7 +608,7 @@ t3_syrk_kernel(const uint8_t* __restrict__ img, int Fp, int nkb_total, int D, in
       // ===================== relay (peer CTA): my stage landed =====================
       uint32_t g = 0;
       for (int item = pair; item < nitems; item += npairs) {
-        const S3Item it = s3_decode(item, ntiles, NIB, NJB, nkb_total, diag_skip);
+        const S3Item it = s3_decode(item, ntiles, NIB, NJB, nkb_total);
         for (int kb = 0; kb < it.nkb; ++kb, ++g) {
           const uint32_t s = g % S3_STAGES;
           mbar_wait_cl(&sb.full[s], (g / S3_STAGES) & 1);
@@ -630,21 +622,21 @@ t3_syrk_kernel(const uint8_t* __restrict__ img, int Fp, int nkb_total, int D, in
     const int q = warp & 3;               // TMEM lane quadrant this warp may read
     uint32_t itc = 0;
     for (int item = pair; item < nitems; item += npairs, ++itc) {
-      const S3Item it = s3_decode(item, ntiles, NIB, NJB, nkb_total, diag_skip);
+      const S3Item it = s3_decode(item, ntiles, NIB, NJB, nkb_total);
       const int fa = S3_TM * it.ib + (S3_TM / 2) * (int)crank + 32 * q + lane;
-      const int fb0 = S3_TN * it.jb + it.skip;
+      const int fb0 = S3_TN * it.jb;
       mbar_wait_cl(&sb.acc_full, itc & 1);
       tc_fence_after_sync();
       const uint32_t tacc = tmem + ((uint32_t)(32 * q) << 16);
       double* Tcol = T + fa;
 #pragma unroll 1
-      for (int c0 = 0; c0 < it.nn; c0 += 16) {
+      for (int c0 = 0; c0 < S3_TN; c0 += 16) {
         int a0[16], a1[16], a2[16];
         tmem_ld16i_nowait(tacc + (uint32_t)c0, a0);
         tmem_ld16i_nowait(tacc + (uint32_t)(S3_TN + c0), a1);
         tmem_ld16i_nowait(tacc + (uint32_t)(2 * S3_TN + c0), a2);
         tmem_ld_wait();
-        if (c0 + 16 >= it.nn) {             // all TMEM reads of this chain are done
+        if (c0 + 16 >= S3_TN) {             // all TMEM reads of this chain are done
           tc_fence_before_sync();
           __syncwarp();
           if (lane == 0) mbar_arrive_cluster(mapa_u32(smem_u32(&sb.acc_empty), 0));
@@ -779,11 +771,8 @@ static int launch_syrk(const uint8_t* img, const S3Shape& s, int nkb, double* T,
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  // (A/B switch: REVRAND_B200_T3_DIAG_SKIP=0 multiplies the whole first tile of a row panel)
-  const char* ds = getenv("REVRAND_B200_T3_DIAG_SKIP");
-  const int diag_skip = (ds != nullptr && ds[0] == '0') ? 0 : 1;
   RR_CUDA_CHECK(cudaLaunchKernelEx(&cfg, t3_syrk_kernel, img, s.Fp, nkb, s.D, s.NIB, s.NJB,
-                                   s.ntiles, nitems, T, s.ldT, diag_skip));
+                                   s.ntiles, nitems, T, s.ldT));
   RR_LAUNCH_CHECK("t3_syrk_kernel");
   return RR_OK;
 }
