@@ -1046,3 +1046,31 @@ def test_config5_large_K_ragged_vs_oracle():
     assert abs(dv - ref["dvar"]) <= 1e-4 * abs(ref["dvar"])
     np.testing.assert_allclose(np.ravel(dr), np.ravel(ref["dreg"]), rtol=1e-4)
     assert relerr(np.ravel(dl), np.ravel(ref["dhyp"][0])) < 5e-3
+
+
+@pytest.mark.gpu
+def test_kept_features_with_supertile_order_vs_oracle():
+    """K = 2600 frequencies: 5376 padded feature columns -- still within the kept-image
+    limit (6144), but the fp16 image of C (58 MB) is past the size up to which the
+    gradient GEMM visits tiles with the feature block fastest, so the ONE launch over the
+    kept image runs in supertile order with a ragged last supertile (65 row blocks)."""
+    N, d, K = 16411, 8, 2600
+    X, y = _synthetic(N, d, seed=29)
+    ls = 2.0
+    rbf = bf.RandomRBF(nbases=K, Xdim=d, random_state=9, lenscale=Parameter(ls, Positive()),
+                       regularizer=Parameter(1.3, Positive()))
+    old = config.ENGINE
+    config.ENGINE = "tcgen05"
+    try:
+        slm = rr.StandardLinearModel(basis=rbf)
+        slm.obj_ = -np.inf
+        nelbo, (dv, dr, dl) = slm._elbo(X, y, 0.05, 1.3, ls)
+        assert slm._cached_problem._kept is not None
+    finally:
+        config.ENGINE = old
+    blocks = [dict(kind="trig", W=rbf.W, lenscale=np.array([ls]), cols=None)]
+    ref = orc.slm_elbo_chunked(X, y, 0.05, [1.3], blocks, chunk=4096)
+    assert abs(nelbo - ref["neg_elbo"]) <= 1e-4 * abs(ref["neg_elbo"])
+    assert relerr(slm.weights_, ref["m"]) < 1e-4
+    assert abs(dv - ref["dvar"]) <= 1e-4 * abs(ref["dvar"])
+    assert relerr(np.ravel(dl), np.ravel(ref["dhyp"][0])) < 5e-3
